@@ -1,0 +1,183 @@
+/* suchtree_b200 -- C ABI of the B200-native patristic-distance path.
+ *
+ * Drop-in boundary for the ONE hot path of ryneches/SuchTree:
+ * batched MRCA / patristic distance, the all-pairs distance matrix, the
+ * linked-tree pair enumeration + sampler and pearson().  The reference has no
+ * FFI layer of its own -- the seam is the `def` -> `cdef` call inside
+ * SuchTree/MuchTree.pyx -- so every entry point below cites the reference
+ * `cdef`/`def` it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - plain C types only; opaque handles; every function returns an st_status
+ *     (0 = ST_OK) and st_last_error() gives a thread-local message.
+ *   - a tree handle is immutable after st_tree_create(): any number of host
+ *     threads may query it concurrently.
+ *   - node ids are the reference's ids: in-order ranks of the binarised tree
+ *     (MuchTree.pyx:171-180), leaves even, internal nodes odd.
+ *   - "host" entry points take host pointers (pageable or pinned) and do the
+ *     H2D/D2H copies themselves; "_device" entry points take device pointers on
+ *     the tree's device and a cudaStream_t (as void*), and never synchronise.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point
+ *     fails with ST_ERR_CUDA.
+ */
+#ifndef SUCHTREE_B200_H
+#define SUCHTREE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ST_API __attribute__((visibility("default")))
+#else
+#define ST_API
+#endif
+
+typedef enum st_status {
+    ST_OK = 0,
+    ST_ERR_INVALID_ARG = 1,   /* NULL pointer, negative size, bad dtype ...            */
+    ST_ERR_CUDA = 2,          /* CUDA runtime / driver error, or no device             */
+    ST_ERR_NOT_BINARY = 3,    /* a node with exactly one child, or child/parent mismatch */
+    ST_ERR_NOT_INORDER = 4,   /* ids are not in-order ranks (MuchTree.pyx:171-180)     */
+    ST_ERR_NODE_RANGE = 5,    /* a queried id is outside [0, n_nodes): see st_bad_node */
+    ST_ERR_LENGTH_MISMATCH = 6,
+    ST_ERR_NOMEM = 7
+} st_status;
+
+typedef struct st_tree st_tree; /* device-resident index of one tree on one GPU */
+
+typedef struct st_tree_info {
+    int64_t n_nodes;      /* SuchTree.size        MuchTree.pyx:236-240 */
+    int64_t n_leaves;     /* SuchTree.num_leaves  MuchTree.pyx:247-251 */
+    int32_t root;         /* SuchTree.root_node   MuchTree.pyx:265-269 */
+    int32_t depth;        /* SuchTree.depth: max #nodes on a leaf->root path, MuchTree.pyx:218-225 */
+    int32_t device;       /* CUDA device ordinal the index lives on */
+    int32_t block_shift;  /* log2(ids per RMQ block)        */
+    int32_t micro_shift;  /* log2(ids per RMQ micro block)  */
+    int32_t n_blocks;     /* RMQ blocks (block table lives in shared memory) */
+    int64_t index_bytes;  /* device bytes held by the index */
+    int32_t query_smem_bytes;
+    int32_t sm_count;
+} st_tree_info;
+
+/* thread-local text of the last error raised on this thread ("" if none) */
+ST_API const char *st_last_error(void);
+ST_API int st_version(void);
+ST_API int st_device_count(int *count);
+
+/* ---- tree: replaces `cdef struct Node` + SuchTree.__init__'s fill/depth passes
+ *      (MuchTree.pyx:55-60, 160, 182-225) and __dealloc__ (:230-232).
+ * parent/left/right/edge_len are HOST arrays of n_nodes entries in the
+ * reference's Node layout split by field; the root has parent -1 (its edge_len
+ * is ignored: the reference stores the -1 sentinel there), leaves have left ==
+ * right == -1; edge_len is fp32 exactly as the reference quantises it, epsilon
+ * substitution (MuchTree.pyx:136,188-194) already applied by the caller.
+ * The structure is validated on the host (strictly binary, ids are in-order
+ * ranks); depth, root distance (double-double) and the range-minimum index are
+ * then built by kernels on `device`.
+ * block_shift / micro_shift = 0 pick the defaults (tests force small blocks to
+ * cover every query path on small trees). */
+ST_API int st_tree_create(int device, int64_t n_nodes, const int32_t *parent, const int32_t *left,
+                   const int32_t *right, const float *edge_len, int block_shift, int micro_shift,
+                   st_tree **out);
+ST_API void st_tree_destroy(st_tree *tree);
+ST_API int st_tree_get_info(const st_tree *tree, st_tree_info *info);
+/* copies the device-built per-node arrays back (any pointer may be NULL):
+ * node depth (root = 0) and root distance as a double-double (hi + lo). */
+ST_API int st_tree_export(const st_tree *tree, int32_t *depth, double *rd_hi, double *rd_lo);
+
+/* after ST_ERR_NODE_RANGE: the id SuchTree.distances_bulk would report in its
+ * InvalidNodeError (max id if it is >= size, else min id; MuchTree.pyx:897-903) */
+ST_API int64_t st_bad_node(void);
+
+/* ---- batched distances, host buffers: replaces SuchTree._distances
+ *      (MuchTree.pyx:911-943) as called from distances_bulk (:872-909).
+ * pairs: int64 [n,2] with element strides (stride0, stride1) -- the reference's
+ * `long[:,:]` memoryview accepts any strides; out: double [n]. */
+ST_API int st_distances(const st_tree *tree, const int64_t *pairs, int64_t stride0, int64_t stride1,
+                 int64_t n, double *out);
+
+/* ---- batched MRCA, host buffers: replaces SuchTree._mrca (MuchTree.pyx:999-1030)
+ *      as called from common_ancestor (:1128-1149); out: int32 [n]. */
+ST_API int st_mrca(const st_tree *tree, const int64_t *pairs, int64_t stride0, int64_t stride1, int64_t n,
+            int32_t *out);
+
+/* ---- device-resident variant (the throughput path): d_pairs is a device array
+ * of n (a,b) pairs, contiguous, of int32 (idx_bits = 32) or int64 (idx_bits =
+ * 64); d_out double[n] and/or d_mrca int32[n] may be NULL.  Asynchronous on
+ * `stream`.  Out-of-range ids produce NaN / -1 and are reported by the next
+ * st_check_range(). */
+ST_API int st_distances_device(const st_tree *tree, const void *d_pairs, int idx_bits, int64_t n,
+                        double *d_out, int32_t *d_mrca, void *stream);
+/* synchronises `stream`, returns ST_ERR_NODE_RANGE if any launch since the last
+ * check saw an out-of-range id (st_bad_node() then reports it), and resets. */
+ST_API int st_check_range(const st_tree *tree, void *stream);
+
+/* deterministic synthetic input: n random leaf-id pairs (ids 2*k, k uniform in
+ * [0, n_leaves)), Philox4x32-10 keyed by `seed`, counter = first_pair + i, as
+ * int32 (idx_bits = 32) or int64 pairs on the device. */
+ST_API int st_random_leaf_pairs_device(const st_tree *tree, uint64_t seed, int64_t first_pair, int64_t n,
+                                void *d_pairs, int idx_bits, void *stream);
+
+/* ---- all-pairs matrix: replaces SuchTree.pairwise_distances (MuchTree.pyx:1082-1124).
+ * ids: HOST int64[n] node ids (NULL = all leaves in ascending id, the
+ * reference's default, :1097-1099); writes rows [row_begin,row_end) of the
+ * symmetric n x n fp64 matrix, row-major, to `out` (row_end-row_begin rows of n).
+ * out_on_device != 0: `out` is a device pointer on the tree's device and the
+ * call is asynchronous on `stream`; else `out` is a host pointer. */
+ST_API int st_distance_matrix(const st_tree *tree, const int64_t *ids, int64_t n, int64_t row_begin,
+                       int64_t row_end, double *out, int out_on_device, void *stream);
+
+/* ---- linked trees: replaces the body of SuchLinkedTrees.linked_distances
+ *      (MuchTree.pyx:2900-2934).  linklist: HOST int64 [n_links,2] rows
+ * [TreeB leaf id, TreeA leaf id] (:2869-2870).  For k enumerating (i, j<i) in
+ * the reference's order (:2919-2925): ids_a[k] = (ll[j,1], ll[i,1]),
+ * ids_b[k] = (ll[j,0], ll[i,0]); out_a[k] / out_b[k] the distances in tree_a /
+ * tree_b.  ids_a / ids_b may be NULL.  Both trees must be on the same device. */
+ST_API int st_linked_distances(const st_tree *tree_a, const st_tree *tree_b, const int64_t *linklist,
+                        int64_t n_links, double *out_a, double *out_b, int64_t *ids_a,
+                        int64_t *ids_b);
+
+/* ---- sampler, exact reference stream: one cycle of
+ *      SuchLinkedTrees.sample_linked_distances (MuchTree.pyx:3024-3052):
+ * buckets x n sampled link pairs drawn with the reference's xorshift64* stream
+ * (:2936-2949) starting from *seed (updated on return as the reference's
+ * self.seed would be), distances in both trees written to out_a/out_b
+ * [buckets*n] (HOST), per-bucket sums of d and d^2 ADDED to sums_a/sumsq_a/
+ * sums_b/sumsq_b [buckets] (HOST). */
+ST_API int st_sample_linked_cycle(const st_tree *tree_a, const st_tree *tree_b, const int64_t *linklist,
+                           int64_t n_links, uint64_t *seed, int32_t buckets, int32_t n,
+                           double *out_a, double *out_b, double *sums_a, double *sumsq_a,
+                           double *sums_b, double *sumsq_b);
+
+/* ---- sampler, throughput path: n_samples link pairs (with replacement) drawn
+ * by Philox4x32-10 (key = seed, counter = first_sample + i); nothing is
+ * materialised.  moments[8] (HOST) receives
+ *   { n, sum x, sum y, sum (x-x0)^2.. } -- see st_moments below.           */
+typedef struct st_moments {
+    double n;
+    double x0, y0;        /* shift used for conditioning (first sample)   */
+    double sx, sy;        /* sum (x - x0), sum (y - y0)                    */
+    double sxx, syy, sxy; /* sum (x-x0)^2, sum (y-y0)^2, sum (x-x0)(y-y0)  */
+} st_moments;
+ST_API int st_sample_moments(const st_tree *tree_a, const st_tree *tree_b, const int64_t *linklist,
+                      int64_t n_links, uint64_t seed, int64_t first_sample, int64_t n_samples,
+                      double x0, double y0, st_moments *out);
+/* Pearson r from (possibly all-reduced) moments: sxy / sqrt(sxx*syy + 1e-20),
+ * the reference's formula (MuchTree.pyx:79) on centred sums. */
+ST_API double st_moments_pearson(const st_moments *m);
+
+/* ---- pearson(): replaces _pearson (MuchTree.pyx:62-79); x, y HOST double[n]. */
+ST_API int st_pearson(int device, const double *x, const double *y, int64_t n, double *r);
+
+/* ---- measurement helper: random 32-byte-sector gather bandwidth over a
+ * `bytes`-sized device buffer (the L2-gather roofline of SURVEY.md §8d). */
+ST_API int st_bench_gather(int device, int64_t bytes, int64_t loads_per_thread, int iters,
+                    double *sectors_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUCHTREE_B200_H */

@@ -1,0 +1,197 @@
+// Device-side building blocks: double-double arithmetic, packed (depth,id) keys,
+// the range-minimum MRCA lookup, Philox4x32-10, cache-hinted loads/stores.
+#pragma once
+
+#include "st_internal.cuh"
+
+// ---------------------------------------------------------------- keys ------
+// MRCA(a,b) = the node of minimum depth among ids [min(a,b), max(a,b)]
+// (ids are in-order ranks, MuchTree.pyx:171-180; the minimum is unique).
+// A key packs (depth << 32 | id) so that an unsigned 64-bit min is an argmin.
+__device__ __forceinline__ uint64_t st_key(int32_t depth, int32_t id) {
+    return (uint64_t(uint32_t(depth)) << 32) | uint32_t(id);
+}
+__device__ __forceinline__ int32_t st_key_id(uint64_t k) { return int32_t(uint32_t(k)); }
+__device__ __forceinline__ uint64_t st_min64(uint64_t a, uint64_t b) { return a < b ? a : b; }
+
+// ------------------------------------------------------- double-double ------
+// Root distances are kept as unevaluated sums hi + lo so that
+// rd[a] + rd[b] - 2 rd[mrca] does not lose the short edges (the reference's
+// 2.2e-16 polytomy epsilon, MuchTree.pyx:136) against O(1) root distances.
+// Explicit _rn intrinsics: no FMA contraction, no reassociation.
+struct dd {
+    double hi, lo;
+};
+__device__ __forceinline__ dd dd_two_sum(double a, double b) {
+    double s = __dadd_rn(a, b);
+    double bb = __dsub_rn(s, a);
+    double e = __dadd_rn(__dsub_rn(a, __dsub_rn(s, bb)), __dsub_rn(b, bb));
+    return dd{s, e};
+}
+__device__ __forceinline__ dd dd_fast_two_sum(double a, double b) {  // |a| >= |b|
+    double s = __dadd_rn(a, b);
+    double e = __dsub_rn(b, __dsub_rn(s, a));
+    return dd{s, e};
+}
+__device__ __forceinline__ dd dd_add(dd x, dd y) {  // accurate (IEEE-style) variant
+    dd s = dd_two_sum(x.hi, y.hi);
+    dd t = dd_two_sum(x.lo, y.lo);
+    s.lo = __dadd_rn(s.lo, t.hi);
+    s = dd_fast_two_sum(s.hi, s.lo);
+    s.lo = __dadd_rn(s.lo, t.lo);
+    return dd_fast_two_sum(s.hi, s.lo);
+}
+// d = rd[a] + rd[b] - 2 rd[m], rounded once to fp64
+__device__ __forceinline__ double st_patristic(dd ra, dd rb, dd rm) {
+    dd s = dd_add(ra, rb);
+    dd m2{-2.0 * rm.hi, -2.0 * rm.lo};  // exact scaling
+    dd r = dd_add(s, m2);
+    return r.hi;  // normalised: hi = fl(hi + lo)
+}
+// one-add variant for pre-combined operands (matrix writer): fl(x + y)
+__device__ __forceinline__ double dd_add_to_double(dd x, dd y) {
+    dd s = dd_two_sum(x.hi, y.hi);
+    double lo = __dadd_rn(__dadd_rn(x.lo, y.lo), s.lo);
+    return __dadd_rn(s.hi, lo);
+}
+
+// ------------------------------------------------------ cache-hinted I/O ----
+// pair streams and results are touched once: keep them out of L1 and mark them
+// evict-first in L2 so the index (rec[] etc.) stays resident.
+__device__ __forceinline__ uint64_t st_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ int4 st_ld_stream_int4(const void *p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(st_policy_evict_first()));
+    return r;
+}
+__device__ __forceinline__ void st_st_stream_f64x2(double *p, double a, double b) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(p),
+                 "d"(a), "d"(b), "l"(st_policy_evict_first())
+                 : "memory");
+}
+__device__ __forceinline__ void st_st_stream_f64(double *p, double a) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(a),
+                 "l"(st_policy_evict_first())
+                 : "memory");
+}
+__device__ __forceinline__ void st_st_stream_i32x2(int32_t *p, int32_t a, int32_t b) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.s32 [%0], {%1,%2}, %3;" ::"l"(p),
+                 "r"(a), "r"(b), "l"(st_policy_evict_first())
+                 : "memory");
+}
+__device__ __forceinline__ void st_st_stream_i32(int32_t *p, int32_t a) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(a),
+                 "l"(st_policy_evict_first())
+                 : "memory");
+}
+// one 32-byte node record = one sector, fetched with ONE 256-bit load
+// (ld.global.v4.b64, sm_100+), marked evict-last so the index outlives the streams in L2
+struct RecRaw {
+    double rd_hi, rd_lo;
+    uint64_t suf, pre;
+};
+__device__ __forceinline__ RecRaw st_ld_rec(const NodeRec *p) {
+    RecRaw r;
+    uint64_t a, b;
+    asm volatile("ld.global.nc.L2::evict_last.v4.b64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(a), "=l"(b), "=l"(r.suf), "=l"(r.pre)
+                 : "l"(p));
+    r.rd_hi = __longlong_as_double((long long)a);
+    r.rd_lo = __longlong_as_double((long long)b);
+    return r;
+}
+__device__ __forceinline__ dd st_ld_rd(const NodeRec *p) {
+    double2 a = __ldg(reinterpret_cast<const double2 *>(p));
+    return dd{a.x, a.y};
+}
+
+// ------------------------------------------------------------- RMQ ----------
+// Shared-memory copy of the block-level tables (<= ~60 KB): blockmin keys and
+// the sparse table of argmin block indices.
+struct SmemTables {
+    const uint64_t *blockmin;
+    const uint16_t *st;  // [levels][n_blocks]
+};
+
+__device__ __forceinline__ uint64_t st_scan_depth(const int32_t *__restrict__ depth, int32_t s,
+                                                  int32_t e) {
+    uint64_t best = ~0ull;
+    for (int32_t i = s; i <= e; ++i) best = st_min64(best, st_key(__ldg(depth + i), i));
+    return best;
+}
+
+// slow path: lo and hi in the same block -> micro blocks + per-level micro table.
+// Kept out of line (it is rare for far-apart pairs) and fed scalars only, so
+// the fast path holds no stack frame.
+static __device__ __noinline__ uint64_t st_rmq_inblock(const int32_t *__restrict__ depth,
+                                                       const uint64_t *__restrict__ mst,
+                                                       int32_t n_micro, int ms, int32_t lo,
+                                                       int32_t hi) {
+    int32_t mlo = lo >> ms, mhi = hi >> ms;
+    if (mlo == mhi) return st_scan_depth(depth, lo, hi);
+    uint64_t best = st_min64(st_scan_depth(depth, lo, ((mlo + 1) << ms) - 1),
+                             st_scan_depth(depth, mhi << ms, hi));
+    int32_t span = mhi - mlo - 1;
+    if (span > 0) {
+        int k = 31 - __clz(span);
+        const uint64_t *lvl = mst + size_t(k) * n_micro;
+        best = st_min64(best, st_min64(__ldg(lvl + mlo + 1), __ldg(lvl + mhi - (1 << k))));
+    }
+    return best;
+}
+
+// key of the MRCA given both endpoint records (already loaded)
+__device__ __forceinline__ uint64_t st_rmq(const TreeView &tv, const SmemTables &sm, int32_t lo,
+                                           int32_t hi, uint64_t suf_lo, uint64_t pre_hi) {
+    int32_t blo = lo >> tv.block_shift, bhi = hi >> tv.block_shift;
+    if (blo == bhi) return st_rmq_inblock(tv.depth, tv.mst, tv.n_micro, tv.micro_shift, lo, hi);
+    uint64_t best = st_min64(suf_lo, pre_hi);
+    int32_t span = bhi - blo - 1;
+    if (span > 0) {
+        int k = 31 - __clz(span);
+        const uint16_t *lvl = sm.st + k * tv.n_blocks;
+        uint32_t i1 = lvl[blo + 1], i2 = lvl[bhi - (1 << k)];
+        best = st_min64(best, st_min64(sm.blockmin[i1], sm.blockmin[i2]));
+    }
+    return best;
+}
+
+// cooperative copy of the block tables into dynamic shared memory
+__device__ __forceinline__ SmemTables st_load_tables(const TreeView &tv, unsigned char *smem) {
+    uint64_t *bm = reinterpret_cast<uint64_t *>(smem);
+    uint16_t *st = reinterpret_cast<uint16_t *>(bm + tv.n_blocks);
+    for (int i = threadIdx.x; i < tv.n_blocks; i += blockDim.x) bm[i] = tv.blockmin[i];
+    int tot = tv.st_levels * tv.n_blocks;
+    for (int i = threadIdx.x; i < tot; i += blockDim.x) st[i] = tv.st[i];
+    __syncthreads();
+    return SmemTables{bm, st};
+}
+
+// ------------------------------------------------------------ Philox --------
+// Philox4x32-10 (Salmon et al. 2011), counter-based: the i-th draw depends on
+// (key, i) only, so any sharding of the sample stream gives the same numbers.
+struct Philox4 {
+    uint32_t x, y, z, w;
+};
+__device__ __forceinline__ Philox4 st_philox4x32_10(uint64_t counter, uint64_t key) {
+    uint32_t c0 = uint32_t(counter), c1 = uint32_t(counter >> 32), c2 = 0u, c3 = 0u;
+    uint32_t k0 = uint32_t(key), k1 = uint32_t(key >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+// unbiased-enough map of a 32-bit draw to [0, n): floor(u * n / 2^32)
+__device__ __forceinline__ uint32_t st_bounded(uint32_t u, uint32_t n) { return __umulhi(u, n); }

@@ -1,0 +1,553 @@
+// Tree handle: host-side validation of the reference's Node arrays, then the
+// device-side build of everything the query kernels read.
+//
+// Replaces `cdef struct Node` / `Node* data` (MuchTree.pyx:55-60, 114, 160) and
+// the depth pass of SuchTree.__init__ (MuchTree.pyx:218-225).
+//
+// Device layout (all buffers read-only after the build):
+//   rec[n]        32 B/node: root distance (double-double), suffix/prefix argmin
+//                 of depth within the node's RMQ block           -> 1 sector/lookup
+//   depth[n]      int32 node depth (root 0); only the same-block slow path scans it
+//   blockmin[nb]  packed (depth,id) minimum of each block          \  copied to shared
+//   st[K][nb]     uint16 sparse table over blocks (argmin block)   /  memory by queries
+//   mst[Km][nm]   packed-key sparse table over micro blocks (same-block slow path)
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cstdlib>
+#include <new>
+
+#include "st_device.cuh"
+
+// ------------------------------------------------------------ error state ---
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_bad_node = 0;
+
+void st_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void st_set_bad_node(int64_t id) { g_bad_node = id; }
+
+extern "C" const char *st_last_error(void) { return g_err; }
+extern "C" int64_t st_bad_node(void) { return g_bad_node; }
+extern "C" int st_version(void) { return 100; }
+extern "C" int st_device_count(int *count) {
+    if (!count) return ST_ERR_INVALID_ARG;
+    *count = 0;
+    ST_CUDA(cudaGetDeviceCount(count));
+    return ST_OK;
+}
+
+// ------------------------------------------------------------ build kernels -
+// Pointer jumping: after round r every node knows its 2^r-th ancestor and the
+// (depth, root-distance) contribution of the 2^r edges below it.  ceil(log2(max
+// depth))+1 rounds, each a flat pass over n nodes -- the 10^6-deep caterpillar
+// costs 21 rounds, same as a balanced tree of the same size.
+__global__ void k_jump_init(int32_t n, const int32_t *__restrict__ parent,
+                            const float *__restrict__ edge, int32_t *__restrict__ anc,
+                            int32_t *__restrict__ dep, double *__restrict__ rhi,
+                            double *__restrict__ rlo) {
+    int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    int32_t p = parent[v];
+    anc[v] = p;
+    dep[v] = p >= 0 ? 1 : 0;
+    rhi[v] = p >= 0 ? double(edge[v]) : 0.0;  // root carries the reference's -1 sentinel: not an edge
+    rlo[v] = 0.0;
+}
+
+__global__ void k_jump_round(int32_t n, const int32_t *__restrict__ anc_in,
+                             const int32_t *__restrict__ dep_in, const double *__restrict__ rhi_in,
+                             const double *__restrict__ rlo_in, int32_t *__restrict__ anc_out,
+                             int32_t *__restrict__ dep_out, double *__restrict__ rhi_out,
+                             double *__restrict__ rlo_out, int *__restrict__ live) {
+    int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    int32_t a = anc_in[v];
+    int32_t d = dep_in[v];
+    dd r{rhi_in[v], rlo_in[v]};
+    int32_t a2 = -1;
+    if (a >= 0) {
+        d += dep_in[a];
+        r = dd_add(r, dd{rhi_in[a], rlo_in[a]});
+        a2 = anc_in[a];
+        if (a2 >= 0) *live = 1;
+    }
+    anc_out[v] = a2;
+    dep_out[v] = d;
+    rhi_out[v] = r.hi;
+    rlo_out[v] = r.lo;
+}
+
+__global__ void k_max_depth(int32_t n, const int32_t *__restrict__ dep, int *__restrict__ out) {
+    int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    int d = v < n ? dep[v] : 0;
+    for (int o = 16; o; o >>= 1) d = max(d, __shfl_xor_sync(0xffffffffu, d, o));
+    if ((threadIdx.x & 31) == 0 && d > 0) atomicMax(out, d);
+}
+
+// One CTA per RMQ block: prefix / suffix argmin of depth inside the block, node
+// records, and the block minimum.  Thread t owns a contiguous chunk of the block.
+__global__ void k_block_records(int32_t n, int block_shift, const int32_t *__restrict__ dep,
+                                const double *__restrict__ rhi, const double *__restrict__ rlo,
+                                NodeRec *__restrict__ rec, uint64_t *__restrict__ blockmin) {
+    __shared__ uint64_t cmin[256];
+    __shared__ uint64_t cpre[256];  // min over chunks [0, t)
+    __shared__ uint64_t csuf[256];  // min over chunks (t, T)
+    const int32_t B = 1 << block_shift;
+    const int32_t base = blockIdx.x << block_shift;
+    const int T = blockDim.x;  // <= 256, divides B or equals B
+    const int32_t chunk = B / T;
+    const int32_t s = base + threadIdx.x * chunk;
+    const int32_t e = min(s + chunk, n);  // exclusive
+    uint64_t m = ~0ull;
+    for (int32_t i = s; i < e; ++i) m = st_min64(m, st_key(dep[i], i));
+    cmin[threadIdx.x] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t run = ~0ull;
+        for (int t = 0; t < T; ++t) {
+            cpre[t] = run;
+            run = st_min64(run, cmin[t]);
+        }
+        blockmin[blockIdx.x] = run;
+        run = ~0ull;
+        for (int t = T - 1; t >= 0; --t) {
+            csuf[t] = run;
+            run = st_min64(run, cmin[t]);
+        }
+    }
+    __syncthreads();
+    uint64_t run = cpre[threadIdx.x];
+    for (int32_t i = s; i < e; ++i) {
+        run = st_min64(run, st_key(dep[i], i));
+        rec[i].pre = run;
+    }
+    run = csuf[threadIdx.x];
+    for (int32_t i = e - 1; i >= s; --i) {
+        run = st_min64(run, st_key(dep[i], i));
+        rec[i].suf = run;
+        rec[i].rd_hi = rhi[i];
+        rec[i].rd_lo = rlo[i];
+    }
+}
+
+// Sparse table over <= 2048 block minima, one CTA.  st[k][i] = index of the
+// block with the smallest key among blocks [i, min(i + 2^k, nb)).
+__global__ void k_block_sparse_table(int nb, int levels, const uint64_t *__restrict__ blockmin,
+                                     uint16_t *st) {
+    extern __shared__ uint64_t bm[];
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+        bm[i] = blockmin[i];
+        st[i] = uint16_t(i);
+    }
+    __syncthreads();
+    for (int k = 1; k < levels; ++k) {
+        const uint16_t *prev = st + (k - 1) * nb;
+        uint16_t *cur = st + k * nb;
+        int half = 1 << (k - 1);
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+            uint16_t a = prev[i], b = prev[min(i + half, nb - 1)];
+            cur[i] = bm[b] < bm[a] ? b : a;
+        }
+        __syncthreads();  // global writes by this CTA are visible to it after the barrier
+    }
+}
+
+__global__ void k_micro_min(int32_t n, int micro_shift, int32_t n_micro,
+                            const int32_t *__restrict__ dep, uint64_t *__restrict__ mst0) {
+    int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_micro) return;
+    int32_t s = j << micro_shift, e = min(s + (1 << micro_shift), n);
+    uint64_t m = ~0ull;
+    for (int32_t i = s; i < e; ++i) m = st_min64(m, st_key(dep[i], i));
+    mst0[j] = m;
+}
+
+__global__ void k_micro_level(int32_t n_micro, int half, const uint64_t *__restrict__ prev,
+                              uint64_t *__restrict__ cur) {
+    int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_micro) return;
+    cur[j] = st_min64(prev[j], prev[min(j + half, n_micro - 1)]);
+}
+
+// ------------------------------------------------------------ validation ----
+// Host check that (parent,left,right) describe ONE strictly binary tree whose
+// ids are in-order ranks (the property every query relies on).  Iterative.
+static int validate_tree(int64_t n, const int32_t *parent, const int32_t *left, const int32_t *right,
+                         int32_t *root_out, int64_t *leaves_out) {
+    int32_t root = -1;
+    int64_t leaves = 0;
+    for (int64_t v = 0; v < n; ++v) {
+        int32_t p = parent[v], l = left[v], r = right[v];
+        if (p < -1 || p >= n || l < -1 || l >= n || r < -1 || r >= n) {
+            st_set_error("node %lld: parent/child index out of range", (long long)v);
+            return ST_ERR_INVALID_ARG;
+        }
+        if (p == -1) {
+            if (root != -1) {
+                st_set_error("more than one root (nodes %d and %lld)", root, (long long)v);
+                return ST_ERR_NOT_BINARY;
+            }
+            root = int32_t(v);
+        } else if (left[p] != v && right[p] != v) {
+            st_set_error("node %lld: parent %d does not list it as a child", (long long)v, p);
+            return ST_ERR_NOT_BINARY;
+        }
+        if ((l == -1) != (r == -1)) {
+            st_set_error("node %lld has exactly one child (tree must be strictly bifurcating)",
+                         (long long)v);
+            return ST_ERR_NOT_BINARY;
+        }
+        if (l == -1) {
+            ++leaves;
+        } else {
+            if (l == r || parent[l] != v || parent[r] != v) {
+                st_set_error("node %lld: children do not point back to it", (long long)v);
+                return ST_ERR_NOT_BINARY;
+            }
+        }
+    }
+    if (root == -1) {
+        st_set_error("no root (no node with parent -1)");
+        return ST_ERR_NOT_BINARY;
+    }
+    // in-order walk without recursion or a stack: Morris-free, parent pointers suffice
+    int64_t next_id = 0;
+    int32_t v = root;
+    while (left[v] != -1) v = left[v];
+    for (;;) {
+        if (v != next_id) {
+            st_set_error("ids are not in-order ranks: in-order position %lld holds node %d",
+                         (long long)next_id, v);
+            return ST_ERR_NOT_INORDER;
+        }
+        ++next_id;
+        if (right[v] != -1) {
+            v = right[v];
+            while (left[v] != -1) v = left[v];
+        } else {
+            int32_t c = v;
+            v = parent[v];
+            while (v != -1 && right[v] == c) {
+                c = v;
+                v = parent[v];
+            }
+            if (v == -1) break;
+        }
+        if (next_id > n) break;
+    }
+    if (next_id != n) {
+        st_set_error("tree is not connected: in-order walk visited %lld of %lld nodes",
+                     (long long)next_id, (long long)n);
+        return ST_ERR_NOT_BINARY;
+    }
+    *root_out = root;
+    *leaves_out = leaves;
+    return ST_OK;
+}
+
+// ------------------------------------------------------------ create --------
+// Upper bound on RMQ blocks: the block tables (8 + 2*levels bytes per block) are
+// copied to shared memory by every query CTA.  1024 blocks -> <= 28 KB.
+// SUCHTREE_B200_MAX_BLOCKS overrides (power of two, <= 4096) for experiments.
+static int st_max_blocks() {
+    int v = 1024;
+    if (const char *e = getenv("SUCHTREE_B200_MAX_BLOCKS")) {
+        int x = atoi(e);
+        if (x >= 1 && x <= 4096) v = x;
+    }
+    return v;
+}
+static const int ST_DEFAULT_MICRO_SHIFT = 5;
+
+template <typename T>
+static int dev_alloc(T **p, size_t count, int64_t *acc) {
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(p), bytes);
+    if (e != cudaSuccess) {
+        st_set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return ST_ERR_NOMEM;
+    }
+    if (acc) *acc += int64_t(bytes);
+    return ST_OK;
+}
+
+extern "C" void st_tree_destroy(st_tree *t) {
+    if (!t) return;
+    DeviceGuard g(t->device);
+    cudaFree(t->d_rec);
+    cudaFree(t->d_depth);
+    cudaFree(t->d_blockmin);
+    cudaFree(t->d_st);
+    cudaFree(t->d_mst);
+    cudaFree(t->d_status);
+    for (int i = 0; i < 3; ++i) {
+        if (t->d_stage_in[i]) cudaFree(t->d_stage_in[i]);
+        if (t->d_stage_out[i]) cudaFree(t->d_stage_out[i]);
+        if (t->d_stage_out2[i]) cudaFree(t->d_stage_out2[i]);
+        if (t->h_stage[i]) cudaFreeHost(t->h_stage[i]);
+        if (t->ev[i]) cudaEventDestroy(t->ev[i]);
+        if (t->streams[i]) cudaStreamDestroy(t->streams[i]);
+    }
+    delete t;
+}
+
+extern "C" int st_tree_create(int device, int64_t n_nodes, const int32_t *parent,
+                              const int32_t *left, const int32_t *right, const float *edge_len,
+                              int block_shift, int micro_shift, st_tree **out) {
+    if (!out) return ST_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (!parent || !left || !right || !edge_len || n_nodes < 1) {
+        st_set_error("st_tree_create: NULL array or n_nodes < 1");
+        return ST_ERR_INVALID_ARG;
+    }
+    if (n_nodes >= (int64_t(1) << 31) - 1) {
+        st_set_error("st_tree_create: n_nodes must be < 2^31-1");
+        return ST_ERR_INVALID_ARG;
+    }
+    int32_t root = -1;
+    int64_t n_leaves = 0;
+    int rc = validate_tree(n_nodes, parent, left, right, &root, &n_leaves);
+    if (rc != ST_OK) return rc;
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        st_set_error("no CUDA device available (this library has no CPU fallback)");
+        return ST_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        st_set_error("device %d out of range (%d devices)", device, ndev);
+        return ST_ERR_INVALID_ARG;
+    }
+    DeviceGuard guard(device);
+    if (!guard.ok) {
+        st_set_error("cudaSetDevice(%d) failed", device);
+        return ST_ERR_CUDA;
+    }
+
+    st_tree *t = new (std::nothrow) st_tree();
+    if (!t) return ST_ERR_NOMEM;
+    t->device = device;
+    t->n_nodes = n_nodes;
+    t->n_leaves = n_leaves;
+    t->root = root;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete t;
+        st_set_error("cudaGetDeviceProperties failed");
+        return ST_ERR_CUDA;
+    }
+    t->sm_count = prop.multiProcessorCount;
+
+    // block geometry: smallest power-of-two block (>= micro block) with <= ST_MAX_BLOCKS blocks
+    const int32_t n = int32_t(n_nodes);
+    int ms = micro_shift > 0 ? micro_shift : ST_DEFAULT_MICRO_SHIFT;
+    if (ms > 10) ms = 10;
+    int bs = block_shift > 0 ? block_shift : ms;
+    if (bs < ms) bs = ms;
+    const int max_blocks = st_max_blocks();
+    while (((int64_t(n) + (int64_t(1) << bs) - 1) >> bs) > max_blocks) ++bs;
+    t->block_shift = bs;
+    t->micro_shift = ms;
+    t->n_blocks = int32_t((int64_t(n) + (int64_t(1) << bs) - 1) >> bs);
+    t->n_micro = int32_t((int64_t(n) + (int64_t(1) << ms) - 1) >> ms);
+    // level k answers spans of [2^k, 2^(k+1)) full blocks; the longest span is n_blocks-2
+    t->st_levels = 1;
+    while ((1 << t->st_levels) <= std::max(t->n_blocks - 2, 1)) ++t->st_levels;
+    t->m_levels = std::max(bs - ms, 1);  // spans of < 2^(bs-ms) micro blocks inside one block
+
+#define ST_TRY(x)              \
+    do {                       \
+        int _rc = (x);         \
+        if (_rc != ST_OK) {    \
+            st_tree_destroy(t);\
+            return _rc;        \
+        }                      \
+    } while (0)
+#define ST_TRY_CUDA(call)                                                                 \
+    do {                                                                                  \
+        cudaError_t _e = (call);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            st_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__,\
+                         __LINE__);                                                       \
+            st_tree_destroy(t);                                                           \
+            return ST_ERR_CUDA;                                                           \
+        }                                                                                 \
+    } while (0)
+
+    ST_TRY(dev_alloc(&t->d_rec, size_t(n), &t->index_bytes));
+    ST_TRY(dev_alloc(&t->d_depth, size_t(n), &t->index_bytes));
+    ST_TRY(dev_alloc(&t->d_blockmin, size_t(t->n_blocks), &t->index_bytes));
+    ST_TRY(dev_alloc(&t->d_st, size_t(t->st_levels) * t->n_blocks, &t->index_bytes));
+    ST_TRY(dev_alloc(&t->d_mst, size_t(t->m_levels) * t->n_micro, &t->index_bytes));
+    ST_TRY(dev_alloc(&t->d_status, 1, &t->index_bytes));
+    ST_TRY_CUDA(cudaMemset(t->d_status, 0, sizeof(RangeStatus)));
+
+    // ---- temporaries for the build
+    int32_t *d_parent = nullptr, *d_anc[2] = {nullptr, nullptr}, *d_dep[2] = {nullptr, nullptr};
+    float *d_edge = nullptr;
+    double *d_rhi[2] = {nullptr, nullptr}, *d_rlo[2] = {nullptr, nullptr};
+    int *d_flag = nullptr;
+    auto free_tmp = [&]() {
+        cudaFree(d_parent);
+        cudaFree(d_edge);
+        cudaFree(d_flag);
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(d_anc[i]);
+            if (d_dep[i] != t->d_depth) cudaFree(d_dep[i]);
+            cudaFree(d_rhi[i]);
+            cudaFree(d_rlo[i]);
+        }
+    };
+#define ST_TRY2(x)             \
+    do {                       \
+        int _rc = (x);         \
+        if (_rc != ST_OK) {    \
+            free_tmp();        \
+            st_tree_destroy(t);\
+            return _rc;        \
+        }                      \
+    } while (0)
+#define ST_TRY2_CUDA(call)                                                                \
+    do {                                                                                  \
+        cudaError_t _e = (call);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            st_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__,\
+                         __LINE__);                                                       \
+            free_tmp();                                                                   \
+            st_tree_destroy(t);                                                           \
+            return ST_ERR_CUDA;                                                           \
+        }                                                                                 \
+    } while (0)
+
+    ST_TRY2(dev_alloc(&d_parent, size_t(n), nullptr));
+    ST_TRY2(dev_alloc(&d_edge, size_t(n), nullptr));
+    ST_TRY2(dev_alloc(&d_flag, 2, nullptr));
+    for (int i = 0; i < 2; ++i) {
+        ST_TRY2(dev_alloc(&d_anc[i], size_t(n), nullptr));
+        ST_TRY2(dev_alloc(&d_dep[i], size_t(n), nullptr));
+        ST_TRY2(dev_alloc(&d_rhi[i], size_t(n), nullptr));
+        ST_TRY2(dev_alloc(&d_rlo[i], size_t(n), nullptr));
+    }
+    cudaStream_t s = nullptr;  // legacy default stream: build is synchronous by design
+    ST_TRY2_CUDA(cudaMemcpy(d_parent, parent, size_t(n) * 4, cudaMemcpyHostToDevice));
+    ST_TRY2_CUDA(cudaMemcpy(d_edge, edge_len, size_t(n) * 4, cudaMemcpyHostToDevice));
+
+    const int TPB = 256;
+    const int grid = (n + TPB - 1) / TPB;
+    k_jump_init<<<grid, TPB, 0, s>>>(n, d_parent, d_edge, d_anc[0], d_dep[0], d_rhi[0], d_rlo[0]);
+    int cur = 0;
+    for (int round = 0; round < 40; ++round) {
+        ST_TRY2_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), s));
+        k_jump_round<<<grid, TPB, 0, s>>>(n, d_anc[cur], d_dep[cur], d_rhi[cur], d_rlo[cur],
+                                          d_anc[cur ^ 1], d_dep[cur ^ 1], d_rhi[cur ^ 1],
+                                          d_rlo[cur ^ 1], d_flag);
+        cur ^= 1;
+        int live = 0;
+        ST_TRY2_CUDA(cudaMemcpy(&live, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+        if (!live) break;
+    }
+    // after the loop every anc is -1 except possibly one more hop: run until quiescent
+    // (the flag is raised only when a second-level ancestor exists, so one extra
+    //  round has already folded the last hop in).
+    ST_TRY2_CUDA(cudaMemcpyAsync(t->d_depth, d_dep[cur], size_t(n) * 4, cudaMemcpyDeviceToDevice, s));
+    ST_TRY2_CUDA(cudaMemsetAsync(d_flag + 1, 0, sizeof(int), s));
+    k_max_depth<<<grid, TPB, 0, s>>>(n, t->d_depth, d_flag + 1);
+    int maxd = 0;
+    ST_TRY2_CUDA(cudaMemcpy(&maxd, d_flag + 1, sizeof(int), cudaMemcpyDeviceToHost));
+    t->depth = maxd + 1;  // reference counts nodes on the path, MuchTree.pyx:218-225
+
+    {
+        int T = std::min(256, 1 << bs);
+        k_block_records<<<t->n_blocks, T, 0, s>>>(n, bs, t->d_depth, d_rhi[cur], d_rlo[cur],
+                                                  t->d_rec, t->d_blockmin);
+        k_block_sparse_table<<<1, 1024, size_t(t->n_blocks) * 8, s>>>(t->n_blocks, t->st_levels,
+                                                                      t->d_blockmin, t->d_st);
+        int gm = (t->n_micro + TPB - 1) / TPB;
+        k_micro_min<<<gm, TPB, 0, s>>>(n, ms, t->n_micro, t->d_depth, t->d_mst);
+        for (int k = 1; k < t->m_levels; ++k)
+            k_micro_level<<<gm, TPB, 0, s>>>(t->n_micro, 1 << (k - 1),
+                                             t->d_mst + size_t(k - 1) * t->n_micro,
+                                             t->d_mst + size_t(k) * t->n_micro);
+    }
+    ST_TRY2_CUDA(cudaGetLastError());
+    ST_TRY2_CUDA(cudaDeviceSynchronize());
+    free_tmp();
+
+    t->query_smem_bytes = t->n_blocks * 8 + t->st_levels * t->n_blocks * 2;
+    t->view.rec = t->d_rec;
+    t->view.depth = t->d_depth;
+    t->view.blockmin = t->d_blockmin;
+    t->view.st = t->d_st;
+    t->view.mst = t->d_mst;
+    t->view.status = t->d_status;
+    t->view.n_nodes = n;
+    t->view.n_blocks = t->n_blocks;
+    t->view.n_micro = t->n_micro;
+    t->view.block_shift = bs;
+    t->view.micro_shift = ms;
+    t->view.st_levels = t->st_levels;
+    t->view.m_levels = t->m_levels;
+    for (int i = 0; i < 3; ++i) {
+        ST_TRY_CUDA(cudaStreamCreateWithFlags(&t->streams[i], cudaStreamNonBlocking));
+        ST_TRY_CUDA(cudaEventCreateWithFlags(&t->ev[i], cudaEventDisableTiming));
+    }
+    *out = t;
+    return ST_OK;
+}
+
+extern "C" int st_tree_get_info(const st_tree *t, st_tree_info *info) {
+    if (!t || !info) return ST_ERR_INVALID_ARG;
+    info->n_nodes = t->n_nodes;
+    info->n_leaves = t->n_leaves;
+    info->root = t->root;
+    info->depth = t->depth;
+    info->device = t->device;
+    info->block_shift = t->block_shift;
+    info->micro_shift = t->micro_shift;
+    info->n_blocks = t->n_blocks;
+    info->index_bytes = t->index_bytes;
+    info->query_smem_bytes = t->query_smem_bytes;
+    info->sm_count = t->sm_count;
+    return ST_OK;
+}
+
+__global__ void k_export_rd(int32_t n, const NodeRec *__restrict__ rec, double *__restrict__ hi,
+                            double *__restrict__ lo) {
+    int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    if (hi) hi[v] = rec[v].rd_hi;
+    if (lo) lo[v] = rec[v].rd_lo;
+}
+
+extern "C" int st_tree_export(const st_tree *t, int32_t *depth, double *rd_hi, double *rd_lo) {
+    if (!t) return ST_ERR_INVALID_ARG;
+    DeviceGuard g(t->device);
+    const int32_t n = int32_t(t->n_nodes);
+    if (depth) ST_CUDA(cudaMemcpy(depth, t->d_depth, size_t(n) * 4, cudaMemcpyDeviceToHost));
+    if (rd_hi || rd_lo) {
+        double *d_hi = nullptr, *d_lo = nullptr;
+        ST_CUDA(cudaMalloc(&d_hi, size_t(n) * 8));
+        if (cudaMalloc(&d_lo, size_t(n) * 8) != cudaSuccess) {
+            cudaFree(d_hi);
+            st_set_error("cudaMalloc failed in st_tree_export");
+            return ST_ERR_NOMEM;
+        }
+        k_export_rd<<<(n + 255) / 256, 256>>>(n, t->d_rec, d_hi, d_lo);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e == cudaSuccess && rd_hi) e = cudaMemcpy(rd_hi, d_hi, size_t(n) * 8, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && rd_lo) e = cudaMemcpy(rd_lo, d_lo, size_t(n) * 8, cudaMemcpyDeviceToHost);
+        cudaFree(d_hi);
+        cudaFree(d_lo);
+        if (e != cudaSuccess) {
+            st_set_error("st_tree_export: %s", cudaGetErrorString(e));
+            return ST_ERR_CUDA;
+        }
+    }
+    return ST_OK;
+}

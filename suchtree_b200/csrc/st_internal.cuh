@@ -1,0 +1,116 @@
+// Internal definitions shared by the translation units of libsuchtree_b200.so.
+// Nothing here is part of the C ABI (include/suchtree_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/suchtree_b200.h"
+
+// ---------------------------------------------------------------- errors ----
+void st_set_error(const char *fmt, ...);
+void st_set_bad_node(int64_t id);
+
+#define ST_CUDA(call)                                                                      \
+    do {                                                                                   \
+        cudaError_t _e = (call);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            st_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, \
+                         __LINE__);                                                        \
+            return ST_ERR_CUDA;                                                            \
+        }                                                                                  \
+    } while (0)
+
+// RAII device switch (the library never leaves the caller's current device changed)
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        ok = (prev == dev) || (cudaSetDevice(dev) == cudaSuccess);
+        if (prev == dev) prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ------------------------------------------------------------ device data ---
+// One 32-byte record per node = exactly one L2 sector.  A query touches rec[a],
+// rec[b] and rec[mrca] -> three sectors.
+struct __align__(32) NodeRec {
+    double rd_hi, rd_lo;  // root distance as a double-double
+    uint64_t suf;         // (depth<<32 | id) of argmin depth over [v, end of v's block]
+    uint64_t pre;         // same over [start of v's block, v]
+};
+static_assert(sizeof(NodeRec) == 32, "NodeRec must be one sector");
+
+// range status written by query kernels (pinned-host mapped would also do; it
+// lives in device memory and is read back by st_check_range / host entry points)
+struct RangeStatus {
+    unsigned long long max_bad;  // max id >= n_nodes seen (0 = none; ids are stored +1... see kernels)
+    long long min_bad;           // min id < 0 seen (0 = none)
+};
+
+// Device-side view handed to kernels by value.
+struct TreeView {
+    const NodeRec *rec;        // [n_nodes]
+    const int32_t *depth;      // [n_nodes] node depth, root = 0
+    const uint64_t *blockmin;  // [n_blocks] packed (depth,id) min of each block
+    const uint16_t *st;        // [st_levels][n_blocks] block sparse table (argmin block index)
+    const uint64_t *mst;       // [m_levels][n_micro] micro sparse table (packed keys)
+    RangeStatus *status;
+    int32_t n_nodes;
+    int32_t n_blocks;
+    int32_t n_micro;
+    int32_t block_shift;
+    int32_t micro_shift;
+    int32_t st_levels;  // levels stored, level k covers 2^k blocks, level 0 = identity (stored)
+    int32_t m_levels;
+};
+
+struct st_tree {
+    int device = 0;
+    int sm_count = 0;
+    int64_t n_nodes = 0, n_leaves = 0;
+    int32_t root = -1, depth = 0;
+    int32_t block_shift = 0, micro_shift = 0, n_blocks = 0, n_micro = 0, st_levels = 0, m_levels = 0;
+    int64_t index_bytes = 0;
+    // device allocations
+    NodeRec *d_rec = nullptr;
+    int32_t *d_depth = nullptr;
+    uint64_t *d_blockmin = nullptr;
+    uint16_t *d_st = nullptr;
+    uint64_t *d_mst = nullptr;
+    RangeStatus *d_status = nullptr;
+    int32_t *d_leaf_ids = nullptr;  // lazily unused; leaves are the even ids
+    TreeView view{};
+    int query_smem_bytes = 0;
+
+    // host-path scratch: streams + device/pinned staging, guarded by a mutex so
+    // concurrent host calls serialise on the staging buffers only
+    mutable std::mutex host_mu;
+    mutable cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+    mutable void *d_stage_in[3] = {nullptr, nullptr, nullptr};
+    mutable void *d_stage_out[3] = {nullptr, nullptr, nullptr};
+    mutable void *d_stage_out2[3] = {nullptr, nullptr, nullptr};
+    mutable void *h_stage[3] = {nullptr, nullptr, nullptr};
+    mutable int64_t stage_pairs = 0;
+    mutable cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+};
+
+// ------------------------------------------------------- internal launches --
+// query kernels (st_query.cu)
+int st_launch_pairs(const st_tree *t, const void *d_pairs, int idx_bits, int64_t n, double *d_out,
+                    int32_t *d_mrca, cudaStream_t stream);
+int st_read_range_status(const st_tree *t, cudaStream_t stream, bool *bad);
+
+static inline int st_ceil_log2_i64(int64_t x) {
+    int k = 0;
+    while ((int64_t(1) << k) < x) ++k;
+    return k;
+}

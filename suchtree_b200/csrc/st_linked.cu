@@ -1,0 +1,460 @@
+// Linked-tree paths: exhaustive link-pair distances, the bucketed sampler with the
+// reference's exact xorshift64* stream, and the Philox sampler with fused moments.
+//
+// Replaces SuchLinkedTrees.linked_distances (MuchTree.pyx:2900-2934),
+// _random_int (:2936-2949) and the sampling loop of sample_linked_distances
+// (:3023-3052).  Link pairs are generated ON the device from the link list: the
+// (size,2) int64 id arrays the reference materialises are only written when the
+// caller asks for them.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "st_device.cuh"
+
+static const int LT = 256;
+
+// one full pair query (fast path tables in shared memory)
+__device__ __forceinline__ double linked_query(const TreeView &tv, const SmemTables &sm, int32_t a,
+                                               int32_t b) {
+    int32_t lo = min(a, b), hi = max(a, b);
+    if (lo == hi) return 0.0;
+    RecRaw l = st_ld_rec(tv.rec + lo), h = st_ld_rec(tv.rec + hi);
+    uint64_t key = st_rmq(tv, sm, lo, hi, l.suf, h.pre);
+    return st_patristic(dd{l.rd_hi, l.rd_lo}, dd{h.rd_hi, h.rd_lo}, st_ld_rd(tv.rec + st_key_id(key)));
+}
+
+// k = i(i-1)/2 + j, 0 <= j < i   (the reference's loop order, MuchTree.pyx:2919-2925)
+__device__ __forceinline__ void tri_unrank(int64_t k, int64_t &i, int64_t &j) {
+    int64_t r = (int64_t)((1.0 + sqrt(1.0 + 8.0 * (double)k)) * 0.5);
+    while (r * (r - 1) / 2 > k) --r;
+    while ((r + 1) * r / 2 <= k) ++r;
+    i = r;
+    j = k - r * (r - 1) / 2;
+}
+
+// ids of one tree for link pairs [k0, k0+m): out[k-k0] = dist(col[j], col[i])
+__global__ void __launch_bounds__(LT)
+k_linked(const TreeView tv, const int32_t *__restrict__ col, int64_t k0, int64_t m,
+         double *__restrict__ out, int64_t *__restrict__ ids_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SmemTables sm = st_load_tables(tv, smem_raw);
+    for (int64_t q = int64_t(blockIdx.x) * LT + threadIdx.x; q < m; q += int64_t(gridDim.x) * LT) {
+        int64_t i, j;
+        tri_unrank(k0 + q, i, j);
+        int32_t a = __ldg(col + j), b = __ldg(col + i);
+        st_st_stream_f64(out + q, linked_query(tv, sm, a, b));
+        if (ids_out) {
+            ids_out[2 * q] = a;
+            ids_out[2 * q + 1] = b;
+        }
+    }
+}
+
+// ------------------------------------------------------------ link upload ---
+struct DevLinks {
+    int32_t *col_a = nullptr, *col_b = nullptr;  // linklist[:,1] (TreeA ids), linklist[:,0] (TreeB ids)
+    int2 *rows = nullptr;                        // (b, a) per link, for the samplers
+    ~DevLinks() {
+        cudaFree(col_a);
+        cudaFree(col_b);
+        cudaFree(rows);
+    }
+};
+
+static int upload_links(const st_tree *ta, const st_tree *tb, const int64_t *linklist, int64_t L,
+                        DevLinks &d) {
+    std::vector<int32_t> a(L), b(L);
+    std::vector<int2> rows(L);
+    for (int64_t i = 0; i < L; ++i) {
+        int64_t vb = linklist[2 * i], va = linklist[2 * i + 1];
+        if (va < 0 || va >= ta->n_nodes) {
+            st_set_bad_node(va);
+            st_set_error("linklist row %lld: TreeA id %lld out of bounds", (long long)i, (long long)va);
+            return ST_ERR_NODE_RANGE;
+        }
+        if (vb < 0 || vb >= tb->n_nodes) {
+            st_set_bad_node(vb);
+            st_set_error("linklist row %lld: TreeB id %lld out of bounds", (long long)i, (long long)vb);
+            return ST_ERR_NODE_RANGE;
+        }
+        a[i] = int32_t(va);
+        b[i] = int32_t(vb);
+        rows[i] = make_int2(int32_t(vb), int32_t(va));
+    }
+    ST_CUDA(cudaMalloc(&d.col_a, size_t(L) * 4));
+    ST_CUDA(cudaMalloc(&d.col_b, size_t(L) * 4));
+    ST_CUDA(cudaMalloc(&d.rows, size_t(L) * 8));
+    ST_CUDA(cudaMemcpy(d.col_a, a.data(), size_t(L) * 4, cudaMemcpyHostToDevice));
+    ST_CUDA(cudaMemcpy(d.col_b, b.data(), size_t(L) * 4, cudaMemcpyHostToDevice));
+    ST_CUDA(cudaMemcpy(d.rows, rows.data(), size_t(L) * 8, cudaMemcpyHostToDevice));
+    return ST_OK;
+}
+
+static int check_pair_of_trees(const st_tree *ta, const st_tree *tb, const int64_t *linklist, int64_t L) {
+    if (!ta || !tb || !linklist || L < 0) {
+        st_set_error("linked: NULL tree / linklist or negative n_links");
+        return ST_ERR_INVALID_ARG;
+    }
+    if (ta->device != tb->device) {
+        st_set_error("linked: both trees must live on the same device (%d vs %d)", ta->device, tb->device);
+        return ST_ERR_INVALID_ARG;
+    }
+    return ST_OK;
+}
+
+template <typename K>
+static int set_smem(K kern, int bytes) {
+    if (bytes > 48 * 1024)
+        ST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    return ST_OK;
+}
+
+// ------------------------------------------------------ linked_distances ----
+extern "C" int st_linked_distances(const st_tree *ta, const st_tree *tb, const int64_t *linklist,
+                                   int64_t L, double *out_a, double *out_b, int64_t *ids_a,
+                                   int64_t *ids_b) {
+    int rc = check_pair_of_trees(ta, tb, linklist, L);
+    if (rc != ST_OK) return rc;
+    const int64_t total = L * (L - 1) / 2;
+    if (total <= 0) return ST_OK;
+    if (!out_a || !out_b) {
+        st_set_error("st_linked_distances: NULL output");
+        return ST_ERR_INVALID_ARG;
+    }
+    DeviceGuard g(ta->device);
+    DevLinks dl;
+    rc = upload_links(ta, tb, linklist, L, dl);
+    if (rc != ST_OK) return rc;
+    rc = set_smem(k_linked, std::max(ta->query_smem_bytes, tb->query_smem_bytes));
+    if (rc != ST_OK) return rc;
+
+    const int64_t C = std::min<int64_t>(total, int64_t(1) << 22);
+    double *d_out[2] = {nullptr, nullptr};
+    int64_t *d_ids[2] = {nullptr, nullptr};
+    cudaStream_t st[2] = {ta->streams[0], ta->streams[1]};
+    std::lock_guard<std::mutex> lock(ta->host_mu);
+    auto cleanup = [&]() {
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(d_out[i]);
+            cudaFree(d_ids[i]);
+        }
+    };
+    for (int i = 0; i < 2; ++i) {
+        if (cudaMalloc(&d_out[i], size_t(C) * 8) != cudaSuccess ||
+            ((ids_a || ids_b) && cudaMalloc(&d_ids[i], size_t(C) * 16) != cudaSuccess)) {
+            cleanup();
+            st_set_error("st_linked_distances: cudaMalloc failed");
+            return ST_ERR_NOMEM;
+        }
+    }
+    int slot = 0;
+    for (int tree = 0; tree < 2; ++tree) {
+        const st_tree *t = tree ? tb : ta;
+        const int32_t *col = tree ? dl.col_b : dl.col_a;
+        double *out = tree ? out_b : out_a;
+        int64_t *ids = tree ? ids_b : ids_a;
+        for (int64_t k0 = 0; k0 < total; k0 += C, slot ^= 1) {
+            const int64_t m = std::min(C, total - k0);
+            int grid = int(std::min<int64_t>((m + LT - 1) / LT, int64_t(t->sm_count) * 8));
+            k_linked<<<grid, LT, t->query_smem_bytes, st[slot]>>>(t->view, col, k0, m, d_out[slot],
+                                                                  ids ? d_ids[slot] : nullptr);
+            cudaMemcpyAsync(out + k0, d_out[slot], size_t(m) * 8, cudaMemcpyDeviceToHost, st[slot]);
+            if (ids)
+                cudaMemcpyAsync(ids + 2 * k0, d_ids[slot], size_t(m) * 16, cudaMemcpyDeviceToHost, st[slot]);
+        }
+    }
+    cudaError_t e0 = cudaStreamSynchronize(st[0]), e1 = cudaStreamSynchronize(st[1]);
+    cudaError_t e2 = cudaGetLastError();
+    cleanup();
+    if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess) {
+        st_set_error("st_linked_distances: %s",
+                     cudaGetErrorString(e0 != cudaSuccess ? e0 : (e1 != cudaSuccess ? e1 : e2)));
+        return ST_ERR_CUDA;
+    }
+    return ST_OK;
+}
+
+// ------------------------------------------- xorshift64*: exact jump-ahead --
+// The reference draws link indices from ONE sequential xorshift64* state
+// (MuchTree.pyx:2946-2949).  The state update s ^= s>>12; s ^= s<<25; s ^= s>>27
+// is linear over GF(2): s' = T s.  With the 64x64 bit matrices T^(2^k) a thread
+// jumps straight to the state before ITS draws, so the device reproduces the
+// reference's stream bit for bit, in parallel.
+static const int XS_LEVELS = 48;
+struct XsJump {
+    uint64_t col[XS_LEVELS][64];  // col[k][b] = T^(2^k) applied to the unit vector e_b
+};
+static XsJump g_xs;
+static bool g_xs_ready = false;
+static std::mutex g_xs_mu;
+
+static inline uint64_t xs_step(uint64_t s) {
+    s ^= s >> 12;
+    s ^= s << 25;
+    s ^= s >> 27;
+    return s;
+}
+static inline uint64_t xs_apply(const uint64_t *col, uint64_t s) {
+    uint64_t r = 0;
+    for (int b = 0; b < 64; ++b)
+        if ((s >> b) & 1) r ^= col[b];
+    return r;
+}
+static const XsJump &xs_table() {
+    std::lock_guard<std::mutex> lock(g_xs_mu);
+    if (!g_xs_ready) {
+        for (int b = 0; b < 64; ++b) g_xs.col[0][b] = xs_step(uint64_t(1) << b);
+        for (int k = 1; k < XS_LEVELS; ++k)
+            for (int b = 0; b < 64; ++b) g_xs.col[k][b] = xs_apply(g_xs.col[k - 1], g_xs.col[k - 1][b]);
+        g_xs_ready = true;
+    }
+    return g_xs;
+}
+static uint64_t xs_jump_host(uint64_t s, uint64_t steps) {
+    const XsJump &J = xs_table();
+    for (int k = 0; k < XS_LEVELS && steps; ++k, steps >>= 1)
+        if (steps & 1) s = xs_apply(J.col[k], s);
+    return s;
+}
+
+__device__ __forceinline__ uint64_t xs_apply_dev(const uint64_t *__restrict__ col, uint64_t s) {
+    uint64_t r = 0;
+#pragma unroll 8
+    for (int b = 0; b < 64; ++b) r ^= ((s >> b) & 1) ? __ldg(col + b) : 0ull;
+    return r;
+}
+
+static const int XS_RUN = 8;  // consecutive samples per thread after one jump
+
+// One pass over the cycle's samples for ONE tree.  which = 1: TreeA (linklist[:,1]),
+// which = 0: TreeB (linklist[:,0]).  Sample q consumes draws 2q, 2q+1 of the stream.
+__global__ void __launch_bounds__(LT)
+k_sample_xs(const TreeView tv, const int2 *__restrict__ links, uint64_t n_links, int which,
+            uint64_t seed, const uint64_t *__restrict__ jump, int64_t total, int32_t n_per_bucket,
+            double *__restrict__ out, double *__restrict__ sums, double *__restrict__ sumsq) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SmemTables sm = st_load_tables(tv, smem_raw);
+    const int64_t runs = (total + XS_RUN - 1) / XS_RUN;
+    for (int64_t r = int64_t(blockIdx.x) * LT + threadIdx.x; r < runs; r += int64_t(gridDim.x) * LT) {
+        const int64_t q0 = r * XS_RUN;
+        uint64_t s = seed, steps = 2ull * uint64_t(q0);
+        for (int k = 0; steps; ++k, steps >>= 1)
+            if (steps & 1) s = xs_apply_dev(jump + k * 64, s);
+        double acc = 0.0, acc2 = 0.0;
+        int64_t cur_bucket = q0 / n_per_bucket;
+        for (int u = 0; u < XS_RUN && q0 + u < total; ++u) {
+            s ^= s >> 12; s ^= s << 25; s ^= s >> 27;
+            int l1 = int((s * 2685821657736338717ull) % n_links);  // `cdef int l1` (MuchTree.pyx:3009)
+            s ^= s >> 12; s ^= s << 25; s ^= s >> 27;
+            int l2 = int((s * 2685821657736338717ull) % n_links);
+            int2 r1 = __ldg(links + l1), r2 = __ldg(links + l2);
+            double d = which ? linked_query(tv, sm, r1.y, r2.y) : linked_query(tv, sm, r1.x, r2.x);
+            out[q0 + u] = d;
+            int64_t bkt = (q0 + u) / n_per_bucket;
+            if (bkt != cur_bucket) {
+                atomicAdd(sums + cur_bucket, acc);
+                atomicAdd(sumsq + cur_bucket, acc2);
+                acc = acc2 = 0.0;
+                cur_bucket = bkt;
+            }
+            acc += d;
+            acc2 += d * d;
+        }
+        atomicAdd(sums + cur_bucket, acc);
+        atomicAdd(sumsq + cur_bucket, acc2);
+    }
+}
+
+extern "C" int st_sample_linked_cycle(const st_tree *ta, const st_tree *tb, const int64_t *linklist,
+                                      int64_t L, uint64_t *seed, int32_t buckets, int32_t n,
+                                      double *out_a, double *out_b, double *sums_a, double *sumsq_a,
+                                      double *sums_b, double *sumsq_b) {
+    int rc = check_pair_of_trees(ta, tb, linklist, L);
+    if (rc != ST_OK) return rc;
+    if (!seed || buckets < 1 || n < 1 || L < 1 || !out_a || !out_b || !sums_a || !sumsq_a || !sums_b ||
+        !sumsq_b) {
+        st_set_error("st_sample_linked_cycle: bad arguments");
+        return ST_ERR_INVALID_ARG;
+    }
+    DeviceGuard g(ta->device);
+    DevLinks dl;
+    rc = upload_links(ta, tb, linklist, L, dl);
+    if (rc != ST_OK) return rc;
+    rc = set_smem(k_sample_xs, std::max(ta->query_smem_bytes, tb->query_smem_bytes));
+    if (rc != ST_OK) return rc;
+    const int64_t total = int64_t(buckets) * n;
+    const XsJump &J = xs_table();
+    uint64_t *d_jump = nullptr;
+    double *d_out = nullptr, *d_stats = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_jump);
+        cudaFree(d_out);
+        cudaFree(d_stats);
+    };
+    if (cudaMalloc(&d_jump, sizeof(J.col)) != cudaSuccess ||
+        cudaMalloc(&d_out, size_t(total) * 8 * 2) != cudaSuccess ||
+        cudaMalloc(&d_stats, size_t(buckets) * 8 * 4) != cudaSuccess) {
+        cleanup();
+        st_set_error("st_sample_linked_cycle: cudaMalloc failed");
+        return ST_ERR_NOMEM;
+    }
+    std::lock_guard<std::mutex> lock(ta->host_mu);
+    cudaStream_t s = ta->streams[0];
+    cudaMemcpyAsync(d_jump, J.col, sizeof(J.col), cudaMemcpyHostToDevice, s);
+    cudaMemsetAsync(d_stats, 0, size_t(buckets) * 8 * 4, s);
+    const int64_t runs = (total + XS_RUN - 1) / XS_RUN;
+    for (int tree = 0; tree < 2; ++tree) {
+        const st_tree *t = tree ? tb : ta;
+        int grid = int(std::min<int64_t>((runs + LT - 1) / LT, int64_t(t->sm_count) * 8));
+        k_sample_xs<<<grid, LT, t->query_smem_bytes, s>>>(
+            t->view, dl.rows, uint64_t(L), tree ? 0 : 1, *seed, d_jump, total, n, d_out + tree * total,
+            d_stats + (tree ? 2 : 0) * buckets, d_stats + (tree ? 3 : 1) * buckets);
+    }
+    std::vector<double> stats(size_t(buckets) * 4);
+    cudaMemcpyAsync(out_a, d_out, size_t(total) * 8, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(out_b, d_out + total, size_t(total) * 8, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(stats.data(), d_stats, stats.size() * 8, cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cleanup();
+    if (e != cudaSuccess) {
+        st_set_error("st_sample_linked_cycle: %s", cudaGetErrorString(e));
+        return ST_ERR_CUDA;
+    }
+    for (int i = 0; i < buckets; ++i) {
+        sums_a[i] += stats[i];
+        sumsq_a[i] += stats[buckets + i];
+        sums_b[i] += stats[2 * buckets + i];
+        sumsq_b[i] += stats[3 * buckets + i];
+    }
+    *seed = xs_jump_host(*seed, 2ull * uint64_t(total));
+    return ST_OK;
+}
+
+// ------------------------------------------------ Philox sampler + moments --
+// Throughput path for the sampled two-tree correlation: nothing is
+// materialised.  Per sample: 2 link rows + 2 x (3 index sectors); moments are
+// kept in registers, reduced by warp shuffles, one partial per CTA.
+struct Mom5 {
+    double sx, sy, sxx, syy, sxy;
+};
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(LT)
+k_sample_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ links,
+                 uint32_t n_links, uint64_t seed, int64_t first, int64_t n, double x0, double y0,
+                 double *__restrict__ partials /* [grid][5] */) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // two table sets back to back (second one 16-byte aligned)
+    const SmemTables sa = st_load_tables(ta, smem_raw);
+    const int offs = ((ta.n_blocks * 8 + ta.st_levels * ta.n_blocks * 2) + 15) & ~15;
+    const SmemTables sb = st_load_tables(tb, smem_raw + offs);
+    __shared__ double red[5][LT / 32];
+
+    Mom5 m{0, 0, 0, 0, 0};
+    // samples are processed two at a time: one Philox call = 4 words = 2 samples
+    const int64_t c_begin = first >> 1, c_end = (first + n + 1) >> 1;
+    for (int64_t c = c_begin + int64_t(blockIdx.x) * LT + threadIdx.x; c < c_end;
+         c += int64_t(gridDim.x) * LT) {
+        Philox4 r = st_philox4x32_10(uint64_t(c), seed);
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t s = 2 * c + h;
+            if (s < first || s >= first + n) continue;
+            int2 l1 = __ldg(links + st_bounded(w[2 * h], n_links));
+            int2 l2 = __ldg(links + st_bounded(w[2 * h + 1], n_links));
+            double x = linked_query(ta, sa, l1.y, l2.y) - x0;
+            double y = linked_query(tb, sb, l1.x, l2.x) - y0;
+            m.sx += x; m.sy += y;
+            m.sxx += x * x; m.syy += y * y; m.sxy += x * y;
+        }
+    }
+    double v[5] = {m.sx, m.sy, m.sxx, m.syy, m.sxy};
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        double s = warp_sum(v[k]);
+        if (lane == 0) red[k][wid] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double s = 0;
+        for (int w2 = 0; w2 < LT / 32; ++w2) s += red[threadIdx.x][w2];
+        partials[size_t(blockIdx.x) * 5 + threadIdx.x] = s;
+    }
+}
+
+__global__ void k_reduce_partials(int grid, const double *__restrict__ partials, double *__restrict__ out) {
+    // one warp per moment, fixed order -> deterministic
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (k >= 5) return;
+    double s = 0;
+    for (int i = lane; i < grid; i += 32) s += partials[size_t(i) * 5 + k];
+    s = warp_sum(s);
+    if (lane == 0) out[k] = s;
+}
+
+extern "C" int st_sample_moments(const st_tree *ta, const st_tree *tb, const int64_t *linklist,
+                                 int64_t L, uint64_t seed, int64_t first_sample, int64_t n_samples,
+                                 double x0, double y0, st_moments *out) {
+    int rc = check_pair_of_trees(ta, tb, linklist, L);
+    if (rc != ST_OK) return rc;
+    if (!out || L < 1 || L >= (int64_t(1) << 32) || n_samples < 0 || first_sample < 0) {
+        st_set_error("st_sample_moments: bad arguments");
+        return ST_ERR_INVALID_ARG;
+    }
+    out->n = double(n_samples);
+    out->x0 = x0;
+    out->y0 = y0;
+    out->sx = out->sy = out->sxx = out->syy = out->sxy = 0.0;
+    if (n_samples == 0) return ST_OK;
+    DeviceGuard g(ta->device);
+    DevLinks dl;
+    rc = upload_links(ta, tb, linklist, L, dl);
+    if (rc != ST_OK) return rc;
+    const int smem = ((ta->query_smem_bytes + 15) & ~15) + tb->query_smem_bytes;
+    rc = set_smem(k_sample_moments, smem);
+    if (rc != ST_OK) return rc;
+    int per_sm = 0;
+    ST_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sample_moments, LT, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t calls = (n_samples + 1) / 2 + 1;
+    int grid = int(std::min<int64_t>((calls + LT - 1) / LT, int64_t(ta->sm_count) * per_sm));
+    double *d_part = nullptr, *d_out = nullptr;
+    ST_CUDA(cudaMalloc(&d_part, size_t(grid) * 5 * 8));
+    if (cudaMalloc(&d_out, 5 * 8) != cudaSuccess) {
+        cudaFree(d_part);
+        return ST_ERR_NOMEM;
+    }
+    cudaStream_t s = ta->streams[0];
+    k_sample_moments<<<grid, LT, smem, s>>>(ta->view, tb->view, dl.rows, uint32_t(L), seed, first_sample,
+                                           n_samples, x0, y0, d_part);
+    k_reduce_partials<<<1, 160, 0, s>>>(grid, d_part, d_out);
+    double h[5];
+    cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(d_part);
+    cudaFree(d_out);
+    if (e != cudaSuccess) {
+        st_set_error("st_sample_moments: %s", cudaGetErrorString(e));
+        return ST_ERR_CUDA;
+    }
+    out->sx = h[0]; out->sy = h[1]; out->sxx = h[2]; out->syy = h[3]; out->sxy = h[4];
+    return ST_OK;
+}
+
+extern "C" double st_moments_pearson(const st_moments *m) {
+    if (!m || m->n <= 0) return 0.0;
+    // centred second moments from shifted sums; the shift cancels exactly in exact arithmetic
+    const double n = m->n;
+    const double cxx = m->sxx - m->sx * m->sx / n;
+    const double cyy = m->syy - m->sy * m->sy / n;
+    const double cxy = m->sxy - m->sx * m->sy / n;
+    return cxy / std::sqrt(cxx * cyy + 1.0e-20);  // guard of MuchTree.pyx:79
+}

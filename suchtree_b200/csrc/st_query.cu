@@ -1,0 +1,353 @@
+// Batched (a,b) -> (MRCA, patristic distance) queries.
+//
+// Replaces SuchTree._mrca (MuchTree.pyx:999-1030) and SuchTree._distances
+// (MuchTree.pyx:911-943): instead of recording a's ancestor chain and scanning it
+// for every ancestor of b (O(depth^2) pointer chasing per pair), the MRCA is the
+// argmin of depth over the id interval [min(a,b), max(a,b)] (ids are in-order
+// ranks), answered in O(1) from
+//     rec[lo].suf, rec[hi].pre            one 32-B sector each (they also carry rd)
+//     two block-table entries             shared memory
+// and the distance is rd[a] + rd[b] - 2 rd[mrca] in double-double
+//     rec[mrca].rd                        one more sector.
+// => 3 random L2 sectors + 16 B (int32x2 in, fp64 out) of streamed HBM per pair.
+#include <algorithm>
+#include <cmath>
+
+#include "st_device.cuh"
+
+static const int QT = 512;  // threads per CTA
+
+template <typename IdxT>
+struct PairIO;
+
+template <>
+struct PairIO<int32_t> {
+    // two pairs per 16-byte load
+    static __device__ __forceinline__ void load2(const int32_t *p, int64_t pair_idx, long long &a0,
+                                                 long long &b0, long long &a1, long long &b1) {
+        int4 v = st_ld_stream_int4(p + 2 * pair_idx);
+        a0 = v.x; b0 = v.y; a1 = v.z; b1 = v.w;
+    }
+    static __device__ __forceinline__ void load1(const int32_t *p, int64_t pair_idx, long long &a,
+                                                 long long &b) {
+        a = __ldg(p + 2 * pair_idx);
+        b = __ldg(p + 2 * pair_idx + 1);
+    }
+    static constexpr int kAlign = 16;
+};
+template <>
+struct PairIO<int64_t> {
+    static __device__ __forceinline__ void load2(const int64_t *p, int64_t pair_idx, long long &a0,
+                                                 long long &b0, long long &a1, long long &b1) {
+        int4 v = st_ld_stream_int4(p + 2 * pair_idx);
+        int4 w = st_ld_stream_int4(p + 2 * pair_idx + 2);
+        a0 = (long long)(uint32_t(v.x) | (uint64_t(uint32_t(v.y)) << 32));
+        b0 = (long long)(uint32_t(v.z) | (uint64_t(uint32_t(v.w)) << 32));
+        a1 = (long long)(uint32_t(w.x) | (uint64_t(uint32_t(w.y)) << 32));
+        b1 = (long long)(uint32_t(w.z) | (uint64_t(uint32_t(w.w)) << 32));
+    }
+    static __device__ __forceinline__ void load1(const int64_t *p, int64_t pair_idx, long long &a,
+                                                 long long &b) {
+        a = __ldg(reinterpret_cast<const long long *>(p) + 2 * pair_idx);
+        b = __ldg(reinterpret_cast<const long long *>(p) + 2 * pair_idx + 1);
+    }
+    static constexpr int kAlign = 16;
+};
+
+struct PairQ {
+    int32_t lo, hi;
+    bool bad;
+};
+
+// range check as SuchTree.distances_bulk does before the kernel (MuchTree.pyx:897-903),
+// moved onto the device so the host never makes a pass over the pair array.
+__device__ __forceinline__ PairQ st_make_query(const TreeView &tv, long long a, long long b) {
+    PairQ q;
+    const long long n = tv.n_nodes;
+    q.bad = (unsigned long long)a >= (unsigned long long)n || (unsigned long long)b >= (unsigned long long)n;
+    if (q.bad) {
+        long long mx = a > b ? a : b, mn = a < b ? a : b;
+        if (mx >= n) atomicMax(&tv.status->max_bad, (unsigned long long)mx);
+        if (mn < 0) atomicMin(&tv.status->min_bad, mn);
+        a = b = 0;
+    }
+    int32_t x = int32_t(a), y = int32_t(b);
+    q.lo = min(x, y);
+    q.hi = max(x, y);
+    return q;
+}
+
+__device__ __forceinline__ uint64_t st_query_key(const TreeView &tv, const SmemTables &sm,
+                                                 const PairQ &q, const RecRaw &rl,
+                                                 const RecRaw &rh) {
+    if (q.lo == q.hi) return uint64_t(uint32_t(q.lo));  // MRCA(a,a) = a
+    return st_rmq(tv, sm, q.lo, q.hi, rl.suf, rh.pre);
+}
+
+template <typename IdxT, bool VEC>
+__global__ void __launch_bounds__(QT, 2)
+k_pairs(const TreeView tv, const IdxT *__restrict__ pairs, int64_t n, double *__restrict__ out,
+        int32_t *__restrict__ mrca_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SmemTables sm = st_load_tables(tv, smem_raw);
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+
+    if (VEC) {
+        const int64_t n2 = n >> 1;  // pair-of-pairs
+        for (int64_t i = int64_t(blockIdx.x) * QT + threadIdx.x; i < n2; i += int64_t(gridDim.x) * QT) {
+            long long a0, b0, a1, b1;
+            PairIO<IdxT>::load2(pairs, 2 * i, a0, b0, a1, b1);
+            PairQ q0 = st_make_query(tv, a0, b0), q1 = st_make_query(tv, a1, b1);
+            RecRaw l0 = st_ld_rec(tv.rec + q0.lo), h0 = st_ld_rec(tv.rec + q0.hi);
+            RecRaw l1 = st_ld_rec(tv.rec + q1.lo), h1 = st_ld_rec(tv.rec + q1.hi);
+            int32_t m0 = st_key_id(st_query_key(tv, sm, q0, l0, h0));
+            int32_t m1 = st_key_id(st_query_key(tv, sm, q1, l1, h1));
+            if (out) {
+                dd r0 = st_ld_rd(tv.rec + m0), r1 = st_ld_rd(tv.rec + m1);
+                double d0 = st_patristic(dd{l0.rd_hi, l0.rd_lo}, dd{h0.rd_hi, h0.rd_lo}, r0);
+                double d1 = st_patristic(dd{l1.rd_hi, l1.rd_lo}, dd{h1.rd_hi, h1.rd_lo}, r1);
+                st_st_stream_f64x2(out + 2 * i, q0.bad ? nan : d0, q1.bad ? nan : d1);
+            }
+            if (mrca_out) st_st_stream_i32x2(mrca_out + 2 * i, q0.bad ? -1 : m0, q1.bad ? -1 : m1);
+        }
+        if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+            long long a, b;
+            PairIO<IdxT>::load1(pairs, n - 1, a, b);
+            PairQ q = st_make_query(tv, a, b);
+            RecRaw l = st_ld_rec(tv.rec + q.lo), h = st_ld_rec(tv.rec + q.hi);
+            int32_t m = st_key_id(st_query_key(tv, sm, q, l, h));
+            if (out) {
+                double d = st_patristic(dd{l.rd_hi, l.rd_lo}, dd{h.rd_hi, h.rd_lo}, st_ld_rd(tv.rec + m));
+                out[n - 1] = q.bad ? nan : d;
+            }
+            if (mrca_out) mrca_out[n - 1] = q.bad ? -1 : m;
+        }
+    } else {
+        for (int64_t i = int64_t(blockIdx.x) * QT + threadIdx.x; i < n; i += int64_t(gridDim.x) * QT) {
+            long long a, b;
+            PairIO<IdxT>::load1(pairs, i, a, b);
+            PairQ q = st_make_query(tv, a, b);
+            RecRaw l = st_ld_rec(tv.rec + q.lo), h = st_ld_rec(tv.rec + q.hi);
+            int32_t m = st_key_id(st_query_key(tv, sm, q, l, h));
+            if (out) {
+                double d = st_patristic(dd{l.rd_hi, l.rd_lo}, dd{h.rd_hi, h.rd_lo}, st_ld_rd(tv.rec + m));
+                st_st_stream_f64(out + i, q.bad ? nan : d);
+            }
+            if (mrca_out) st_st_stream_i32(mrca_out + i, q.bad ? -1 : m);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ launch --
+template <typename IdxT, bool VEC>
+static int launch_variant(const st_tree *t, const void *d_pairs, int64_t n, double *d_out,
+                          int32_t *d_mrca, cudaStream_t stream) {
+    auto kern = k_pairs<IdxT, VEC>;
+    static thread_local int configured_smem[64] = {0};  // per device, per thread: cheap re-check
+    const int smem = t->query_smem_bytes;
+    if (smem > 48 * 1024 && configured_smem[t->device & 63] < smem) {
+        ST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured_smem[t->device & 63] = smem;
+    }
+    int per_sm = 0;
+    ST_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, QT, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t items = VEC ? std::max<int64_t>(n >> 1, 1) : n;
+    int64_t want = (items + QT - 1) / QT;
+    int grid = int(std::min<int64_t>(want, int64_t(t->sm_count) * per_sm));
+    if (grid < 1) grid = 1;
+    kern<<<grid, QT, smem, stream>>>(t->view, static_cast<const IdxT *>(d_pairs), n, d_out, d_mrca);
+    ST_CUDA(cudaGetLastError());
+    return ST_OK;
+}
+
+int st_launch_pairs(const st_tree *t, const void *d_pairs, int idx_bits, int64_t n, double *d_out,
+                    int32_t *d_mrca, cudaStream_t stream) {
+    if (n == 0) return ST_OK;
+    const bool aligned = (reinterpret_cast<uintptr_t>(d_pairs) % 16 == 0) &&
+                         (!d_out || reinterpret_cast<uintptr_t>(d_out) % 16 == 0) &&
+                         (!d_mrca || reinterpret_cast<uintptr_t>(d_mrca) % 8 == 0);
+    if (idx_bits == 32)
+        return aligned ? launch_variant<int32_t, true>(t, d_pairs, n, d_out, d_mrca, stream)
+                       : launch_variant<int32_t, false>(t, d_pairs, n, d_out, d_mrca, stream);
+    if (idx_bits == 64)
+        return aligned ? launch_variant<int64_t, true>(t, d_pairs, n, d_out, d_mrca, stream)
+                       : launch_variant<int64_t, false>(t, d_pairs, n, d_out, d_mrca, stream);
+    st_set_error("idx_bits must be 32 or 64 (got %d)", idx_bits);
+    return ST_ERR_INVALID_ARG;
+}
+
+int st_read_range_status(const st_tree *t, cudaStream_t stream, bool *bad) {
+    RangeStatus h{};
+    ST_CUDA(cudaMemcpyAsync(&h, t->d_status, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    ST_CUDA(cudaStreamSynchronize(stream));
+    *bad = false;
+    if (h.max_bad != 0 || h.min_bad != 0) {
+        *bad = true;
+        // the reference reports max_id when it is >= size, else min_id (MuchTree.pyx:899-903)
+        st_set_bad_node(h.max_bad != 0 ? (int64_t)h.max_bad : (int64_t)h.min_bad);
+        ST_CUDA(cudaMemsetAsync(t->d_status, 0, sizeof(RangeStatus), stream));
+        ST_CUDA(cudaStreamSynchronize(stream));
+        st_set_error("node id %lld out of bounds (tree size %lld)", (long long)st_bad_node(),
+                     (long long)t->n_nodes);
+    }
+    return ST_OK;
+}
+
+// ------------------------------------------------------------ device API ----
+extern "C" int st_distances_device(const st_tree *t, const void *d_pairs, int idx_bits, int64_t n,
+                                   double *d_out, int32_t *d_mrca, void *stream) {
+    if (!t || n < 0 || (n > 0 && !d_pairs) || (!d_out && !d_mrca && n > 0)) {
+        st_set_error("st_distances_device: bad arguments");
+        return ST_ERR_INVALID_ARG;
+    }
+    DeviceGuard g(t->device);
+    return st_launch_pairs(t, d_pairs, idx_bits, n, d_out, d_mrca, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int st_check_range(const st_tree *t, void *stream) {
+    if (!t) return ST_ERR_INVALID_ARG;
+    DeviceGuard g(t->device);
+    bool bad = false;
+    int rc = st_read_range_status(t, static_cast<cudaStream_t>(stream), &bad);
+    if (rc != ST_OK) return rc;
+    return bad ? ST_ERR_NODE_RANGE : ST_OK;
+}
+
+// ---------------------------------------------------------- synthetic input -
+template <typename IdxT>
+__global__ void k_random_leaf_pairs(uint32_t n_leaves, uint64_t seed, int64_t first, int64_t n,
+                                    IdxT *__restrict__ pairs) {
+    // one Philox call yields two pairs
+    const int64_t n2 = (n + 1) >> 1;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n2;
+         i += int64_t(gridDim.x) * blockDim.x) {
+        // counter is the index of the pair-of-pairs in the GLOBAL stream, so a
+        // shard starting at an even `first` reproduces the same numbers
+        Philox4 r = st_philox4x32_10(uint64_t((first >> 1) + i), seed);
+        int64_t p = 2 * i;
+        pairs[2 * p] = IdxT(2 * st_bounded(r.x, n_leaves));
+        pairs[2 * p + 1] = IdxT(2 * st_bounded(r.y, n_leaves));
+        if (p + 1 < n) {
+            pairs[2 * p + 2] = IdxT(2 * st_bounded(r.z, n_leaves));
+            pairs[2 * p + 3] = IdxT(2 * st_bounded(r.w, n_leaves));
+        }
+    }
+}
+
+extern "C" int st_random_leaf_pairs_device(const st_tree *t, uint64_t seed, int64_t first_pair,
+                                           int64_t n, void *d_pairs, int idx_bits, void *stream) {
+    if (!t || n < 0 || (n > 0 && !d_pairs) || (first_pair & 1)) {
+        st_set_error("st_random_leaf_pairs_device: bad arguments (first_pair must be even)");
+        return ST_ERR_INVALID_ARG;
+    }
+    if (n == 0) return ST_OK;
+    DeviceGuard g(t->device);
+    const int TPB = 256;
+    int64_t want = ((n + 1) / 2 + TPB - 1) / TPB;
+    int grid = int(std::min<int64_t>(want, int64_t(t->sm_count) * 16));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (idx_bits == 32)
+        k_random_leaf_pairs<int32_t><<<grid, TPB, 0, s>>>(uint32_t(t->n_leaves), seed, first_pair, n,
+                                                          static_cast<int32_t *>(d_pairs));
+    else if (idx_bits == 64)
+        k_random_leaf_pairs<int64_t><<<grid, TPB, 0, s>>>(uint32_t(t->n_leaves), seed, first_pair, n,
+                                                          static_cast<int64_t *>(d_pairs));
+    else {
+        st_set_error("idx_bits must be 32 or 64");
+        return ST_ERR_INVALID_ARG;
+    }
+    ST_CUDA(cudaGetLastError());
+    return ST_OK;
+}
+
+// -------------------------------------------------------------- host API ----
+// Chunked 3-stage pipeline: H2D(chunk c+1) | kernel(chunk c) | D2H(chunk c-1) on
+// three streams.  int64 pairs are copied as they are (the kernel reads int64
+// directly: no narrowing pass on either side).  Pinned user buffers give true
+// overlap; pageable ones still work (the driver stages them).
+static const int64_t ST_STAGE_PAIRS_MAX = int64_t(1) << 22;
+
+static int ensure_stage(const st_tree *t, int64_t n, bool need_host_pack) {
+    int64_t want = 4096;
+    while (want < n && want < ST_STAGE_PAIRS_MAX) want <<= 1;
+    if (want > t->stage_pairs) {
+        for (int i = 0; i < 3; ++i) {
+            cudaFree(t->d_stage_in[i]);
+            cudaFree(t->d_stage_out[i]);
+            cudaFree(t->d_stage_out2[i]);
+            if (t->h_stage[i]) cudaFreeHost(t->h_stage[i]);
+            t->d_stage_in[i] = t->d_stage_out[i] = t->d_stage_out2[i] = t->h_stage[i] = nullptr;
+        }
+        t->stage_pairs = 0;
+        for (int i = 0; i < 3; ++i) {
+            ST_CUDA(cudaMalloc(&t->d_stage_in[i], size_t(want) * 16));
+            ST_CUDA(cudaMalloc(&t->d_stage_out[i], size_t(want) * 8));
+            ST_CUDA(cudaMalloc(&t->d_stage_out2[i], size_t(want) * 4));
+        }
+        t->stage_pairs = want;
+    }
+    if (need_host_pack) {
+        for (int i = 0; i < 3; ++i)
+            if (!t->h_stage[i]) ST_CUDA(cudaMallocHost(&t->h_stage[i], size_t(t->stage_pairs) * 16));
+    }
+    return ST_OK;
+}
+
+static int host_pairs_run(const st_tree *t, const int64_t *pairs, int64_t s0, int64_t s1, int64_t n,
+                          double *out_d, int32_t *out_m) {
+    if (!t || n < 0 || (n > 0 && (!pairs || (!out_d && !out_m)))) {
+        st_set_error("bad arguments (NULL pointer or negative n)");
+        return ST_ERR_INVALID_ARG;
+    }
+    if (n == 0) return ST_OK;
+    DeviceGuard g(t->device);
+    std::lock_guard<std::mutex> lock(t->host_mu);
+    const bool contiguous = (s1 == 1 && s0 == 2);
+    int rc = ensure_stage(t, n, !contiguous);
+    if (rc != ST_OK) return rc;
+    const int64_t C = t->stage_pairs;
+    int64_t done = 0;
+    int c = 0;
+    for (; done < n; ++c) {
+        const int s = c % 3;
+        const int64_t m = std::min(C, n - done);
+        cudaStream_t st = t->streams[s];
+        if (c >= 3) ST_CUDA(cudaEventSynchronize(t->ev[s]));  // stage buffers free again
+        const int64_t *src = pairs + done * s0;
+        if (!contiguous) {
+            int64_t *hp = static_cast<int64_t *>(t->h_stage[s]);
+            for (int64_t i = 0; i < m; ++i) {
+                hp[2 * i] = src[i * s0];
+                hp[2 * i + 1] = src[i * s0 + s1];
+            }
+            src = hp;
+        }
+        ST_CUDA(cudaMemcpyAsync(t->d_stage_in[s], src, size_t(m) * 16, cudaMemcpyHostToDevice, st));
+        double *dd_out = out_d ? static_cast<double *>(t->d_stage_out[s]) : nullptr;
+        int32_t *dm_out = out_m ? static_cast<int32_t *>(t->d_stage_out2[s]) : nullptr;
+        rc = st_launch_pairs(t, t->d_stage_in[s], 64, m, dd_out, dm_out, st);
+        if (rc != ST_OK) return rc;
+        if (out_d)
+            ST_CUDA(cudaMemcpyAsync(out_d + done, dd_out, size_t(m) * 8, cudaMemcpyDeviceToHost, st));
+        if (out_m)
+            ST_CUDA(cudaMemcpyAsync(out_m + done, dm_out, size_t(m) * 4, cudaMemcpyDeviceToHost, st));
+        ST_CUDA(cudaEventRecord(t->ev[s], st));
+        done += m;
+    }
+    for (int s = 0; s < 3 && s < c; ++s) ST_CUDA(cudaStreamSynchronize(t->streams[s]));
+    bool bad = false;
+    rc = st_read_range_status(t, t->streams[0], &bad);
+    if (rc != ST_OK) return rc;
+    return bad ? ST_ERR_NODE_RANGE : ST_OK;
+}
+
+extern "C" int st_distances(const st_tree *t, const int64_t *pairs, int64_t stride0, int64_t stride1,
+                            int64_t n, double *out) {
+    return host_pairs_run(t, pairs, stride0, stride1, n, out, nullptr);
+}
+
+extern "C" int st_mrca(const st_tree *t, const int64_t *pairs, int64_t stride0, int64_t stride1,
+                       int64_t n, int32_t *out) {
+    return host_pairs_run(t, pairs, stride0, stride1, n, nullptr, out);
+}

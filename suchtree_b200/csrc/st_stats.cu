@@ -1,0 +1,196 @@
+// pearson() on host vectors, and the L2 random-sector gather micro-benchmark that
+// supplies the gather roofline of SURVEY.md §8d.
+//
+// st_pearson replaces _pearson (MuchTree.pyx:62-79): the same two-pass formula
+// (means first, then centred sums, +1e-20 guard) with fp64 accumulators and a
+// fixed reduction tree instead of the reference's sequential fp32 accumulators.
+#include <algorithm>
+#include <cmath>
+
+#include "st_device.cuh"
+
+static const int PT = 256;
+
+__device__ __forceinline__ double wsum(double v) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int K>
+__device__ __forceinline__ void block_partials(double (&v)[K], double *__restrict__ partials) {
+    __shared__ double red[K][PT / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double s = wsum(v[k]);
+        if (lane == 0) red[k][wid] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        double s = 0;
+        for (int w = 0; w < PT / 32; ++w) s += red[threadIdx.x][w];
+        partials[size_t(blockIdx.x) * K + threadIdx.x] = s;
+    }
+}
+
+__global__ void __launch_bounds__(PT)
+k_pearson_means(int64_t n, const double *__restrict__ x, const double *__restrict__ y,
+                double *__restrict__ partials) {
+    double v[2] = {0, 0};
+    for (int64_t i = int64_t(blockIdx.x) * PT + threadIdx.x; i < n; i += int64_t(gridDim.x) * PT) {
+        v[0] += x[i];
+        v[1] += y[i];
+    }
+    block_partials<2>(v, partials);
+}
+
+__global__ void __launch_bounds__(PT)
+k_pearson_centred(int64_t n, const double *__restrict__ x, const double *__restrict__ y,
+                  const double *__restrict__ sums, double *__restrict__ partials) {
+    const double ax = sums[0] / double(n), ay = sums[1] / double(n);
+    double v[3] = {0, 0, 0};
+    for (int64_t i = int64_t(blockIdx.x) * PT + threadIdx.x; i < n; i += int64_t(gridDim.x) * PT) {
+        double xt = x[i] - ax, yt = y[i] - ay;
+        v[0] += xt * xt;
+        v[1] += yt * yt;
+        v[2] += xt * yt;
+    }
+    block_partials<3>(v, partials);
+}
+
+template <int K>
+__global__ void k_fold(int grid, const double *__restrict__ partials, double *__restrict__ out) {
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (k >= K) return;
+    double s = 0;
+    for (int i = lane; i < grid; i += 32) s += partials[size_t(i) * K + k];
+    s = wsum(s);
+    if (lane == 0) out[k] = s;
+}
+
+extern "C" int st_pearson(int device, const double *x, const double *y, int64_t n, double *r) {
+    if (!r || n < 0 || (n > 0 && (!x || !y))) {
+        st_set_error("st_pearson: bad arguments");
+        return ST_ERR_INVALID_ARG;
+    }
+    if (n == 0) {  // the reference's ZeroDivisionError branch returns 0.0 (MuchTree.pyx:86-87)
+        *r = 0.0;
+        return ST_OK;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        st_set_error("st_pearson: no CUDA device %d (no CPU fallback)", device);
+        return ST_ERR_CUDA;
+    }
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    ST_CUDA(cudaGetDeviceProperties(&prop, device));
+    int grid = int(std::min<int64_t>((n + PT - 1) / PT, int64_t(prop.multiProcessorCount) * 8));
+    double *dx = nullptr, *dy = nullptr, *dp = nullptr, *ds = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(dx);
+        cudaFree(dy);
+        cudaFree(dp);
+        cudaFree(ds);
+    };
+    if (cudaMalloc(&dx, size_t(n) * 8) != cudaSuccess || cudaMalloc(&dy, size_t(n) * 8) != cudaSuccess ||
+        cudaMalloc(&dp, size_t(grid) * 3 * 8) != cudaSuccess || cudaMalloc(&ds, 5 * 8) != cudaSuccess) {
+        cleanup();
+        st_set_error("st_pearson: cudaMalloc failed");
+        return ST_ERR_NOMEM;
+    }
+    cudaStream_t s = nullptr;
+    cudaMemcpyAsync(dx, x, size_t(n) * 8, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(dy, y, size_t(n) * 8, cudaMemcpyHostToDevice, s);
+    k_pearson_means<<<grid, PT, 0, s>>>(n, dx, dy, dp);
+    k_fold<2><<<1, 64, 0, s>>>(grid, dp, ds);
+    k_pearson_centred<<<grid, PT, 0, s>>>(n, dx, dy, ds, dp);
+    k_fold<3><<<1, 96, 0, s>>>(grid, dp, ds + 2);
+    double h[5];
+    cudaMemcpyAsync(h, ds, sizeof(h), cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cleanup();
+    if (e != cudaSuccess) {
+        st_set_error("st_pearson: %s", cudaGetErrorString(e));
+        return ST_ERR_CUDA;
+    }
+    *r = h[4] / std::sqrt(h[2] * h[3] + 1.0e-20);
+    return ST_OK;
+}
+
+// ------------------------------------------------------ gather roofline -----
+// Every thread issues `loads` independent 32-byte (one sector) loads at
+// pseudo-random sector addresses of a `bytes`-sized buffer, 4 in flight at a
+// time -- the access pattern of the pair kernel's index lookups.
+__global__ void __launch_bounds__(512)
+k_gather(const ulonglong4 *__restrict__ buf, uint64_t n_sectors, int64_t loads, uint64_t seed,
+         unsigned long long *__restrict__ sink) {
+    uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    uint64_t acc = 0;
+    for (int64_t i = 0; i < loads; i += 4) {
+        Philox4 r = st_philox4x32_10(tid * uint64_t(loads) + uint64_t(i), seed);
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+        uint64_t a[4], b[4], c[4], d[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint64_t idx = (uint64_t(w[k]) * n_sectors) >> 32;
+            asm volatile("ld.global.nc.L2::evict_last.v4.b64 {%0,%1,%2,%3}, [%4];"
+                         : "=l"(a[k]), "=l"(b[k]), "=l"(c[k]), "=l"(d[k])
+                         : "l"(buf + idx));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc ^= a[k] ^ b[k] ^ c[k] ^ d[k];
+    }
+    if (acc == 0x123456789abcdefull) *sink = acc;  // keep the loads alive
+}
+
+extern "C" int st_bench_gather(int device, int64_t bytes, int64_t loads_per_thread, int iters,
+                               double *sectors_per_s) {
+    if (!sectors_per_s || bytes < 32 || loads_per_thread < 4 || iters < 1) {
+        st_set_error("st_bench_gather: bad arguments");
+        return ST_ERR_INVALID_ARG;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        st_set_error("st_bench_gather: no CUDA device %d", device);
+        return ST_ERR_CUDA;
+    }
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    ST_CUDA(cudaGetDeviceProperties(&prop, device));
+    const uint64_t n_sectors = uint64_t(bytes) / 32;
+    void *buf = nullptr;
+    unsigned long long *sink = nullptr;
+    ST_CUDA(cudaMalloc(&buf, n_sectors * 32));
+    ST_CUDA(cudaMalloc(&sink, 8));
+    ST_CUDA(cudaMemset(buf, 1, n_sectors * 32));
+    const int grid = prop.multiProcessorCount * 4, tpb = 512;
+    loads_per_thread = (loads_per_thread + 3) / 4 * 4;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    k_gather<<<grid, tpb>>>(static_cast<const ulonglong4 *>(buf), n_sectors, loads_per_thread, 1, sink);  // warm
+    float best_ms = 1e30f;
+    for (int it = 0; it < iters; ++it) {
+        cudaEventRecord(e0);
+        k_gather<<<grid, tpb>>>(static_cast<const ulonglong4 *>(buf), n_sectors, loads_per_thread,
+                                uint64_t(it) + 2, sink);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        best_ms = std::min(best_ms, ms);
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    cudaFree(sink);
+    if (e != cudaSuccess) {
+        st_set_error("st_bench_gather: %s", cudaGetErrorString(e));
+        return ST_ERR_CUDA;
+    }
+    *sectors_per_s = double(grid) * tpb * double(loads_per_thread) / (double(best_ms) * 1e-3);
+    return ST_OK;
+}

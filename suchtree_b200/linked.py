@@ -1,0 +1,275 @@
+"""SuchLinkedTrees and pearson(): host-side mirror of the reference's co-phylogeny
+entry points on the hot path:
+
+    SuchLinkedTrees(tree_a, tree_b, link_matrix)     MuchTree.pyx:2562-2667
+    .linklist / subset_a / subset_b                  :2839-2898
+    .linked_distances()                              :2900-2934
+    .sample_linked_distances(sigma, buckets, n, maxcycles)   :2951-3079
+    pearson(x, y)                                    :81-87
+
+Link bookkeeping stays on the host (small, pandas-driven); every distance, the
+sampler's random stream and the moment reductions run in libsuchtree_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .tree import SuchTree
+
+_UINT64_MAX = np.iinfo(np.uint64).max
+
+
+def pearson(x, y, device=0):
+    """Pearson correlation of two float64 vectors; MuchTree.pyx:81-87 (two-pass
+    formula of :62-79 with fp64 accumulators on the GPU)."""
+    x = _as_f64_vector(x)
+    y = _as_f64_vector(y)
+    if not len(x) == len(y):
+        raise Exception("vectors must be the same length.", (len(x), len(y)))
+    r = C.c_double(0.0)
+    rc = _lib.lib().st_pearson(int(device), x.ctypes.data, y.ctypes.data, len(x), C.byref(r))
+    _lib.check(rc)
+    return float(r.value)
+
+
+def _as_f64_vector(v):
+    a = np.asarray(v)
+    if a.dtype != np.float64:
+        # the reference takes `double[:]` memoryviews
+        raise ValueError("Buffer dtype mismatch, expected 'double' but got '%s'" % a.dtype.name)
+    if a.ndim != 1:
+        raise ValueError("Buffer has wrong number of dimensions (expected 1, got %d)" % a.ndim)
+    return np.ascontiguousarray(a)
+
+
+class SuchLinkedTrees:
+    def __init__(self, tree_a, tree_b, link_matrix):
+        # the reference seeds its xorshift64* state in __cinit__ (MuchTree.pyx:2572-2573),
+        # i.e. before anything else happens -- same draw, same place
+        self._seed = int(np.random.randint(_UINT64_MAX >> 1))
+        self._TreeA = self._as_tree(tree_a)
+        self._TreeB = self._as_tree(tree_b)
+        TA, TB = self._TreeA, self._TreeB
+        if TA.device != TB.device:
+            raise Exception("both trees must live on the same device", (TA.device, TB.device))
+        if not link_matrix.shape == (TA.num_leaves, TB.num_leaves):
+            raise Exception("link_matrix shape must match tree leaf counts")
+        if not set(link_matrix.axes[0]) == set(TA.leaves.keys()):
+            raise Exception("axis[0] does not match TreeA leaf names")
+        if not set(link_matrix.axes[1]) == set(TB.leaves.keys()):
+            raise Exception("axis[1] does not match TreeB leaf names")
+
+        self._row_ids = np.array(list(TA.leaves.values()))
+        self._col_ids = np.array(list(TB.leaves.values()))
+        self._row_names = list(TA.leaves.keys())
+        self._col_names = list(TB.leaves.keys())
+        self._n_rows = TA.num_leaves
+        self._n_cols = TB.num_leaves
+        self._row_map = np.zeros(TA.size, dtype=np.int64)
+        self._row_map[self._row_ids] = np.arange(len(self._row_ids))
+        self._col_of_leaf = np.full(TB.size, -1, dtype=np.int64)  # stands in for link_leaf (:2639)
+        self._col_of_leaf[self._col_ids] = np.arange(len(self._col_ids))
+
+        # link table (:2633-2650): column i = TreeB leaf col_names[i]; its links are the
+        # TreeA leaf ids of the rows with value > 0, in the DataFrame's row order
+        values = link_matrix.reindex(columns=self._col_names).to_numpy()
+        row_leaf_ids = np.array([TA.leaves[name] for name in link_matrix.index], dtype=np.int64)
+        cols, rows = np.nonzero((values > 0).T)  # column-major: by column, then DataFrame row order
+        self._link_cols = cols.astype(np.int64)
+        self._link_a = row_leaf_ids[rows]
+        self._n_links = int(cols.shape[0])
+
+        # default subset = everything (:2652-2662)
+        self._subset_a_root = TA.root_node
+        self._subset_b_root = TB.root_node
+        self._subset_a_leafs = self._row_ids
+        self._subset_b_leafs = self._col_ids
+        self._subset_columns = np.arange(self._n_cols)
+        self._subset_rows = np.arange(self._n_rows)
+        self._subset_a_size = self._n_rows
+        self._subset_b_size = self._n_cols
+        self._np_linklist = np.ndarray((self._n_links, 2), dtype=np.int64)
+        self._build_linklist()
+
+    @staticmethod
+    def _as_tree(t):
+        if isinstance(t, str):
+            return SuchTree(t)
+        if type(t) == SuchTree:
+            return t
+        raise Exception("unknown input for tree", type(t))
+
+    # ---- link list (:2845-2874) ------------------------------------------
+    def _build_linklist(self):
+        """rows [TreeB leaf id, TreeA leaf id], ordered by subset column, then by the
+        link order inside the column, restricted to subset_a's leaves."""
+        in_a = np.zeros(self._TreeA.size, dtype=bool)
+        in_a[np.asarray(self._subset_a_leafs, dtype=np.int64)] = True
+        # stable selection of the links of each subset column, in subset-column order
+        order_of_col = np.full(self._n_cols, -1, dtype=np.int64)
+        sc = np.asarray(self._subset_columns, dtype=np.int64)
+        order_of_col[sc] = np.arange(sc.shape[0])
+        keep = (order_of_col[self._link_cols] >= 0) & in_a[self._link_a]
+        cols, a = self._link_cols[keep], self._link_a[keep]
+        perm = np.argsort(order_of_col[cols], kind="stable")
+        cols, a = cols[perm], a[perm]
+        k = cols.shape[0]
+        self._np_linklist[:k, 0] = self._col_ids[cols]
+        self._np_linklist[:k, 1] = a
+        self._subset_n_links = int(k)
+
+    def subset_b(self, node_id):
+        """:2876-2886"""
+        if node_id > self._TreeB.size or node_id < 0:
+            raise Exception("Node ID out of bounds.", node_id)
+        self._subset_b_leafs = self._TreeB.get_leaves(node_id)
+        self._subset_columns = self._col_of_leaf[self._subset_b_leafs]
+        self._subset_b_size = len(self._subset_columns)
+        self._subset_b_root = node_id
+        self._build_linklist()
+
+    def subset_a(self, node_id):
+        """:2888-2898"""
+        if node_id > self._TreeA.size or node_id < 0:
+            raise Exception("Node ID out of bounds.", node_id)
+        self._subset_a_leafs = self._TreeA.get_leaves(node_id)
+        self._subset_rows = self._row_map[self._subset_a_leafs]
+        self._subset_a_size = len(self._subset_rows)
+        self._subset_a_root = node_id
+        self._build_linklist()
+
+    # ---- properties (:2681-2772, :2839-2843) --------------------------------
+    TreeA = property(lambda self: self._TreeA)
+    TreeB = property(lambda self: self._TreeB)
+    n_links = property(lambda self: self._n_links)
+    n_cols = property(lambda self: self._n_cols)
+    n_rows = property(lambda self: self._n_rows)
+    col_ids = property(lambda self: self._col_ids)
+    row_ids = property(lambda self: self._row_ids)
+    col_names = property(lambda self: self._col_names)
+    row_names = property(lambda self: self._row_names)
+    subset_columns = property(lambda self: self._subset_columns)
+    subset_rows = property(lambda self: self._subset_rows)
+    subset_a_leafs = property(lambda self: self._subset_a_leafs)
+    subset_b_leafs = property(lambda self: self._subset_b_leafs)
+    subset_a_size = property(lambda self: self._subset_a_size)
+    subset_b_size = property(lambda self: self._subset_b_size)
+    subset_a_root = property(lambda self: self._subset_a_root)
+    subset_b_root = property(lambda self: self._subset_b_root)
+    subset_n_links = property(lambda self: self._subset_n_links)
+
+    @property
+    def linklist(self):
+        return self._np_linklist[: self._subset_n_links, :]
+
+    def _linklist_c(self):
+        return np.ascontiguousarray(self.linklist, dtype=np.int64)
+
+    # ---- linked_distances (:2900-2934) ---------------------------------------
+    def linked_distances(self):
+        L = self._subset_n_links
+        size = (L * (L - 1)) // 2
+        ids_a = np.ndarray((size, 2), dtype=np.int64)
+        ids_b = np.ndarray((size, 2), dtype=np.int64)
+        out_a = np.zeros(size, dtype=np.float64)
+        out_b = np.zeros(size, dtype=np.float64)
+        if size:
+            ll = self._linklist_c()
+            rc = _lib.lib().st_linked_distances(
+                self._TreeA._handle, self._TreeB._handle, ll.ctypes.data, L,
+                out_a.ctypes.data, out_b.ctypes.data, ids_a.ctypes.data, ids_b.ctypes.data)
+            _lib.check(rc)
+        return {
+            "TreeA": out_a,
+            "TreeB": out_b,
+            "ids_A": ids_a,
+            "ids_B": ids_b,
+            "n_pairs": size,
+            "n_samples": size,
+            "deviation_a": None,
+            "deviation_b": None,
+        }
+
+    # ---- sample_linked_distances (:2951-3079) --------------------------------
+    def sample_linked_distances(self, sigma=0.001, buckets=64, n=4096, maxcycles=100):
+        """Bucketed sampling with the reference's convergence rule.  Link pairs are
+        drawn with the reference's own xorshift64* stream (reproduced exactly on the
+        device by jump-ahead), so for the same numpy seed the returned distances are
+        the reference's, sample for sample."""
+        sigma = float(np.float32(sigma))  # `float sigma` argument
+        buckets, n, maxcycles = int(buckets), int(n), int(maxcycles)
+        L = self._subset_n_links
+        ll = self._linklist_c()
+        sums_a = np.zeros(buckets)
+        sums_b = np.zeros(buckets)
+        sumsq_a = np.zeros(buckets)
+        sumsq_b = np.zeros(buckets)
+        samples = 0
+        all_a, all_b = [], []
+        seed = C.c_uint64(self._seed)
+        cycles = 0
+        lib = _lib.lib()
+        while True:
+            da = np.empty(buckets * n)
+            db = np.empty(buckets * n)
+            rc = lib.st_sample_linked_cycle(
+                self._TreeA._handle, self._TreeB._handle, ll.ctypes.data, L, C.byref(seed), buckets, n,
+                da.ctypes.data, db.ctypes.data, sums_a.ctypes.data, sumsq_a.ctypes.data,
+                sums_b.ctypes.data, sumsq_b.ctypes.data)
+            self._seed = int(seed.value)
+            _lib.check(rc)
+            all_a.append(da)
+            all_b.append(db)
+            samples += n
+            with np.errstate(invalid="ignore"):
+                dev_a = (sumsq_a / samples - (sums_a / samples) ** 2) ** 0.5
+                dev_b = (sumsq_b / samples - (sums_b / samples) ** 2) ** 0.5
+            # std of the bucket stds, with the reference's fp32 scalars (:3016-3019, :3057-3067)
+            f32 = np.float32
+            deviation_a = f32(0)
+            deviation_b = f32(0)
+            ssq_a = f32(0)
+            ssq_b = f32(0)
+            for i in range(buckets):
+                deviation_a = f32(float(deviation_a) + dev_a[i])
+                deviation_b = f32(float(deviation_b) + dev_b[i])
+                ssq_a = f32(float(ssq_a) + dev_a[i] ** 2)
+                ssq_b = f32(float(ssq_b) + dev_b[i] ** 2)
+            with np.errstate(invalid="ignore"):
+                deviation_a = f32((float(ssq_a / f32(buckets)) - float(deviation_a / f32(buckets)) ** 2) ** 0.5)
+                deviation_b = f32((float(ssq_b / f32(buckets)) - float(deviation_b / f32(buckets)) ** 2) ** 0.5)
+            cycles += 1
+            if deviation_a < sigma and deviation_b < sigma:
+                break
+            if cycles >= maxcycles:
+                return None
+        return {
+            "TreeA": np.concatenate(all_a),
+            "TreeB": np.concatenate(all_b),
+            "n_pairs": (L * (L - 1)) / 2,
+            "n_samples": n * buckets * cycles,
+            "deviation_a": float(deviation_a),
+            "deviation_b": float(deviation_b),
+        }
+
+    # ---- throughput path (not in the reference API) --------------------------
+    def sample_moments(self, n_samples, seed=0, first_sample=0, x0=0.0, y0=0.0):
+        """Philox-sampled link pairs, moments fused on the device; returns the
+        _lib.Moments struct (all-reduce its sums across ranks, then moments_pearson)."""
+        ll = self._linklist_c()
+        m = _lib.Moments()
+        rc = _lib.lib().st_sample_moments(
+            self._TreeA._handle, self._TreeB._handle, ll.ctypes.data, self._subset_n_links,
+            int(seed), int(first_sample), int(n_samples), float(x0), float(y0), C.byref(m))
+        _lib.check(rc)
+        return m
+
+    def sample_pearson(self, n_samples, seed=0):
+        """Sampled two-tree Pearson r over n_samples link pairs drawn with replacement."""
+        m = self.sample_moments(n_samples, seed=seed)
+        return moments_pearson(m)
+
+
+def moments_pearson(m):
+    return float(_lib.lib().st_moments_pearson(C.byref(m)))

@@ -1,0 +1,181 @@
+"""NEWICK text -> the flat node arrays the device index is built from.
+
+Host-side replacement for the dendropy calls in SuchTree.__init__
+(MuchTree.pyx:138-157, 171, 182, 200) plus its two fill passes (:171-216).  The
+rules that DEFINE node ids are reproduced exactly, because every id a user holds
+must stay bit-identical:
+
+  * leaf labels are taxa, internal labels are support values; `[...]` comments
+    are dropped; 'quoted labels' keep their text ('' = escaped quote);
+    underscores are preserved (preserve_underscores=True, :141);
+  * polytomies are resolved as dendropy's deterministic resolve_polytomies()
+    does (:157): nodes with >2 children are collected in post-order, then the
+    first two children are repeatedly re-attached under a new zero-length node
+    appended at the END of the child list, until two remain;
+  * ids are in-order ranks of the binarised tree (:171-180) -- leaves get even
+    ids, internal nodes odd ids;
+  * a missing or zero branch length becomes the polytomy epsilon 2.22e-16
+    (:136, :188-194); lengths are stored as fp32 (:55-60); the root gets the -1
+    sentinel (:183-186); support = float(label) or -1 (:207-210).
+
+Unlike oracle/newick_ref.py (objects, used only by the tests) this flattener is
+array-based and never recurses, so a 10^6-deep caterpillar loads fine.
+"""
+import re
+
+import numpy as np
+
+from .exceptions import TreeStructureError
+
+EPSILON = float(np.finfo(np.float64).eps)
+
+_TOKENS = re.compile(r"\[[^\]]*\]|'(?:[^']|'')*'|[(),:;]|[^\s()\[\]',:;]+")
+
+
+class FlatTree:
+    """parent/left/right int32, distance/support float32, in the reference's ids."""
+
+    __slots__ = ("parent", "left", "right", "distance", "support", "leaves", "internal_nodes", "root", "size", "n_leaves")
+
+
+def _tokenize(text):
+    return _TOKENS.findall(text)
+
+
+def parse_newick(text):
+    """Returns (children lists, label list, length list) in creation order; node 0 is the root."""
+    children = [[]]
+    parent = [-1]
+    label = [None]
+    length = [None]
+    cur = 0
+    expect_len = False
+    seen = False
+    for tok in _tokenize(text):
+        c = tok[0]
+        if c == "[":
+            continue
+        seen = True
+        if len(tok) == 1 and c in "(),:;":
+            if c == "(":
+                k = len(children)
+                children.append([]); parent.append(cur); label.append(None); length.append(None)
+                children[cur].append(k)
+                cur = k
+            elif c == ",":
+                p = parent[cur]
+                if p < 0:
+                    raise TreeStructureError("NEWICK: ',' outside parentheses")
+                k = len(children)
+                children.append([]); parent.append(p); label.append(None); length.append(None)
+                children[p].append(k)
+                cur = k
+                expect_len = False
+            elif c == ")":
+                cur = parent[cur]
+                if cur < 0:
+                    raise TreeStructureError("NEWICK: unbalanced ')'")
+                expect_len = False
+            elif c == ":":
+                expect_len = True
+            else:  # ';' ends the first tree
+                break
+        elif expect_len:
+            try:
+                length[cur] = float(tok)
+            except ValueError:
+                raise TreeStructureError("NEWICK: bad branch length %r" % tok)
+            expect_len = False
+        else:
+            label[cur] = tok[1:-1].replace("''", "'") if c == "'" else tok
+    if not seen:
+        raise TreeStructureError("empty NEWICK input")
+    if cur != 0:
+        raise TreeStructureError("NEWICK: unbalanced '('")
+    return children, label, length
+
+
+def _resolve_polytomies(children, label, length):
+    # post-order collection first (dendropy collects, then edits)
+    order = []
+    stack = [(0, False)]
+    while stack:
+        v, done = stack.pop()
+        if done or not children[v]:
+            if len(children[v]) > 2:
+                order.append(v)
+        else:
+            stack.append((v, True))
+            for ch in reversed(children[v]):
+                stack.append((ch, False))
+    for v in order:
+        ch = children[v]
+        while len(ch) > 2:
+            k = len(children)
+            children.append([ch[0], ch[1]])
+            label.append(None)
+            length.append(0.0)
+            del ch[0:2]
+            ch.append(k)
+
+
+def flatten(text):
+    """NEWICK text -> FlatTree with the reference's ids and field values."""
+    children, label, length = parse_newick(text)
+    _resolve_polytomies(children, label, length)
+    n = len(children)
+    for v in range(n):
+        k = len(children[v])
+        if k == 1:
+            raise TreeStructureError(
+                "node with a single child: SuchTree requires a strictly bifurcating tree")
+        if k == 0 and label[v] is None:
+            raise TreeStructureError("leaf without a name")
+    # in-order ranks, iteratively
+    new_id = np.empty(n, np.int64)
+    order = []
+    stack = [(0, False)]
+    while stack:
+        v, emit = stack.pop()
+        ch = children[v]
+        if emit or not ch:
+            new_id[v] = len(order)
+            order.append(v)
+        else:
+            stack.append((ch[1], False))
+            stack.append((v, True))
+            stack.append((ch[0], False))
+    ft = FlatTree()
+    ft.size = n
+    ft.parent = np.full(n, -1, np.int32)
+    ft.left = np.full(n, -1, np.int32)
+    ft.right = np.full(n, -1, np.int32)
+    dist = np.empty(n, np.float64)
+    ft.support = np.full(n, -1.0, np.float32)
+    ft.leaves = {}
+    internal = []
+    ft.n_leaves = 0
+    for i, v in enumerate(order):
+        ch = children[v]
+        if ch:
+            l, r = int(new_id[ch[0]]), int(new_id[ch[1]])
+            ft.left[i], ft.right[i] = l, r
+            ft.parent[l] = i
+            ft.parent[r] = i
+            internal.append(i)
+            if label[v] is not None:
+                try:
+                    ft.support[i] = float(label[v])
+                except ValueError:
+                    pass
+        else:
+            ft.leaves[label[v]] = i
+            ft.n_leaves += 1
+        ln = length[v]
+        dist[i] = ln if ln else EPSILON  # None, 0.0 and -0.0 -> epsilon
+    ft.root = int(new_id[0])
+    dist[ft.root] = -1.0
+    with np.errstate(over="ignore"):
+        ft.distance = dist.astype(np.float32)
+    ft.internal_nodes = np.array(internal, dtype=np.int64)
+    return ft
