@@ -1,0 +1,459 @@
+#!/usr/bin/env python
+"""Benchmark of the batched patristic-distance path (BASELINE.json metric:
+patristic distance pairs/sec, cfg 2: 100k-leaf random binary tree, 1e8 random leaf
+pairs per step through distances()).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Our arm (default): one process per GPU (torchrun for N>1, rank i -> cuda:i).  The
+tree index is replicated, every rank owns its own 1e8-pair shard of the Philox
+pair stream (weak scaling, no data-path collective).  A step = ONE launch of the
+pair kernel over the rank's device-resident pairs.  `value` = pairs all ranks
+processed / max-over-ranks device time (CUDA events on the launching stream).
+`e2e` = the same metric through the drop-in call SuchTree.distances_bulk() on
+PINNED HOST int64 pairs (H2D + kernel + D2H inside the timed region).
+Rank 0 at N=1 also times the unmodified reference (oracle/_ref, its own Cython
+machine code) on a bounded sample of the same pairs -> `cpu_baseline`.
+
+Reference arm (--impl reference): the unmodified reference's distances_bulk() on
+the box's host cores (fork pool over contiguous pair blocks, the decomposition the
+reference's docs recommend), each step a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+TREE_LEAVES = 100_000
+TREE_SEED = 1
+PAIR_SEED = 2
+PAIRS_PER_STEP = 100_000_000
+METRIC = "patristic_distance_pairs_per_sec"
+UNIT = "pairs/s"
+WORKLOAD = ("cfg2: simulated 100k-leaf random binary (Yule, seed 1) tree, 1e8 random leaf-id "
+            "pairs per GPU per step via distances()")
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# --------------------------------------------------------------------------- #
+# reference (CPU) side -- the one place bench.py executes oracle/
+# --------------------------------------------------------------------------- #
+_REF_TREE = None
+_REF_PAIRS = None
+
+
+def _ref_worker(span):
+    # the pair array and the tree are inherited through fork (copy-on-write), as in
+    # the multiprocessing recipe of the reference's docs; only results travel back
+    return _REF_TREE.distances_bulk(_REF_PAIRS[span[0]:span[1]])
+
+
+class ReferenceCPU:
+    """The unmodified reference extension (oracle/_ref) on the bench tree, or the C
+    port (oracle/st_oracle.c, literal fp32 arithmetic) if the extension is absent."""
+
+    def __init__(self, flat_tree):
+        global _REF_TREE
+        sys.path.insert(0, os.path.join(REPO, "oracle"))
+        self.kind = "port"
+        mod = None
+        try:
+            import ref_loader
+
+            mod = ref_loader.load_reference(build_if_missing=os.path.exists("/root/reference"))
+        except Exception as e:  # pragma: no cover - diagnostics only
+            print("[bench] reference extension unavailable: %r" % (e,), file=sys.stderr)
+        from suchtree_b200 import synth
+
+        if mod is not None:
+            ft = flat_tree
+            if ft.leaves is None:
+                ft.leaves = {"L%d" % k: 2 * k for k in range(ft.n_leaves)}
+            nwk = synth.to_newick(ft)
+            t0 = time.time()
+            _REF_TREE = mod.SuchTree(nwk)
+            self.load_s = time.time() - t0
+            assert _REF_TREE.size == ft.size
+            self.kind = "reference"
+        else:
+            import oracle as O
+
+            ot = O.OracleTree(flat_tree.parent, flat_tree.distance)
+
+            class _Port:
+                def distances_bulk(self, pairs):
+                    return ot.distances_f32(pairs)
+
+            _REF_TREE = _Port()
+            self.load_s = 0.0
+
+    def run(self, pairs, cores):
+        """pairs/s of distances_bulk over `pairs` (int64 [n,2]) on `cores` processes."""
+        if cores <= 1:
+            t0 = time.perf_counter()
+            out = _REF_TREE.distances_bulk(pairs)
+            return pairs.shape[0] / (time.perf_counter() - t0), out
+        import multiprocessing as mp
+
+        global _REF_PAIRS
+        _REF_PAIRS = pairs
+        ctx = mp.get_context("fork")  # threads do not scale: the reference holds the GIL
+        edges = np.linspace(0, pairs.shape[0], cores * 4 + 1).astype(np.int64)
+        spans = list(zip(edges[:-1], edges[1:]))
+        with ctx.Pool(cores) as pool:
+            pool.map(_ref_worker, [(0, 1000)] * cores)  # warm the workers
+            t0 = time.perf_counter()
+            res = pool.map(_ref_worker, spans)
+            dt = time.perf_counter() - t0
+        return pairs.shape[0] / dt, np.concatenate(res)
+
+
+def sample_pairs_host(n_leaves, seed, first, n):
+    """The bench's pair stream restated on the host (same Philox stream the device
+    generator produces; suchtree_b200/philox_host.py, checked by tests/)."""
+    from suchtree_b200 import philox_host
+
+    return philox_host.random_leaf_pairs(n_leaves, seed, first, n)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from suchtree_b200 import synth
+
+    ft = synth.yule_tree(TREE_LEAVES, seed=TREE_SEED)
+    ref = ReferenceCPU(ft)
+    cores = host_cores()
+    # calibrate a bounded per-step sample: ~3 s of all-core work per step
+    probe = sample_pairs_host(TREE_LEAVES, PAIR_SEED, 0, 200_000)
+    rate1, _ = ref.run(probe, 1)
+    per_step = int(min(30_000_000, max(200_000, rate1 * cores * 0.6 * 3.0)))
+    per_step -= per_step % 2
+    pairs = sample_pairs_host(TREE_LEAVES, PAIR_SEED, 0, per_step)
+    for _ in range(max(args.warmup, 0) and 1):
+        ref.run(pairs[: per_step // 4], cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ref.run(pairs, cores)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "tree_leaves": TREE_LEAVES, "pairs_per_step": per_step,
+                   "note": "bounded sample of the 1e8-pair step; pool start-up outside the rate"},
+        "cpu_baseline": {
+            "value": value, "unit": UNIT, "cores": cores, "kind": ref.kind,
+            "sample": "%d pairs/step x %d steps of the cfg2 pair stream, fork Pool(%d) over "
+                      "contiguous blocks; single core: %.3g pairs/s" % (per_step, args.steps, cores, rate1),
+        },
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------- #
+# clocks
+# --------------------------------------------------------------------------- #
+class ClockSampler(threading.Thread):
+    def __init__(self, device_index, period=0.1):
+        super().__init__(daemon=True)
+        self.idx, self.period = device_index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.ok:
+            self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def physical_gpu_index(local):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local])
+        except Exception:
+            return local
+    return local
+
+
+# --------------------------------------------------------------------------- #
+# our arm
+# --------------------------------------------------------------------------- #
+def measured_peak():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture."""
+    p = os.path.join(REPO, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get("k_pairs_dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            print("bench.py --gpus %d must be launched with torchrun (one rank per GPU)" % args.gpus, file=sys.stderr)
+            return 2
+    from suchtree_b200 import synth
+
+    ft = synth.yule_tree(TREE_LEAVES, seed=TREE_SEED)
+    n_pairs = args.pairs
+
+    # ---- CPU baseline first (fork pool before this process touches CUDA)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ref = ReferenceCPU(ft)
+        cores = host_cores()
+        probe = sample_pairs_host(TREE_LEAVES, PAIR_SEED, 0, 200_000)
+        rate1, out1 = ref.run(probe, 1)
+        n_s = int(min(n_pairs, max(400_000, rate1 * 4.0)))  # ~4 s on one core
+        n_s -= n_s % 2
+        sample = sample_pairs_host(TREE_LEAVES, PAIR_SEED, 0, n_s)
+        rate1, ref_out = ref.run(sample, 1)
+        rate_all, _ = ref.run(sample, cores) if cores > 1 else (rate1, None)
+        cpu_baseline = {
+            "value": rate_all, "unit": UNIT, "cores": cores, "kind": ref.kind,
+            "single_core_value": rate1,
+            "sample": "first %d pairs of the step's Philox stream through the reference's "
+                      "distances_bulk; 1 core, then fork Pool(%d)" % (n_s, cores),
+        }
+        cpu_sample = (sample, ref_out)
+    else:
+        cpu_sample = None
+
+    import torch
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    from suchtree_b200 import SuchTree, _lib
+
+    T = SuchTree.from_flat(ft, device=local)
+    stream = torch.cuda.current_stream(dev)
+    sptr = stream.cuda_stream
+
+    pairs = torch.empty((n_pairs, 2), dtype=torch.int32, device=dev)
+    out = torch.empty(n_pairs, dtype=torch.float64, device=dev)
+    # rank r owns pairs [r*n, (r+1)*n) of the global stream
+    T.random_leaf_pairs_device(PAIR_SEED, rank * n_pairs, n_pairs, pairs.data_ptr(), idx_bits=32, stream=sptr)
+    torch.cuda.synchronize()
+
+    def step():
+        T.distances_device(pairs.data_ptr(), n_pairs, out.data_ptr(), idx_bits=32, stream=sptr)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(physical_gpu_index(local))
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    T.check_range(sptr)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * n_pairs * args.steps / (ms_max * 1e-3)
+
+    # ---- parity spot check against the reference's own output (rank 0, N=1)
+    parity = None
+    if cpu_sample is not None:
+        sample, ref_out = cpu_sample
+        got = out[: sample.shape[0]].cpu().numpy()
+        # reference accumulates in fp32 (MuchTree.pyx:924): depth-scaled tolerance
+        parity = bool(np.all(np.abs(got - ref_out) <= 2e-7 * T.depth * np.maximum(got, 1e-30)))
+        host_pairs = pairs[: sample.shape[0]].cpu().numpy().astype(np.int64)
+        parity = parity and bool(np.array_equal(host_pairs, sample))
+
+    # ---- e2e: the drop-in call on pinned host buffers
+    n_e2e = min(n_pairs, args.e2e_pairs)
+    h_pairs = torch.empty((n_e2e, 2), dtype=torch.int64).pin_memory()
+    h_pairs.copy_(pairs[:n_e2e].to(torch.int64))
+    h_out = torch.empty(n_e2e, dtype=torch.float64).pin_memory()
+    np_pairs, np_out = h_pairs.numpy(), h_out.numpy()
+    T.distances_bulk(np_pairs, out=np_out)  # warm-up: staging buffers
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        T.distances_bulk(np_pairs, out=np_out)
+    dt = time.perf_counter() - t0
+    te = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_e2e * e2e_steps / float(te.item())
+    e2e_ok = bool(torch.equal(h_out.to(dev), out[:n_e2e]))
+
+    # ---- rooflines (rank 0's kernel; all ranks run the same launch)
+    peak, peak_src = measured_peak()
+    per_launch_s = ms * 1e-3 / args.steps
+    achieved = 16.0 * n_pairs / per_launch_s / 1e9
+    gather = None
+    if rank == 0:
+        import ctypes as C
+
+        sps = C.c_double(0)
+        rc = _lib.lib().st_bench_gather(local, int(T.index_info["index_bytes"]), 64, 5, C.byref(sps))
+        if rc == 0:
+            gather = {
+                "what": "random 32-byte-sector gathers over an index-sized buffer (%d bytes), measured by "
+                        "st_bench_gather in this run" % T.index_info["index_bytes"],
+                "peak_sectors_per_s": sps.value,
+                "achieved_sectors_per_s": 3.0 * n_pairs / per_launch_s,
+                "frac": 3.0 * n_pairs / per_launch_s / sps.value,
+                "sectors_per_pair": 3,
+            }
+    line = {
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_max / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {
+            "workload": WORKLOAD, "tree_leaves": TREE_LEAVES, "tree_nodes": T.size, "tree_depth": T.depth,
+            "pairs_per_step_per_gpu": n_pairs, "pair_dtype": "int32x2", "result_dtype": "f64",
+            "parallelism": "index replicated, pair stream sharded per GPU, no collective",
+            "l2": "inputs larger than L2: %.0f MB of pairs+results streamed per step vs 126 MB L2"
+                  % (16.0 * n_pairs / 1e6),
+            "index_bytes": int(T.index_info["index_bytes"]),
+        },
+        "roofline": {
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "k_pairs<int32,VEC>",
+            "algorithmic_bytes_per_pair": 16,
+            "note": "the kernel is bound by L2 sector gathers (3 random sectors/pair), see gather_roofline",
+        },
+        "gather_roofline": gather,
+        "cpu_baseline": cpu_baseline,
+        "e2e": {
+            "value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n_e2e, "d2h_bytes_per_step": 8 * n_e2e,
+            "pairs_per_step_per_gpu": n_e2e, "steps": e2e_steps, "matches_device_path": e2e_ok,
+            "call": "SuchTree.distances_bulk(int64 (n,2) pinned host array, out=pinned float64)",
+        },
+        "gpu_launches": args.steps,
+        "clocks": clocks,
+        "parity_vs_reference_sample": parity,
+    }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=PAIRS_PER_STEP, help="pairs per GPU per step")
+    ap.add_argument("--e2e-pairs", type=int, default=PAIRS_PER_STEP)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

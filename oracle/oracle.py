@@ -67,15 +67,22 @@ class OracleTree:
         self.parent = np.ascontiguousarray(parent, dtype=np.int32)
         self.distance = np.ascontiguousarray(distance, dtype=np.float32)
         self.size = int(self.parent.shape[0])
-        if depth is None:
-            if leaf_ids is None:
-                has_child = np.zeros(self.size, bool)
-                has_child[self.parent[self.parent >= 0]] = True
-                leaf_ids = np.nonzero(~has_child)[0]
-            leaf_ids = np.ascontiguousarray(leaf_ids, dtype=np.int64)
-            depth = lib().oracle_tree_depth(self.parent, leaf_ids, leaf_ids.shape[0])
-        self.depth = int(depth)
         self._node_depth = None
+        if depth is None:
+            # max #nodes on a leaf->root path.  Computed by exact integer pointer
+            # jumping: the literal walk (literal_depth below, MuchTree.pyx:218-225) is
+            # O(leaves x depth) and cannot finish on a 10^6-deep caterpillar.
+            depth = int(self.node_depths().max()) + 1
+        self.depth = int(depth)
+
+    def literal_depth(self, leaf_ids=None):
+        """MuchTree.pyx:218-225 restated literally (small trees only)."""
+        if leaf_ids is None:
+            has_child = np.zeros(self.size, bool)
+            has_child[self.parent[self.parent >= 0]] = True
+            leaf_ids = np.nonzero(~has_child)[0]
+        leaf_ids = np.ascontiguousarray(leaf_ids, dtype=np.int64)
+        return int(lib().oracle_tree_depth(self.parent, leaf_ids, leaf_ids.shape[0]))
 
     @classmethod
     def from_newick(cls, tree_input):

@@ -17,6 +17,7 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <math.h>
+#include <complex.h>
 
 /* ---- MuchTree.pyx:999-1030  _mrca ------------------------------------------
  * Record a's ancestor chain in visited[], then walk b upward, scanning the
@@ -165,7 +166,11 @@ double oracle_pearson_f32(const double *x, const double *y, unsigned n)
         syy += yt * yt;
         sxy += xt * yt;
     }
-    return sxy / pow((double)(sxx * syy) + 1.0e-20, 0.5);
+    /* Cython compiles `x**(0.5)` on a C double to a COMPLEX power and quotient
+     * (MuchTree.c:22164-22172: __Pyx_c_pow_double = cpow, __Pyx_c_quot_double), which
+     * can differ from sqrt() in the last bit -- restated literally. */
+    double complex den = cpow(((double)(sxx * syy) + 1.0e-20) + 0.0 * I, 0.5 + 0.0 * I);
+    return creal((sxy + 0.0 * I) / den);
 }
 
 /* same two-pass formula with fp64 accumulators (what the fp32 code rounds) */

@@ -296,7 +296,7 @@ class SuchTree:
         node_a, node_b = self._validate_node_pair(a, b)
         return float(self.distances_bulk(np.array([[node_a, node_b]], dtype=np.int64))[0])
 
-    def distances_bulk(self, pairs):
+    def distances_bulk(self, pairs, out=None):
         """Distances for an (n,2) array of node-id pairs; MuchTree.pyx:872-909.
 
         Accepts what the reference accepts: an int64 (n,2) ndarray with any strides,
@@ -307,7 +307,13 @@ class SuchTree:
         """
         pairs = self._coerce_pairs(pairs)
         n = pairs.shape[0]
-        result = np.empty(n, dtype=np.float64)
+        if out is None:
+            result = np.empty(n, dtype=np.float64)
+        else:  # extension: caller-provided (e.g. pinned) float64 result buffer
+            result = out
+            if not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.shape == (n,)
+                    and out.flags.c_contiguous):
+                raise ValueError("out must be a C-contiguous float64 array of shape (n,)")
         if n:
             s0, s1 = pairs.strides[0] // 8, pairs.strides[1] // 8
             rc = _lib.lib().st_distances(self._handle, pairs.ctypes.data, s0, s1, n, result.ctypes.data)

@@ -1,0 +1,206 @@
+"""CPU-only tests of the host side: the array-based NEWICK flattener against the
+reference's structures, the synthetic generators, the C-ABI library (loads,
+exports every declared symbol, fails loudly without a device), helpers."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+from conftest import GOLDEN, REPO, load_pairs, read_tree_text, tree_source
+
+import oracle as O
+from suchtree_b200 import philox_host as philox_ref
+import tree_build
+from suchtree_b200 import _lib, newick, synth
+from suchtree_b200.exceptions import InvalidNodeError, NodeNotFoundError, SuchTreeError, TreeStructureError
+from suchtree_b200.tree import _read_tree_input
+
+
+# ---------------------------------------------------------------- flattener --
+def test_flattener_matches_reference(golden_trees):
+    for name, rec in golden_trees.items():
+        ft = newick.flatten(_read_tree_input(tree_source(name, rec)))
+        assert ft.size == rec["size"] and ft.root == rec["root"] and ft.n_leaves == rec["num_leaves"], name
+        assert list(ft.leaves.items()) == sorted(rec["leaves"].items(), key=lambda kv: kv[1]), name
+        assert ft.parent.tolist() == rec["parent"], name
+        assert ft.left.tolist() == rec["left"] and ft.right.tolist() == rec["right"], name
+        assert [float(x).hex() for x in ft.distance] == rec["distance_hex"], name
+        assert np.allclose(ft.support, rec["support"]), name
+
+
+@pytest.mark.parametrize("name", ["ml", "nj"])
+def test_flattener_big_trees(name, bigtrees):
+    ft = newick.flatten(read_tree_text("%s.tree.gz" % name))
+    z = np.load(os.path.join(GOLDEN, "pairs_big_%s.npz" % name))
+    info = bigtrees[name]
+    assert (ft.size, ft.root, ft.n_leaves) == (info["size"], info["root"], info["num_leaves"])
+    assert np.array_equal(ft.parent, z["parent"])
+    for k, v in list(info["first_leaves"].items()) + list(info["last_leaves"].items()):
+        assert ft.leaves[k] == v
+
+
+def test_flattener_agrees_with_oracle_builder_on_odd_inputs():
+    cases = [
+        "A;",
+        "(A,B);",
+        "(A:1,(B:2,C:3):4,(D:5,E:6,F:7,G:8):9,H:10)r:11;",
+        "((((a,b),c),d),(e,(f,(g,(h,i)))));",
+        " ( 'x y' : 1.5 , ( z:2 , w : 3 ) 0.75 : 4 ) ; ",
+        "(A:1,B:2)[comment](C:3);" if False else "((A:1,B:2)[c]:1,(C:3,D:4):2);",
+        "(a:1e-3,b:1E2,(c:-1,d:+2):0.0);",
+    ]
+    for nw in cases:
+        ft = newick.flatten(nw)
+        a = tree_build.build_arrays(nw.strip()) if nw.strip().startswith("(") else None
+        if a is None:
+            assert ft.size == 1 and ft.root == 0 and ft.leaves == {"A": 0}
+            continue
+        assert ft.parent.tolist() == a["parent"].tolist(), nw
+        assert ft.left.tolist() == a["left"].tolist(), nw
+        assert ft.leaves == a["leaves"], nw
+        assert [float(x).hex() for x in ft.distance] == [float(x).hex() for x in a["distance"]], nw
+
+
+def test_flattener_rejects_bad_trees():
+    for bad in ["((A,B));", "(A,(B));", "((A,B),(C,D)", "(A,B));", "", "(A,,B);"]:
+        with pytest.raises(TreeStructureError):
+            newick.flatten(bad)
+
+
+def test_deep_caterpillar_newick_does_not_recurse():
+    L = 20000
+    ft0 = synth.caterpillar_tree(L, seed=3, names=True)
+    ft1 = newick.flatten(synth.to_newick(ft0))
+    assert np.array_equal(ft0.parent, ft1.parent) and np.array_equal(ft0.left, ft1.left)
+    assert np.array_equal(ft0.distance[ft0.parent >= 0], ft1.distance[ft1.parent >= 0])
+
+
+# --------------------------------------------------------------- generators --
+def _check_inorder(ft):
+    """ids are in-order ranks <=> every left subtree precedes its node, right follows."""
+    n = ft.size
+    assert (ft.parent == -1).sum() == 1 and ft.parent[ft.root] == -1
+    internal = np.nonzero(ft.left != -1)[0]
+    assert np.all(internal % 2 == 1) and np.all(np.nonzero(ft.left == -1)[0] % 2 == 0)
+    assert np.all(ft.parent[ft.left[internal]] == internal) and np.all(ft.parent[ft.right[internal]] == internal)
+    assert np.all(ft.left[internal] < internal) and np.all(ft.right[internal] > internal)
+    # depth-argmin property on random pairs against the parent-walking oracle
+    t = O.OracleTree(ft.parent, ft.distance)
+    depth = t.node_depths()
+    rng = np.random.default_rng(1)
+    pairs = rng.integers(0, n, size=(300, 2))
+    m = (t.distances_f64_climb(pairs, with_mrca=True))[1]
+    for (a, b), mm in zip(pairs, m):
+        lo, hi = min(a, b), max(a, b)
+        assert lo + int(np.argmin(depth[lo:hi + 1])) == mm
+
+
+@pytest.mark.parametrize("gen", [synth.yule_tree, synth.balanced_tree, synth.caterpillar_tree])
+@pytest.mark.parametrize("n_leaves", [1, 2, 3, 7, 64, 1000, 4097])
+def test_generators_produce_valid_inorder_trees(gen, n_leaves):
+    ft = gen(n_leaves, seed=5)
+    assert ft.size == 2 * n_leaves - 1
+    if n_leaves == 1:
+        assert ft.root == 0 and ft.left[0] == -1
+        return
+    _check_inorder(ft)
+    e = ft.distance[ft.parent >= 0]
+    assert e.dtype == np.float32 and np.all(e >= 0.5) and np.all(e < 1.0)
+    assert np.array_equal(gen(n_leaves, seed=5).parent, ft.parent)  # deterministic
+
+
+def test_generator_shapes():
+    assert O.OracleTree(*_pd(synth.balanced_tree(1 << 12))).depth == 13
+    assert O.OracleTree(*_pd(synth.caterpillar_tree(500))).depth == 500
+    d = O.OracleTree(*_pd(synth.yule_tree(100000, seed=1))).depth
+    assert 25 <= d <= 80  # ~2 ln L expected mean leaf depth
+
+
+def _pd(ft):
+    return ft.parent, ft.distance
+
+
+def test_newick_roundtrip_through_oracle_builder():
+    ft = synth.yule_tree(300, seed=9, names=True)
+    a = tree_build.build_arrays(synth.to_newick(ft))
+    assert np.array_equal(a["parent"], ft.parent) and a["leaves"] == ft.leaves
+    assert np.array_equal(a["distance"][a["parent"] >= 0], ft.distance[ft.parent >= 0])
+
+
+# ------------------------------------------------------------------- C ABI ---
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(REPO, "include", "suchtree_b200.h")).read()
+    declared = set(re.findall(r"^ST_API [^;(]*?\b(st_[a-z0-9_]+)\(", header, flags=re.M))
+    assert len(declared) >= 20
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.st_version() >= 100
+
+
+def test_no_cpu_fallback_without_device():
+    n = C.c_int(0)
+    rc = _lib.lib().st_device_count(C.byref(n))
+    if rc == 0 and n.value > 0:
+        pytest.skip("a CUDA device is present")
+    from suchtree_b200 import SuchTree, pearson
+
+    with pytest.raises(SuchTreeError):
+        SuchTree("(A,B,(C,D));")
+    with pytest.raises(SuchTreeError):
+        pearson(np.arange(4.0), np.arange(4.0))
+
+
+def test_tree_validation_happens_before_any_device_work():
+    L = _lib.lib()
+    h = C.c_void_p()
+
+    def create(parent, left, right):
+        p, l, r = (np.array(x, np.int32) for x in (parent, left, right))
+        e = np.ones(len(parent), np.float32)
+        return L.st_tree_create(0, len(parent), p.ctypes.data, l.ctypes.data, r.ctypes.data, e.ctypes.data, 0, 0, C.byref(h))
+
+    # not in-order: root stored first
+    assert create([-1, 0, 0], [1, -1, -1], [2, -1, -1]) == _lib.ST_ERR_NOT_INORDER
+    # unary node
+    assert create([1, -1], [-1, 0], [-1, -1]) == _lib.ST_ERR_NOT_BINARY
+    # two roots
+    assert create([-1, -1, 1], [-1, 0, -1], [-1, 2, -1]) in (_lib.ST_ERR_NOT_BINARY, _lib.ST_ERR_INVALID_ARG)
+    assert b"" != L.st_last_error()
+
+
+def test_exceptions_mirror_reference():
+    e = InvalidNodeError(7, 5)
+    assert str(e) == "Node ID 7 out of bounds (tree size: 5)" and e.node_id == 7 and e.tree_size == 5
+    assert str(InvalidNodeError(3)) == "Invalid node ID: 3"
+    assert str(NodeNotFoundError("x")) == "Leaf name not found: x."
+    assert str(NodeNotFoundError(4)) == "Node not found: 4"
+    assert issubclass(TreeStructureError, SuchTreeError) and issubclass(SuchTreeError, Exception)
+
+
+# ------------------------------------------------------------------ Philox ---
+def test_philox_known_answers():
+    """Random123 kat_vectors: philox4x32-10, zero counter/key and the pi-digits vector."""
+    x = philox_ref.philox4x32_10(np.array([0], np.uint64), 0)
+    assert [int(v[0]) for v in x] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    # counter words (243f6a88, 85a308d3, 13198a2e, 03707344) need c2,c3 != 0: use the
+    # generic round function directly
+    c = [np.array([v], np.uint64) for v in (0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344)]
+    k0, k1 = 0xA4093822, 0x299F31D0
+    for _ in range(10):
+        p0 = philox_ref.M0 * c[0]
+        p1 = philox_ref.M1 * c[2]
+        c = [(p1 >> np.uint64(32)) ^ c[1] ^ np.uint64(k0), p1 & philox_ref.MASK,
+             (p0 >> np.uint64(32)) ^ c[3] ^ np.uint64(k1), p0 & philox_ref.MASK]
+        k0 = (k0 + philox_ref.W0) & 0xFFFFFFFF
+        k1 = (k1 + philox_ref.W1) & 0xFFFFFFFF
+    assert [int(v[0]) for v in c] == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+def test_random_leaf_pairs_reference_is_shardable():
+    a = philox_ref.random_leaf_pairs(1000, 42, 0, 101)
+    b = np.concatenate([philox_ref.random_leaf_pairs(1000, 42, 0, 40), philox_ref.random_leaf_pairs(1000, 42, 40, 61)])
+    assert np.array_equal(a, b)
+    assert a.min() >= 0 and a.max() <= 1998 and np.all(a % 2 == 0)
