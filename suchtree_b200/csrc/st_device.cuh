@@ -112,11 +112,12 @@ __device__ __forceinline__ dd st_ld_rd(const NodeRec *p) {
 }
 
 // ------------------------------------------------------------- RMQ ----------
-// Shared-memory copy of the block-level tables (<= ~60 KB): blockmin keys and
-// the sparse table of argmin block indices.
+// Block-level tables (shared memory in the query kernels, global memory in the
+// matrix kernel's few set-up queries): sparse table of packed keys over blocks and
+// the root distance of every block minimum.
 struct SmemTables {
-    const uint64_t *blockmin;
-    const uint16_t *st;  // [levels][n_blocks]
+    const uint64_t *stk;  // [levels][n_blocks]
+    const double2 *brd;   // [n_blocks]
 };
 
 __device__ __forceinline__ uint64_t st_scan_depth(const int32_t *__restrict__ depth, int32_t s,
@@ -146,31 +147,53 @@ static __device__ __noinline__ uint64_t st_rmq_inblock(const int32_t *__restrict
     return best;
 }
 
-// key of the MRCA given both endpoint records (already loaded)
+// key of the MRCA given both endpoint records (already loaded).  *from_table is set
+// when the winner is a block minimum taken from the block table: its root distance
+// is then tables.brd[id >> block_shift] and no third gather is needed.
 __device__ __forceinline__ uint64_t st_rmq(const TreeView &tv, const SmemTables &sm, int32_t lo,
-                                           int32_t hi, uint64_t suf_lo, uint64_t pre_hi) {
+                                           int32_t hi, uint64_t suf_lo, uint64_t pre_hi,
+                                           bool *from_table) {
     int32_t blo = lo >> tv.block_shift, bhi = hi >> tv.block_shift;
+    *from_table = false;
     if (blo == bhi) return st_rmq_inblock(tv.depth, tv.mst, tv.n_micro, tv.micro_shift, lo, hi);
     uint64_t best = st_min64(suf_lo, pre_hi);
     int32_t span = bhi - blo - 1;
     if (span > 0) {
         int k = 31 - __clz(span);
-        const uint16_t *lvl = sm.st + k * tv.n_blocks;
-        uint32_t i1 = lvl[blo + 1], i2 = lvl[bhi - (1 << k)];
-        best = st_min64(best, st_min64(sm.blockmin[i1], sm.blockmin[i2]));
+        const uint64_t *lvl = sm.stk + k * tv.n_blocks;
+        uint64_t mid = st_min64(lvl[blo + 1], lvl[bhi - (1 << k)]);
+        if (mid < best) {
+            best = mid;
+            *from_table = true;
+        }
     }
     return best;
 }
 
-// cooperative copy of the block tables into dynamic shared memory
+// root distance of the MRCA: shared-memory copy for block minima, one gather otherwise
+__device__ __forceinline__ dd st_mrca_rd(const TreeView &tv, const SmemTables &sm, uint64_t key,
+                                         bool from_table) {
+    int32_t id = st_key_id(key);
+    if (from_table) {
+        double2 r = sm.brd[id >> tv.block_shift];
+        return dd{r.x, r.y};
+    }
+    return st_ld_rd(tv.rec + id);
+}
+
+__host__ __device__ __forceinline__ int st_table_bytes(int n_blocks, int st_levels) {
+    return n_blocks * (8 * st_levels + 16);
+}
+
+// cooperative copy of the block tables into dynamic shared memory (16-byte aligned)
 __device__ __forceinline__ SmemTables st_load_tables(const TreeView &tv, unsigned char *smem) {
-    uint64_t *bm = reinterpret_cast<uint64_t *>(smem);
-    uint16_t *st = reinterpret_cast<uint16_t *>(bm + tv.n_blocks);
-    for (int i = threadIdx.x; i < tv.n_blocks; i += blockDim.x) bm[i] = tv.blockmin[i];
+    double2 *brd = reinterpret_cast<double2 *>(smem);
+    uint64_t *stk = reinterpret_cast<uint64_t *>(brd + tv.n_blocks);
+    for (int i = threadIdx.x; i < tv.n_blocks; i += blockDim.x) brd[i] = tv.brd[i];
     int tot = tv.st_levels * tv.n_blocks;
-    for (int i = threadIdx.x; i < tot; i += blockDim.x) st[i] = tv.st[i];
+    for (int i = threadIdx.x; i < tot; i += blockDim.x) stk[i] = tv.stk[i];
     __syncthreads();
-    return SmemTables{bm, st};
+    return SmemTables{stk, brd};
 }
 
 // ------------------------------------------------------------ Philox --------

@@ -8,8 +8,8 @@
 //   rec[n]        32 B/node: root distance (double-double), suffix/prefix argmin
 //                 of depth within the node's RMQ block           -> 1 sector/lookup
 //   depth[n]      int32 node depth (root 0); only the same-block slow path scans it
-//   blockmin[nb]  packed (depth,id) minimum of each block          \  copied to shared
-//   st[K][nb]     uint16 sparse table over blocks (argmin block)   /  memory by queries
+//   stk[K][nb]    sparse table of packed (depth,id) keys over blocks \  copied to shared
+//   brd[nb]       root distance of each block's minimum node         /  memory by queries
 //   mst[Km][nm]   packed-key sparse table over micro blocks (same-block slow path)
 #include <algorithm>
 #include <cstdarg>
@@ -94,7 +94,8 @@ __global__ void k_max_depth(int32_t n, const int32_t *__restrict__ dep, int *__r
 // records, and the block minimum.  Thread t owns a contiguous chunk of the block.
 __global__ void k_block_records(int32_t n, int block_shift, const int32_t *__restrict__ dep,
                                 const double *__restrict__ rhi, const double *__restrict__ rlo,
-                                NodeRec *__restrict__ rec, uint64_t *__restrict__ blockmin) {
+                                NodeRec *__restrict__ rec, uint64_t *__restrict__ blockmin,
+                                double2 *__restrict__ brd) {
     __shared__ uint64_t cmin[256];
     __shared__ uint64_t cpre[256];  // min over chunks [0, t)
     __shared__ uint64_t csuf[256];  // min over chunks (t, T)
@@ -115,6 +116,8 @@ __global__ void k_block_records(int32_t n, int block_shift, const int32_t *__res
             run = st_min64(run, cmin[t]);
         }
         blockmin[blockIdx.x] = run;
+        const int32_t arg = st_key_id(run);
+        brd[blockIdx.x] = make_double2(rhi[arg], rlo[arg]);
         run = ~0ull;
         for (int t = T - 1; t >= 0; --t) {
             csuf[t] = run;
@@ -136,24 +139,16 @@ __global__ void k_block_records(int32_t n, int block_shift, const int32_t *__res
     }
 }
 
-// Sparse table over <= 2048 block minima, one CTA.  st[k][i] = index of the
-// block with the smallest key among blocks [i, min(i + 2^k, nb)).
-__global__ void k_block_sparse_table(int nb, int levels, const uint64_t *__restrict__ blockmin,
-                                     uint16_t *st) {
-    extern __shared__ uint64_t bm[];
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
-        bm[i] = blockmin[i];
-        st[i] = uint16_t(i);
-    }
-    __syncthreads();
+// Sparse table of keys over the block minima, one CTA (<= 4096 blocks).
+// stk[k][i] = min key over blocks [i, min(i + 2^k, nb)); level 0 (the block minima)
+// is written by k_block_records.
+__global__ void k_block_sparse_table(int nb, int levels, uint64_t *stk) {
     for (int k = 1; k < levels; ++k) {
-        const uint16_t *prev = st + (k - 1) * nb;
-        uint16_t *cur = st + k * nb;
+        const uint64_t *prev = stk + size_t(k - 1) * nb;
+        uint64_t *cur = stk + size_t(k) * nb;
         int half = 1 << (k - 1);
-        for (int i = threadIdx.x; i < nb; i += blockDim.x) {
-            uint16_t a = prev[i], b = prev[min(i + half, nb - 1)];
-            cur[i] = bm[b] < bm[a] ? b : a;
-        }
+        for (int i = threadIdx.x; i < nb; i += blockDim.x)
+            cur[i] = st_min64(prev[i], prev[min(i + half, nb - 1)]);
         __syncthreads();  // global writes by this CTA are visible to it after the barrier
     }
 }
@@ -253,7 +248,8 @@ static int validate_tree(int64_t n, const int32_t *parent, const int32_t *left, 
 
 // ------------------------------------------------------------ create --------
 // Upper bound on RMQ blocks: the block tables (8 + 2*levels bytes per block) are
-// copied to shared memory by every query CTA.  1024 blocks -> <= 28 KB.
+// copied to shared memory by every query CTA.  1024 blocks x 10 levels -> <= 96 KB
+// (two 512-thread CTAs per SM still fit).
 // SUCHTREE_B200_MAX_BLOCKS overrides (power of two, <= 4096) for experiments.
 static int st_max_blocks() {
     int v = 1024;
@@ -282,8 +278,8 @@ extern "C" void st_tree_destroy(st_tree *t) {
     DeviceGuard g(t->device);
     cudaFree(t->d_rec);
     cudaFree(t->d_depth);
-    cudaFree(t->d_blockmin);
-    cudaFree(t->d_st);
+    cudaFree(t->d_stk);
+    cudaFree(t->d_brd);
     cudaFree(t->d_mst);
     cudaFree(t->d_status);
     for (int i = 0; i < 3; ++i) {
@@ -382,8 +378,8 @@ extern "C" int st_tree_create(int device, int64_t n_nodes, const int32_t *parent
 
     ST_TRY(dev_alloc(&t->d_rec, size_t(n), &t->index_bytes));
     ST_TRY(dev_alloc(&t->d_depth, size_t(n), &t->index_bytes));
-    ST_TRY(dev_alloc(&t->d_blockmin, size_t(t->n_blocks), &t->index_bytes));
-    ST_TRY(dev_alloc(&t->d_st, size_t(t->st_levels) * t->n_blocks, &t->index_bytes));
+    ST_TRY(dev_alloc(&t->d_stk, size_t(t->st_levels) * t->n_blocks, &t->index_bytes));
+    ST_TRY(dev_alloc(&t->d_brd, size_t(t->n_blocks), &t->index_bytes));
     ST_TRY(dev_alloc(&t->d_mst, size_t(t->m_levels) * t->n_micro, &t->index_bytes));
     ST_TRY(dev_alloc(&t->d_status, 1, &t->index_bytes));
     ST_TRY_CUDA(cudaMemset(t->d_status, 0, sizeof(RangeStatus)));
@@ -465,9 +461,8 @@ extern "C" int st_tree_create(int device, int64_t n_nodes, const int32_t *parent
     {
         int T = std::min(256, 1 << bs);
         k_block_records<<<t->n_blocks, T, 0, s>>>(n, bs, t->d_depth, d_rhi[cur], d_rlo[cur],
-                                                  t->d_rec, t->d_blockmin);
-        k_block_sparse_table<<<1, 1024, size_t(t->n_blocks) * 8, s>>>(t->n_blocks, t->st_levels,
-                                                                      t->d_blockmin, t->d_st);
+                                                  t->d_rec, t->d_stk, t->d_brd);
+        k_block_sparse_table<<<1, 1024, 0, s>>>(t->n_blocks, t->st_levels, t->d_stk);
         int gm = (t->n_micro + TPB - 1) / TPB;
         k_micro_min<<<gm, TPB, 0, s>>>(n, ms, t->n_micro, t->d_depth, t->d_mst);
         for (int k = 1; k < t->m_levels; ++k)
@@ -479,11 +474,11 @@ extern "C" int st_tree_create(int device, int64_t n_nodes, const int32_t *parent
     ST_TRY2_CUDA(cudaDeviceSynchronize());
     free_tmp();
 
-    t->query_smem_bytes = t->n_blocks * 8 + t->st_levels * t->n_blocks * 2;
+    t->query_smem_bytes = st_table_bytes(t->n_blocks, t->st_levels);
     t->view.rec = t->d_rec;
     t->view.depth = t->d_depth;
-    t->view.blockmin = t->d_blockmin;
-    t->view.st = t->d_st;
+    t->view.stk = t->d_stk;
+    t->view.brd = t->d_brd;
     t->view.mst = t->d_mst;
     t->view.status = t->d_status;
     t->view.n_nodes = n;

@@ -60,8 +60,9 @@ struct RangeStatus {
 struct TreeView {
     const NodeRec *rec;        // [n_nodes]
     const int32_t *depth;      // [n_nodes] node depth, root = 0
-    const uint64_t *blockmin;  // [n_blocks] packed (depth,id) min of each block
-    const uint16_t *st;        // [st_levels][n_blocks] block sparse table (argmin block index)
+    const uint64_t *stk;       // [st_levels][n_blocks] block sparse table of packed (depth,id) keys;
+                               // level k, entry i = min key over blocks [i, i+2^k); level 0 = block minima
+    const double2 *brd;        // [n_blocks] root distance (hi, lo) of each block's minimum node
     const uint64_t *mst;       // [m_levels][n_micro] micro sparse table (packed keys)
     RangeStatus *status;
     int32_t n_nodes;
@@ -83,8 +84,8 @@ struct st_tree {
     // device allocations
     NodeRec *d_rec = nullptr;
     int32_t *d_depth = nullptr;
-    uint64_t *d_blockmin = nullptr;
-    uint16_t *d_st = nullptr;
+    uint64_t *d_stk = nullptr;
+    double2 *d_brd = nullptr;
     uint64_t *d_mst = nullptr;
     RangeStatus *d_status = nullptr;
     int32_t *d_leaf_ids = nullptr;  // lazily unused; leaves are the even ids

@@ -20,8 +20,9 @@ __device__ __forceinline__ double linked_query(const TreeView &tv, const SmemTab
     int32_t lo = min(a, b), hi = max(a, b);
     if (lo == hi) return 0.0;
     RecRaw l = st_ld_rec(tv.rec + lo), h = st_ld_rec(tv.rec + hi);
-    uint64_t key = st_rmq(tv, sm, lo, hi, l.suf, h.pre);
-    return st_patristic(dd{l.rd_hi, l.rd_lo}, dd{h.rd_hi, h.rd_lo}, st_ld_rd(tv.rec + st_key_id(key)));
+    bool ft;
+    uint64_t key = st_rmq(tv, sm, lo, hi, l.suf, h.pre, &ft);
+    return st_patristic(dd{l.rd_hi, l.rd_lo}, dd{h.rd_hi, h.rd_lo}, st_mrca_rd(tv, sm, key, ft));
 }
 
 // k = i(i-1)/2 + j, 0 <= j < i   (the reference's loop order, MuchTree.pyx:2919-2925)
@@ -344,22 +345,25 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-__global__ void __launch_bounds__(LT)
+// both trees' block tables live in shared memory (up to ~2 x 96 KB): one big CTA per SM
+static const int MLT = 1024;
+
+__global__ void __launch_bounds__(MLT)
 k_sample_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ links,
                  uint32_t n_links, uint64_t seed, int64_t first, int64_t n, double x0, double y0,
                  double *__restrict__ partials /* [grid][5] */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // two table sets back to back (second one 16-byte aligned)
     const SmemTables sa = st_load_tables(ta, smem_raw);
-    const int offs = ((ta.n_blocks * 8 + ta.st_levels * ta.n_blocks * 2) + 15) & ~15;
+    const int offs = (st_table_bytes(ta.n_blocks, ta.st_levels) + 15) & ~15;
     const SmemTables sb = st_load_tables(tb, smem_raw + offs);
-    __shared__ double red[5][LT / 32];
+    __shared__ double red[5][MLT / 32];
 
     Mom5 m{0, 0, 0, 0, 0};
     // samples are processed two at a time: one Philox call = 4 words = 2 samples
     const int64_t c_begin = first >> 1, c_end = (first + n + 1) >> 1;
-    for (int64_t c = c_begin + int64_t(blockIdx.x) * LT + threadIdx.x; c < c_end;
-         c += int64_t(gridDim.x) * LT) {
+    for (int64_t c = c_begin + int64_t(blockIdx.x) * MLT + threadIdx.x; c < c_end;
+         c += int64_t(gridDim.x) * MLT) {
         Philox4 r = st_philox4x32_10(uint64_t(c), seed);
         const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
@@ -384,7 +388,7 @@ k_sample_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ 
     __syncthreads();
     if (threadIdx.x < 5) {
         double s = 0;
-        for (int w2 = 0; w2 < LT / 32; ++w2) s += red[threadIdx.x][w2];
+        for (int w2 = 0; w2 < MLT / 32; ++w2) s += red[threadIdx.x][w2];
         partials[size_t(blockIdx.x) * 5 + threadIdx.x] = s;
     }
 }
@@ -421,10 +425,10 @@ extern "C" int st_sample_moments(const st_tree *ta, const st_tree *tb, const int
     rc = set_smem(k_sample_moments, smem);
     if (rc != ST_OK) return rc;
     int per_sm = 0;
-    ST_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sample_moments, LT, smem));
+    ST_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sample_moments, MLT, smem));
     if (per_sm < 1) per_sm = 1;
     const int64_t calls = (n_samples + 1) / 2 + 1;
-    int grid = int(std::min<int64_t>((calls + LT - 1) / LT, int64_t(ta->sm_count) * per_sm));
+    int grid = int(std::min<int64_t>((calls + MLT - 1) / MLT, int64_t(ta->sm_count) * per_sm));
     double *d_part = nullptr, *d_out = nullptr;
     ST_CUDA(cudaMalloc(&d_part, size_t(grid) * 5 * 8));
     if (cudaMalloc(&d_out, 5 * 8) != cudaSuccess) {
@@ -432,7 +436,7 @@ extern "C" int st_sample_moments(const st_tree *ta, const st_tree *tb, const int
         return ST_ERR_NOMEM;
     }
     cudaStream_t s = ta->streams[0];
-    k_sample_moments<<<grid, LT, smem, s>>>(ta->view, tb->view, dl.rows, uint32_t(L), seed, first_sample,
+    k_sample_moments<<<grid, MLT, smem, s>>>(ta->view, tb->view, dl.rows, uint32_t(L), seed, first_sample,
                                            n_samples, x0, y0, d_part);
     k_reduce_partials<<<1, 160, 0, s>>>(grid, d_part, d_out);
     double h[5];

@@ -40,8 +40,9 @@ __device__ __forceinline__ uint64_t mat_query(const TreeView &tv, int32_t a, int
     int32_t lo = min(a, b), hi = max(a, b);
     if (lo == hi) return st_key(__ldg(tv.depth + lo), lo);
     RecRaw rl = st_ld_rec(tv.rec + lo), rh = st_ld_rec(tv.rec + hi);
-    SmemTables g{tv.blockmin, tv.st};
-    return st_rmq(tv, g, lo, hi, rl.suf, rh.pre);
+    SmemTables g{tv.stk, tv.brd};
+    bool ft;
+    return st_rmq(tv, g, lo, hi, rl.suf, rh.pre, &ft);
 }
 
 __device__ __forceinline__ dd dd_minus_2x(dd a, dd m) {  // a - 2m
@@ -106,7 +107,7 @@ k_matrix(const TreeView tv, const int32_t *__restrict__ ids, int64_t n, int64_t 
         if (hasA) ra = st_ld_rec(tv.rec + idA);
         if (hasB) rb = st_ld_rec(tv.rec + idB);
         __syncthreads();
-        SmemTables g{tv.blockmin, tv.st};
+        SmemTables g{tv.stk, tv.brd};
         for (int i = 0; i < rows; ++i) {
             const int32_t rid = s_id[i];
             const dd rrd{s_ph[i], s_pl[i]};
@@ -117,8 +118,9 @@ k_matrix(const TreeView tv, const int32_t *__restrict__ ids, int64_t n, int64_t 
                 const int32_t cid = h ? idB : idA;
                 const RecRaw &rc = h ? rb : ra;
                 if (has && cid != rid) {
-                    uint64_t key = rid < cid ? st_rmq(tv, g, rid, cid, s_suf[i], rc.pre)
-                                             : st_rmq(tv, g, cid, rid, rc.suf, s_pre[i]);
+                    bool ft;
+                    uint64_t key = rid < cid ? st_rmq(tv, g, rid, cid, s_suf[i], rc.pre, &ft)
+                                             : st_rmq(tv, g, cid, rid, rc.suf, s_pre[i], &ft);
                     dd rm = st_ld_rd(tv.rec + st_key_id(key));
                     // low-id operand first, as in the pair kernel
                     v[h] = rid < cid ? st_patristic(rrd, dd{rc.rd_hi, rc.rd_lo}, rm)

@@ -79,9 +79,10 @@ __device__ __forceinline__ PairQ st_make_query(const TreeView &tv, long long a, 
 
 __device__ __forceinline__ uint64_t st_query_key(const TreeView &tv, const SmemTables &sm,
                                                  const PairQ &q, const RecRaw &rl,
-                                                 const RecRaw &rh) {
+                                                 const RecRaw &rh, bool *from_table) {
+    *from_table = false;
     if (q.lo == q.hi) return uint64_t(uint32_t(q.lo));  // MRCA(a,a) = a
-    return st_rmq(tv, sm, q.lo, q.hi, rl.suf, rh.pre);
+    return st_rmq(tv, sm, q.lo, q.hi, rl.suf, rh.pre, from_table);
 }
 
 template <typename IdxT, bool VEC>
@@ -100,10 +101,12 @@ k_pairs(const TreeView tv, const IdxT *__restrict__ pairs, int64_t n, double *__
             PairQ q0 = st_make_query(tv, a0, b0), q1 = st_make_query(tv, a1, b1);
             RecRaw l0 = st_ld_rec(tv.rec + q0.lo), h0 = st_ld_rec(tv.rec + q0.hi);
             RecRaw l1 = st_ld_rec(tv.rec + q1.lo), h1 = st_ld_rec(tv.rec + q1.hi);
-            int32_t m0 = st_key_id(st_query_key(tv, sm, q0, l0, h0));
-            int32_t m1 = st_key_id(st_query_key(tv, sm, q1, l1, h1));
+            bool t0, t1;
+            const uint64_t k0 = st_query_key(tv, sm, q0, l0, h0, &t0);
+            const uint64_t k1 = st_query_key(tv, sm, q1, l1, h1, &t1);
+            const int32_t m0 = st_key_id(k0), m1 = st_key_id(k1);
             if (out) {
-                dd r0 = st_ld_rd(tv.rec + m0), r1 = st_ld_rd(tv.rec + m1);
+                dd r0 = st_mrca_rd(tv, sm, k0, t0), r1 = st_mrca_rd(tv, sm, k1, t1);
                 double d0 = st_patristic(dd{l0.rd_hi, l0.rd_lo}, dd{h0.rd_hi, h0.rd_lo}, r0);
                 double d1 = st_patristic(dd{l1.rd_hi, l1.rd_lo}, dd{h1.rd_hi, h1.rd_lo}, r1);
                 st_st_stream_f64x2(out + 2 * i, q0.bad ? nan : d0, q1.bad ? nan : d1);
@@ -115,9 +118,11 @@ k_pairs(const TreeView tv, const IdxT *__restrict__ pairs, int64_t n, double *__
             PairIO<IdxT>::load1(pairs, n - 1, a, b);
             PairQ q = st_make_query(tv, a, b);
             RecRaw l = st_ld_rec(tv.rec + q.lo), h = st_ld_rec(tv.rec + q.hi);
-            int32_t m = st_key_id(st_query_key(tv, sm, q, l, h));
+            bool ft;
+            const uint64_t k = st_query_key(tv, sm, q, l, h, &ft);
+            const int32_t m = st_key_id(k);
             if (out) {
-                double d = st_patristic(dd{l.rd_hi, l.rd_lo}, dd{h.rd_hi, h.rd_lo}, st_ld_rd(tv.rec + m));
+                double d = st_patristic(dd{l.rd_hi, l.rd_lo}, dd{h.rd_hi, h.rd_lo}, st_mrca_rd(tv, sm, k, ft));
                 out[n - 1] = q.bad ? nan : d;
             }
             if (mrca_out) mrca_out[n - 1] = q.bad ? -1 : m;
@@ -128,9 +133,11 @@ k_pairs(const TreeView tv, const IdxT *__restrict__ pairs, int64_t n, double *__
             PairIO<IdxT>::load1(pairs, i, a, b);
             PairQ q = st_make_query(tv, a, b);
             RecRaw l = st_ld_rec(tv.rec + q.lo), h = st_ld_rec(tv.rec + q.hi);
-            int32_t m = st_key_id(st_query_key(tv, sm, q, l, h));
+            bool ft;
+            const uint64_t k = st_query_key(tv, sm, q, l, h, &ft);
+            const int32_t m = st_key_id(k);
             if (out) {
-                double d = st_patristic(dd{l.rd_hi, l.rd_lo}, dd{h.rd_hi, h.rd_lo}, st_ld_rd(tv.rec + m));
+                double d = st_patristic(dd{l.rd_hi, l.rd_lo}, dd{h.rd_hi, h.rd_lo}, st_mrca_rd(tv, sm, k, ft));
                 st_st_stream_f64(out + i, q.bad ? nan : d);
             }
             if (mrca_out) st_st_stream_i32(mrca_out + i, q.bad ? -1 : m);

@@ -6,6 +6,7 @@
 // fixed reduction tree instead of the reference's sequential fp32 accumulators.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "st_device.cuh"
 
@@ -145,6 +146,95 @@ k_gather(const ulonglong4 *__restrict__ buf, uint64_t n_sectors, int64_t loads, 
     if (acc == 0x123456789abcdefull) *sink = acc;  // keep the loads alive
 }
 
+// Experiment: the same random sectors fetched by the bulk-copy (TMA) engine
+// straight into shared memory (cp.async.bulk, one 32-byte copy per sector,
+// completion on an mbarrier), bypassing the LSU/L1TEX data pipe.
+// Selected with SUCHTREE_B200_GATHER_MODE=bulk.
+__global__ void __launch_bounds__(256)
+k_gather_bulk(const ulonglong4 *__restrict__ buf, uint64_t n_sectors, int64_t loads, uint64_t seed,
+              unsigned long long *__restrict__ sink) {
+    __shared__ __align__(128) ulonglong4 slots[256 * 4];
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    uint64_t acc = 0;
+    uint32_t phase = 0;
+    for (int64_t i = 0; i < loads; i += 4) {
+        if (threadIdx.x == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a),
+                         "r"(256 * 4 * 32)
+                         : "memory");
+        Philox4 r = st_philox4x32_10(tid * uint64_t(loads) + uint64_t(i), seed);
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint64_t idx = (uint64_t(w[k]) * n_sectors) >> 32;
+            uint32_t dst = (uint32_t)__cvta_generic_to_shared(&slots[threadIdx.x * 4 + k]);
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 32, [%2];" ::"r"(dst),
+                "l"(buf + idx), "r"(bar_a)
+                : "memory");
+        }
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                : "=r"(done)
+                : "r"(bar_a), "r"(phase)
+                : "memory");
+        }
+        phase ^= 1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            ulonglong4 v = slots[threadIdx.x * 4 + k];
+            acc ^= v.x ^ v.y ^ v.z ^ v.w;
+        }
+        __syncthreads();  // slots are rewritten next round
+    }
+    if (acc == 0x123456789abcdefull) *sink = acc;
+}
+
+// Experiment: route the sector gathers through the TEXTURE data pipe
+// (tex1Dfetch on a linear int4 texture, two 16-byte texels per 32-byte sector).
+// MODE 0: all four gathers of a round via TEX; MODE 1: two via TEX, two via LSU.
+// Selected with SUCHTREE_B200_GATHER_MODE=tex / mix.
+template <int MODE>
+__global__ void __launch_bounds__(512)
+k_gather_tex(cudaTextureObject_t tex, const ulonglong4 *__restrict__ buf, uint64_t n_sectors,
+             int64_t loads, uint64_t seed, unsigned long long *__restrict__ sink) {
+    uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    uint64_t acc = 0;
+    for (int64_t i = 0; i < loads; i += 4) {
+        Philox4 r = st_philox4x32_10(tid * uint64_t(loads) + uint64_t(i), seed);
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+        int4 ta[4], tb[4];
+        uint64_t a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0}, d[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint64_t idx = (uint64_t(w[k]) * n_sectors) >> 32;
+            if (MODE == 0 || k < 2) {
+                ta[k] = tex1Dfetch<int4>(tex, int(2 * idx));
+                tb[k] = tex1Dfetch<int4>(tex, int(2 * idx + 1));
+            } else {
+                ta[k] = tb[k] = make_int4(0, 0, 0, 0);
+                asm volatile("ld.global.nc.L2::evict_last.v4.b64 {%0,%1,%2,%3}, [%4];"
+                             : "=l"(a[k]), "=l"(b[k]), "=l"(c[k]), "=l"(d[k])
+                             : "l"(buf + idx));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            acc ^= a[k] ^ b[k] ^ c[k] ^ d[k] ^ uint64_t(uint32_t(ta[k].x ^ ta[k].y ^ ta[k].z ^ ta[k].w)) ^
+                   (uint64_t(uint32_t(tb[k].x ^ tb[k].y ^ tb[k].z ^ tb[k].w)) << 32);
+    }
+    if (acc == 0x123456789abcdefull) *sink = acc;
+}
+
 extern "C" int st_bench_gather(int device, int64_t bytes, int64_t loads_per_thread, int iters,
                                double *sectors_per_s) {
     if (!sectors_per_s || bytes < 32 || loads_per_thread < 4 || iters < 1) {
@@ -170,12 +260,35 @@ extern "C" int st_bench_gather(int device, int64_t bytes, int64_t loads_per_thre
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    k_gather<<<grid, tpb>>>(static_cast<const ulonglong4 *>(buf), n_sectors, loads_per_thread, 1, sink);  // warm
+    const char *mode = getenv("SUCHTREE_B200_GATHER_MODE");
+    const bool bulk = mode && mode[0] == 'b';
+    const bool use_tex = mode && mode[0] == 't', mix = mode && mode[0] == 'm';
+    cudaTextureObject_t tex = 0;
+    if (use_tex || mix) {
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = buf;
+        rd.res.linear.desc = cudaCreateChannelDesc<int4>();
+        rd.res.linear.sizeInBytes = n_sectors * 32;
+        cudaTextureDesc td{};
+        td.readMode = cudaReadModeElementType;
+        ST_CUDA(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+    }
+    auto launch = [&](uint64_t seed) {
+        if (use_tex)
+            k_gather_tex<0><<<grid, tpb>>>(tex, static_cast<const ulonglong4 *>(buf), n_sectors, loads_per_thread, seed, sink);
+        else if (mix)
+            k_gather_tex<1><<<grid, tpb>>>(tex, static_cast<const ulonglong4 *>(buf), n_sectors, loads_per_thread, seed, sink);
+        else if (bulk)  // same thread count: twice the CTAs of half the size
+            k_gather_bulk<<<grid * 2, tpb / 2>>>(static_cast<const ulonglong4 *>(buf), n_sectors, loads_per_thread, seed, sink);
+        else
+            k_gather<<<grid, tpb>>>(static_cast<const ulonglong4 *>(buf), n_sectors, loads_per_thread, seed, sink);
+    };
+    launch(1);  // warm
     float best_ms = 1e30f;
     for (int it = 0; it < iters; ++it) {
         cudaEventRecord(e0);
-        k_gather<<<grid, tpb>>>(static_cast<const ulonglong4 *>(buf), n_sectors, loads_per_thread,
-                                uint64_t(it) + 2, sink);
+        launch(uint64_t(it) + 2);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms = 0;
@@ -183,6 +296,7 @@ extern "C" int st_bench_gather(int device, int64_t bytes, int64_t loads_per_thre
         best_ms = std::min(best_ms, ms);
     }
     cudaError_t e = cudaGetLastError();
+    if (tex) cudaDestroyTextureObject(tex);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(buf);
