@@ -235,6 +235,110 @@ k_gather_tex(cudaTextureObject_t tex, const ulonglong4 *__restrict__ buf, uint64
     if (acc == 0x123456789abcdefull) *sink = acc;
 }
 
+
+// Experiment: TMA tile::gather4 (sm_100): ONE bulk-tensor instruction fetches four
+// rows (here: four 32-byte sectors) of a 2-D view of the buffer into shared memory.
+// MIX = 0: every sector via gather4.  MIX = K: per round each thread also issues
+// 4*K LSU sector loads, to see whether the TMA path adds to the L1TEX gather rate.
+// Selected with SUCHTREE_B200_GATHER_MODE=g4 / g4mix1 / g4mix2.
+#include <cuda.h>
+
+template <int MIX>
+__global__ void __launch_bounds__(128)
+k_gather_g4(const __grid_constant__ CUtensorMap tmap, const ulonglong4 *__restrict__ buf,
+            uint64_t n_sectors, int64_t rounds, uint64_t seed, unsigned long long *__restrict__ sink) {
+    constexpr int STAGES = 2;
+    __shared__ __align__(128) ulonglong4 slots[STAGES][128 * 4];
+    __shared__ __align__(8) uint64_t bar[STAGES];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&bar[s])), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    uint64_t acc = 0;
+    auto issue = [&](int64_t r) {
+        const int s = int(r % STAGES);
+        const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar[s]);
+        if (threadIdx.x == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(128 * 4 * 32) : "memory");
+        Philox4 p = st_philox4x32_10(tid * uint64_t(rounds) + uint64_t(r), seed);
+        int32_t r0 = int32_t((uint64_t(p.x) * n_sectors) >> 32), r1 = int32_t((uint64_t(p.y) * n_sectors) >> 32);
+        int32_t r2 = int32_t((uint64_t(p.z) * n_sectors) >> 32), r3 = int32_t((uint64_t(p.w) * n_sectors) >> 32);
+        uint32_t dst = (uint32_t)__cvta_generic_to_shared(&slots[s][threadIdx.x * 4]);
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+            ::"r"(dst), "l"(&tmap), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar_a)
+            : "memory");
+    };
+    issue(0);
+    for (int64_t r = 0; r < rounds; ++r) {
+        if (r + 1 < rounds) issue(r + 1);
+        if (MIX > 0) {
+#pragma unroll
+            for (int m = 0; m < MIX; ++m) {
+                Philox4 p = st_philox4x32_10(tid * uint64_t(rounds) + uint64_t(r), seed + 77 + m);
+                const uint32_t w[4] = {p.x, p.y, p.z, p.w};
+                uint64_t a[4], b[4], c[4], d[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint64_t idx = (uint64_t(w[k]) * n_sectors) >> 32;
+                    asm volatile("ld.global.nc.L2::evict_last.v4.b64 {%0,%1,%2,%3}, [%4];"
+                                 : "=l"(a[k]), "=l"(b[k]), "=l"(c[k]), "=l"(d[k])
+                                 : "l"(buf + idx));
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc ^= a[k] ^ b[k] ^ c[k] ^ d[k];
+            }
+        }
+        const int s = int(r % STAGES);
+        const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar[s]);
+        const uint32_t phase = uint32_t(r / STAGES) & 1;
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                : "=r"(done) : "r"(bar_a), "r"(phase) : "memory");
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            ulonglong4 v = slots[s][threadIdx.x * 4 + k];
+            acc ^= v.x ^ v.y ^ v.z ^ v.w;
+        }
+        __syncthreads();  // stage s is rewritten by issue(r + 2)
+    }
+    if (acc == 0x123456789abcdefull) *sink = acc;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+// 2-D view of a buffer of 32-byte sectors: inner dim = 8 x u32, outer dim = sectors
+static int make_sector_tmap(void *buf, uint64_t n_sectors, CUtensorMap *out) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    ST_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) {
+        st_set_error("cuTensorMapEncodeTiled not available");
+        return ST_ERR_CUDA;
+    }
+    cuuint64_t gdim[2] = {8, n_sectors};
+    cuuint64_t gstride[1] = {32};
+    cuuint32_t box[2] = {8, 1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = reinterpret_cast<PFN_encodeTiled>(fn)(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, buf, gdim, gstride, box,
+                                                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                       CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        st_set_error("cuTensorMapEncodeTiled failed: %d", int(r));
+        return ST_ERR_CUDA;
+    }
+    return ST_OK;
+}
+
 extern "C" int st_bench_gather(int device, int64_t bytes, int64_t loads_per_thread, int iters,
                                double *sectors_per_s) {
     if (!sectors_per_s || bytes < 32 || loads_per_thread < 4 || iters < 1) {
@@ -263,6 +367,13 @@ extern "C" int st_bench_gather(int device, int64_t bytes, int64_t loads_per_thre
     const char *mode = getenv("SUCHTREE_B200_GATHER_MODE");
     const bool bulk = mode && mode[0] == 'b';
     const bool use_tex = mode && mode[0] == 't', mix = mode && mode[0] == 'm';
+    const bool g4 = mode && mode[0] == 'g';
+    const int g4mix = (g4 && mode[2] == 'm') ? (mode[5] ? mode[5] - '0' : 1) : 0;
+    CUtensorMap tmap;
+    if (g4) {
+        int rc = make_sector_tmap(buf, n_sectors, &tmap);
+        if (rc != ST_OK) return rc;
+    }
     cudaTextureObject_t tex = 0;
     if (use_tex || mix) {
         cudaResourceDesc rd{};
@@ -279,7 +390,13 @@ extern "C" int st_bench_gather(int device, int64_t bytes, int64_t loads_per_thre
             k_gather_tex<0><<<grid, tpb>>>(tex, static_cast<const ulonglong4 *>(buf), n_sectors, loads_per_thread, seed, sink);
         else if (mix)
             k_gather_tex<1><<<grid, tpb>>>(tex, static_cast<const ulonglong4 *>(buf), n_sectors, loads_per_thread, seed, sink);
-        else if (bulk)  // same thread count: twice the CTAs of half the size
+        else if (g4) {
+            const int64_t rounds = loads_per_thread / 4;
+            if (g4mix == 0) k_gather_g4<0><<<grid * 4, tpb / 4>>>(tmap, static_cast<const ulonglong4 *>(buf), n_sectors, rounds, seed, sink);
+            else if (g4mix == 1) k_gather_g4<1><<<grid * 4, tpb / 4>>>(tmap, static_cast<const ulonglong4 *>(buf), n_sectors, rounds, seed, sink);
+            else if (g4mix == 2) k_gather_g4<2><<<grid * 4, tpb / 4>>>(tmap, static_cast<const ulonglong4 *>(buf), n_sectors, rounds, seed, sink);
+            else k_gather_g4<3><<<grid * 4, tpb / 4>>>(tmap, static_cast<const ulonglong4 *>(buf), n_sectors, rounds, seed, sink);
+        } else if (bulk)  // same thread count: twice the CTAs of half the size
             k_gather_bulk<<<grid * 2, tpb / 2>>>(static_cast<const ulonglong4 *>(buf), n_sectors, loads_per_thread, seed, sink);
         else
             k_gather<<<grid, tpb>>>(static_cast<const ulonglong4 *>(buf), n_sectors, loads_per_thread, seed, sink);
@@ -305,6 +422,6 @@ extern "C" int st_bench_gather(int device, int64_t bytes, int64_t loads_per_thre
         st_set_error("st_bench_gather: %s", cudaGetErrorString(e));
         return ST_ERR_CUDA;
     }
-    *sectors_per_s = double(grid) * tpb * double(loads_per_thread) / (double(best_ms) * 1e-3);
+    *sectors_per_s = double(grid) * tpb * double(loads_per_thread) * (1 + g4mix) / (double(best_ms) * 1e-3);
     return ST_OK;
 }
