@@ -390,9 +390,11 @@ def run_ours(args):
                 "what": "random 32-byte-sector gathers over an index-sized buffer (%d bytes), measured by "
                         "st_bench_gather in this run" % T.index_info["index_bytes"],
                 "peak_sectors_per_s": sps.value,
-                "achieved_sectors_per_s": 3.0 * n_pairs / per_launch_s,
-                "frac": 3.0 * n_pairs / per_launch_s / sps.value,
-                "sectors_per_pair": 3,
+                "achieved_sectors_per_s": 2.0 * n_pairs / per_launch_s,
+                "frac": 2.0 * n_pairs / per_launch_s / sps.value,
+                "sectors_per_pair": 2,
+                "note": "rec[lo] + rec[hi]; rd[mrca] comes from the shared-memory block table for ~97 % of "
+                        "far-apart pairs (DESIGN.md 4.1)",
             }
     line = {
         "metric": METRIC,
@@ -419,7 +421,7 @@ def run_ours(args):
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "k_pairs<int32,VEC>",
             "algorithmic_bytes_per_pair": 16,
-            "note": "the kernel is bound by L2 sector gathers (3 random sectors/pair), see gather_roofline",
+            "note": "the kernel is bound by the per-SM L1TEX rate of random sector gathers (2 per pair), see gather_roofline",
         },
         "gather_roofline": gather,
         "cpu_baseline": cpu_baseline,
@@ -432,6 +434,13 @@ def run_ours(args):
         "clocks": clocks,
         "parity_vs_reference_sample": parity,
     }
+    if not args.no_other_workloads:
+        del pairs, out, h_pairs, h_out
+        torch.cuda.empty_cache()
+        try:
+            line["other_workloads"] = run_other_workloads(args, rank, world, local, dev, peak)
+        except Exception as e:  # the headline line must still be printed
+            line["other_workloads"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -439,6 +448,137 @@ def run_ours(args):
         dist.destroy_process_group()
     return 0
 
+
+
+# --------------------------------------------------------------------------- #
+# the other BASELINE.json configs (cfg 3, 4, 5), same process, short runs
+# --------------------------------------------------------------------------- #
+def _timed(stream, fn, steps, warmup=3):
+    import torch
+
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / steps
+
+
+def run_other_workloads(args, rank, world, local, dev, peak):
+    """cfg3 (1M-leaf caterpillar + balanced, 1.25e9 pairs per GPU), cfg5 (100k x 100k
+    matrix, 12,500-row block per GPU, device-resident) and cfg4 (two 100k-leaf trees,
+    1.25e8 Philox-sampled link pairs per GPU, moments all-reduced).  Every rank runs
+    its own shard; times are max over ranks; rank 0 reports."""
+    import torch
+    import torch.distributed as dist
+
+    from suchtree_b200 import SuchTree, shard, synth
+    from suchtree_b200.linked import moments_pearson
+
+    stream = torch.cuda.current_stream(dev)
+    sptr = stream.cuda_stream
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    res = {}
+    # ---- cfg3: deep-path worst case + balanced, 1M leaves
+    n3 = args.cfg3_pairs
+    pairs = torch.empty((n3, 2), dtype=torch.int32, device=dev)
+    out = torch.empty(n3, dtype=torch.float64, device=dev)
+    for shape, gen in (("caterpillar", synth.caterpillar_tree), ("balanced", synth.balanced_tree)):
+        ft = gen(1_000_000, seed=3)
+        t0 = time.perf_counter()
+        T = SuchTree.from_flat(ft, device=local)
+        build_s = time.perf_counter() - t0
+        T.random_leaf_pairs_device(3, rank * n3, n3, pairs.data_ptr(), idx_bits=32, stream=sptr)
+        sec = _timed(stream, lambda: T.distances_device(pairs.data_ptr(), n3, out.data_ptr(), idx_bits=32,
+                                                        stream=sptr), steps=5)
+        T.check_range(sptr)
+        sec = max_over_ranks(sec)
+        # size-independent properties at full size: symmetric pairs give d(a,a)=0 and the
+        # result is finite and bounded by twice the largest root distance
+        finite = bool(torch.isfinite(out).all().item())
+        res["cfg3_" + shape] = {
+            "workload": "1M-leaf %s tree (depth %d), %d random leaf pairs per GPU per launch" % (shape, T.depth, n3),
+            "pairs_per_s": world * n3 / sec, "ms_per_launch": sec * 1e3, "index_build_s": build_s,
+            "index_bytes": int(T.index_info["index_bytes"]),
+            "hbm_frac": 16.0 * n3 / sec / 1e9 / peak, "all_finite": finite,
+        }
+        del T
+    del pairs, out
+    torch.cuda.empty_cache()
+
+    # ---- cfg5: 100k x 100k fp64 matrix, one row block per GPU, left on the device
+    ft = synth.yule_tree(TREE_LEAVES, seed=TREE_SEED)
+    T = SuchTree.from_flat(ft, device=local)
+    n = TREE_LEAVES
+    rb, re_ = shard.row_block(rank, max(world, 8), n)  # 12,500-row blocks as in the 8-GPU plan
+    block = torch.empty((re_ - rb, n), dtype=torch.float64, device=dev)
+    from suchtree_b200 import _lib
+
+    def mat():
+        _lib.check(_lib.lib().st_distance_matrix(T._handle, None, n, rb, re_, block.data_ptr(), 1, sptr))
+
+    sec = max_over_ranks(_timed(stream, mat, steps=5))
+    elems = (re_ - rb) * n
+    # spot check against the pair kernel (same index): 4096 random elements of the block
+    g = torch.Generator(device="cpu").manual_seed(11 + rank)
+    ri = torch.randint(0, re_ - rb, (4096,), generator=g)
+    ci = torch.randint(0, n, (4096,), generator=g)
+    chk_pairs = torch.stack([2 * (ri + rb), 2 * ci], dim=1).to(torch.int32).to(dev)
+    chk = torch.empty(4096, dtype=torch.float64, device=dev)
+    T.distances_device(chk_pairs.data_ptr(), 4096, chk.data_ptr(), idx_bits=32, stream=sptr)
+    torch.cuda.synchronize()
+    same = bool(torch.equal(block[ri.to(dev), ci.to(dev)], chk))
+    res["cfg5_matrix"] = {
+        "workload": "rows [%d,%d) of the 100k x 100k all-leaves fp64 matrix per GPU, device-resident" % (rb, re_),
+        "elements_per_s": world * elems / sec, "ms_per_block": sec * 1e3, "bytes_written_per_gpu": 8 * elems,
+        "hbm_frac": 8.0 * elems / sec / 1e9 / peak, "matches_pair_kernel_on_4096_samples": same,
+    }
+    del block
+    torch.cuda.empty_cache()
+
+    # ---- cfg4: sampled two-tree correlation, moments via NCCL
+    fa, fb = synth.yule_tree(TREE_LEAVES, seed=4, names=True), synth.yule_tree(TREE_LEAVES, seed=5, names=True)
+    TA, TB = SuchTree.from_flat(fa, device=local), SuchTree.from_flat(fb, device=local)
+    rng = np.random.default_rng(6)
+    la = 2 * rng.integers(0, TREE_LEAVES, TREE_LEAVES)
+    lb = 2 * rng.integers(0, TREE_LEAVES, TREE_LEAVES)
+    linklist = np.ascontiguousarray(np.stack([lb, la], axis=1).astype(np.int64))
+    n4 = args.cfg4_samples
+    from suchtree_b200 import _lib as L_
+
+    import ctypes as C
+
+    def sample():
+        m = L_.Moments()
+        L_.check(L_.lib().st_sample_moments(TA._handle, TB._handle, linklist.ctypes.data, linklist.shape[0], 7,
+                                            rank * n4, n4, 0.0, 0.0, C.byref(m)))
+        return m
+
+    sample()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        m = sample()
+    sec = max_over_ranks((time.perf_counter() - t0) / reps)
+    m = shard.allreduce_moments(m, device=dev)
+    res["cfg4_pearson_sampler"] = {
+        "workload": "two 100k-leaf Yule trees (seeds 4,5), 100k random links (seed 6), %d Philox-sampled "
+                    "link pairs per GPU per call, 5 moments all-reduced (NCCL)" % n4,
+        "samples_per_s": world * n4 / sec, "ms_per_call": sec * 1e3, "pearson_r": moments_pearson(m),
+        "timing": "host wall clock around the blocking C-ABI call (includes link upload + moment read-back)",
+    }
+    return res
 
 def main():
     ap = argparse.ArgumentParser()
@@ -449,6 +589,9 @@ def main():
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_STEP, help="pairs per GPU per step")
     ap.add_argument("--e2e-pairs", type=int, default=PAIRS_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-workloads", action="store_true", help="skip the cfg3/cfg4/cfg5 side measurements")
+    ap.add_argument("--cfg3-pairs", type=int, default=1_250_000_000, help="cfg3 pairs per GPU per launch")
+    ap.add_argument("--cfg4-samples", type=int, default=125_000_000, help="cfg4 samples per GPU per call")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -26,16 +26,11 @@ static const int MT = 256;       // threads per CTA
 static const int TC = 2 * MT;    // columns per tile (two per thread -> 16-byte stores)
 static const int TR = 64;        // rows per tile
 
-struct SideData {  // per row (shared memory) or per column (registers)
-    uint64_t key;
-    dd comb, plain;
-};
-
 __device__ __forceinline__ int32_t mat_id(const int32_t *__restrict__ ids, int64_t k) {
     return ids ? __ldg(ids + k) : int32_t(2 * k);  // default: leaf k has id 2k
 }
 
-// full query through global-memory tables (few per tile; L1/L2 cached)
+// full query through global-memory tables (set-up pass and diagonal tiles only)
 __device__ __forceinline__ uint64_t mat_query(const TreeView &tv, int32_t a, int32_t b) {
     int32_t lo = min(a, b), hi = max(a, b);
     if (lo == hi) return st_key(__ldg(tv.depth + lo), lo);
@@ -63,16 +58,170 @@ __device__ __forceinline__ void mat_store2(double *row, int64_t col, int64_t n, 
     }
 }
 
-template <bool SORTED>
+// ------------------------------------------------------------ set-up pass ---
+// Per-call side tables for an ASCENDING id list (built by k_matrix_sides /
+// k_matrix_mid, a few queries per row/column, then read coalesced by every tile):
+//   rd[k]                      root distance of ids[k]
+//   p*/s* [k] = (depth, comb)  depth of the range argmin and comb = rd[k] - 2 rd[argmin] for
+//       pcol: argmin depth[ids[c0] .. ids[k]],   c0 = first column of k's column tile
+//       scol: argmin depth[ids[k] .. ids[c1-1]], c1-1 = last column of k's column tile
+//       prow / srow: the same relative to k's ROW tile (rows are counted from row_begin)
+//   mid[rt][ct] = (depth, rd) of argmin depth[lowmax .. highmin] between a row tile and a
+//       column tile that do not overlap
+struct __align__(32) SideRec {  // 32 bytes
+    double comb_hi, comb_lo;
+    uint32_t depth;
+    uint32_t pad0;
+    uint64_t pad1;
+};
+struct __align__(32) MidRec {  // 32 bytes
+    double rd_hi, rd_lo;
+    uint32_t depth;
+    uint32_t valid;
+    uint64_t pad1;
+};
+struct MatTables {
+    const double2 *rd;     // [n]
+    const SideRec *pcol;   // [n]
+    const SideRec *scol;   // [n]
+    const SideRec *prow;   // [rows]  (index k - row_begin)
+    const SideRec *srow;   // [rows]
+    const MidRec *mid;     // [row tiles][col tiles]
+    int32_t n_ct;
+};
+
+__device__ __forceinline__ SideRec mat_side(const TreeView &tv, dd rd, int32_t a, int32_t b) {
+    const uint64_t k = mat_query(tv, a, b);
+    const dd c = dd_minus_2x(rd, st_ld_rd(tv.rec + st_key_id(k)));
+    return SideRec{c.hi, c.lo, uint32_t(k >> 32), 0u, 0ull};
+}
+
+__global__ void k_matrix_sides(const TreeView tv, const int32_t *__restrict__ ids, int64_t n,
+                               int64_t row_begin, int64_t row_end, double2 *__restrict__ rd_out,
+                               SideRec *__restrict__ pcol, SideRec *__restrict__ scol,
+                               SideRec *__restrict__ prow, SideRec *__restrict__ srow) {
+    const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int32_t id = mat_id(ids, k);
+    const dd rd = st_ld_rd(tv.rec + id);
+    rd_out[k] = make_double2(rd.hi, rd.lo);
+    const int64_t c0 = k / TC * TC, c1 = min(c0 + TC, n);
+    pcol[k] = mat_side(tv, rd, mat_id(ids, c0), id);
+    scol[k] = mat_side(tv, rd, id, mat_id(ids, c1 - 1));
+    if (k >= row_begin && k < row_end) {
+        const int64_t r0 = row_begin + (k - row_begin) / TR * TR, r1 = min(r0 + TR, row_end);
+        prow[k - row_begin] = mat_side(tv, rd, mat_id(ids, r0), id);
+        srow[k - row_begin] = mat_side(tv, rd, id, mat_id(ids, r1 - 1));
+    }
+}
+
+__global__ void k_matrix_mid(const TreeView tv, const int32_t *__restrict__ ids, int64_t n,
+                             int64_t row_begin, int64_t row_end, int32_t n_rt, int32_t n_ct,
+                             MidRec *__restrict__ mid) {
+    const int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (q >= int64_t(n_rt) * n_ct) return;
+    const int64_t rt = q / n_ct, ct = q % n_ct;
+    const int64_t r0 = row_begin + rt * TR, r1 = min(r0 + TR, row_end);
+    const int64_t c0 = ct * TC, c1 = min(c0 + TC, n);
+    MidRec m{0.0, 0.0, 0u, 0u, 0ull};
+    int32_t a = -1, b = -1;
+    if (r1 <= c0) { a = mat_id(ids, r1 - 1); b = mat_id(ids, c0); }
+    else if (c1 <= r0) { a = mat_id(ids, c1 - 1); b = mat_id(ids, r0); }
+    if (a >= 0) {
+        const uint64_t k = mat_query(tv, a, b);
+        const dd r = st_ld_rd(tv.rec + st_key_id(k));
+        m = MidRec{r.hi, r.lo, uint32_t(k >> 32), 1u, 0ull};
+    }
+    mid[q] = m;
+}
+
+__device__ __forceinline__ SideRec ld_side(const SideRec *p) {
+    uint64_t x, y, z, w;  // one 256-bit load per record
+    asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(x), "=l"(y), "=l"(z), "=l"(w) : "l"(p));
+    SideRec s;
+    s.comb_hi = __longlong_as_double((long long)x);
+    s.comb_lo = __longlong_as_double((long long)y);
+    s.depth = uint32_t(z);
+    s.pad0 = 0; s.pad1 = 0;
+    return s;
+}
+
+// low side meets the tile's middle range: the candidate is the shallower of S and M
+__device__ __forceinline__ void mat_apply_mid(SideRec &s, dd plain, uint32_t mdepth, dd mrd) {
+    if (mdepth < s.depth) {
+        const dd c = dd_minus_2x(plain, mrd);
+        s.comb_hi = c.hi; s.comb_lo = c.lo; s.depth = mdepth;
+    }
+}
+
+// ---------------------------------------------------- generic (slow) tile ---
+// per-element RMQ + one rd gather: diagonal tiles and unsorted id lists
+// DIAG_ONLY: grid = (2, row tiles); CTA x handles the x-th column tile that overlaps its
+// row tile (ascending lists: the ordered kernel has written everything else).
+template <bool DIAG_ONLY>
 __global__ void __launch_bounds__(MT)
-k_matrix(const TreeView tv, const int32_t *__restrict__ ids, int64_t n, int64_t row_begin,
-         int64_t row_end, double *__restrict__ out) {
+k_matrix_generic(const TreeView tv, const int32_t *__restrict__ ids, int64_t n, int64_t row_begin,
+                 int64_t row_end, double *__restrict__ out) {
+    const int64_t r0 = row_begin + int64_t(blockIdx.y) * TR;
+    const int rows = int(row_end - r0 < TR ? row_end - r0 : TR);
+    if (rows <= 0) return;
+    const int64_t c0 = DIAG_ONLY ? (r0 / TC + blockIdx.x) * TC : int64_t(blockIdx.x) * TC;
+    if (c0 >= n || (DIAG_ONLY && c0 >= r0 + rows)) return;
+    const int64_t c1 = c0 + TC < n ? c0 + TC : n;
     __shared__ int32_t s_id[TR];
-    __shared__ uint64_t s_key[TR];
-    __shared__ double s_ch[TR], s_cl[TR], s_ph[TR], s_pl[TR];
+    __shared__ double s_ph[TR], s_pl[TR];
     __shared__ uint64_t s_suf[TR], s_pre[TR];
-    __shared__ uint64_t s_mid;
-    __shared__ dd s_midrd;
+    const int t = threadIdx.x;
+    const int64_t cA = c0 + 2 * t, cB = cA + 1;
+    const bool hasA = cA < c1, hasB = cB < c1;
+    const int32_t idA = hasA ? mat_id(ids, cA) : 0, idB = hasB ? mat_id(ids, cB) : 0;
+    for (int i = t; i < rows; i += MT) {
+        int32_t id = mat_id(ids, r0 + i);
+        RecRaw r = st_ld_rec(tv.rec + id);
+        s_id[i] = id;
+        s_ph[i] = r.rd_hi; s_pl[i] = r.rd_lo;
+        s_suf[i] = r.suf;  s_pre[i] = r.pre;
+    }
+    RecRaw ra{}, rb{};
+    if (hasA) ra = st_ld_rec(tv.rec + idA);
+    if (hasB) rb = st_ld_rec(tv.rec + idB);
+    __syncthreads();
+    SmemTables g{tv.stk, tv.brd};
+    for (int i = 0; i < rows; ++i) {
+        const int32_t rid = s_id[i];
+        const dd rrd{s_ph[i], s_pl[i]};
+        double v[2] = {0.0, 0.0};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const bool has = h ? hasB : hasA;
+            const int32_t cid = h ? idB : idA;
+            const RecRaw &rc = h ? rb : ra;
+            if (has && cid != rid) {
+                bool ft;
+                uint64_t key = rid < cid ? st_rmq(tv, g, rid, cid, s_suf[i], rc.pre, &ft)
+                                         : st_rmq(tv, g, cid, rid, rc.suf, s_pre[i], &ft);
+                dd rm = st_ld_rd(tv.rec + st_key_id(key));
+                // low-id operand first, as in the pair kernel
+                v[h] = rid < cid ? st_patristic(rrd, dd{rc.rd_hi, rc.rd_lo}, rm)
+                                 : st_patristic(dd{rc.rd_hi, rc.rd_lo}, rrd, rm);
+            }
+        }
+        mat_store2(out + (r0 + i - row_begin) * n, cA, n, v[0], v[1]);
+    }
+}
+
+// ------------------------------------------------------------- tile kernel --
+// Ordered tiles read their side data from the set-up tables: no index query, no
+// gather.  Every element is one depth compare and
+//     d = lowdepth <= highdepth ? lowcomb + highplain : lowplain + highcomb
+// in double-double (9 fp64 adds) -- or, when every low word of the tile's operands
+// is zero (always the case for trees whose root distances are exact in fp64), in
+// ONE fp64 add with a bit-identical result.
+__global__ void __launch_bounds__(MT)
+k_matrix_ordered(const TreeView tv, const int32_t *__restrict__ ids, const MatTables mt, int64_t n,
+                 int64_t row_begin, int64_t row_end, double *__restrict__ out) {
+    __shared__ double s_ch[TR], s_cl[TR], s_ph[TR], s_pl[TR];
+    __shared__ uint32_t s_dep[TR];
 
     const int64_t r0 = row_begin + int64_t(blockIdx.y) * TR;
     const int64_t c0 = int64_t(blockIdx.x) * TC;
@@ -82,111 +231,69 @@ k_matrix(const TreeView tv, const int32_t *__restrict__ ids, int64_t n, int64_t 
     const int64_t r1 = r0 + rows, c1 = c0 + cols;  // exclusive
     const int t = threadIdx.x;
 
-    // tile class: 0 = per-element (diagonal / unsorted), 1 = rows are the low side, 2 = columns are
-    int cls = 0;
-    if (SORTED) {
-        if (r1 <= c0) cls = 1;
-        else if (c1 <= r0) cls = 2;
-    }
+    // rows are the low side (above the diagonal), or the columns are; tiles that
+    // overlap the diagonal belong to k_matrix_generic
+    if (!(r1 <= c0) && !(c1 <= r0)) return;
+    const bool rows_low = r1 <= c0;
+    const MidRec mid = mt.mid[int64_t(blockIdx.y) * mt.n_ct + blockIdx.x];
+    const dd midrd{mid.rd_hi, mid.rd_lo};
 
+    int nonzero_lo = 0;
+    if (t < rows) {
+        const int64_t k = r0 + t;
+        const double2 p = __ldg(mt.rd + k);
+        SideRec s = ld_side((rows_low ? mt.srow : mt.prow) + (k - row_begin));
+        if (rows_low) mat_apply_mid(s, dd{p.x, p.y}, mid.depth, midrd);
+        s_dep[t] = s.depth;
+        s_ch[t] = s.comb_hi; s_cl[t] = s.comb_lo;
+        s_ph[t] = p.x;       s_pl[t] = p.y;
+        nonzero_lo |= (s.comb_lo != 0.0) | (p.y != 0.0);
+    }
     // this thread's two columns
     const int64_t cA = c0 + 2 * t, cB = cA + 1;
     const bool hasA = cA < c1, hasB = cB < c1;
-    const int32_t idA = hasA ? mat_id(ids, cA) : 0, idB = hasB ? mat_id(ids, cB) : 0;
+    SideRec a{}, b{};
+    dd pa{0.0, 0.0}, pb{0.0, 0.0};
+    if (hasA) {
+        const double2 p = __ldg(mt.rd + cA);
+        pa = dd{p.x, p.y};
+        a = ld_side((rows_low ? mt.pcol : mt.scol) + cA);
+        if (!rows_low) mat_apply_mid(a, pa, mid.depth, midrd);
+        nonzero_lo |= (a.comb_lo != 0.0) | (pa.lo != 0.0);
+    }
+    if (hasB) {
+        const double2 p = __ldg(mt.rd + cB);
+        pb = dd{p.x, p.y};
+        b = ld_side((rows_low ? mt.pcol : mt.scol) + cB);
+        if (!rows_low) mat_apply_mid(b, pb, mid.depth, midrd);
+        nonzero_lo |= (b.comb_lo != 0.0) | (pb.lo != 0.0);
+    }
+    const int slow = __syncthreads_or(nonzero_lo);
+    double *orow = out + (r0 - row_begin) * n;
 
-    if (cls == 0) {
-        // ---- generic tile: per-element RMQ + one rd gather
-        for (int i = t; i < rows; i += MT) {
-            int32_t id = mat_id(ids, r0 + i);
-            RecRaw r = st_ld_rec(tv.rec + id);
-            s_id[i] = id;
-            s_ph[i] = r.rd_hi; s_pl[i] = r.rd_lo;
-            s_suf[i] = r.suf;  s_pre[i] = r.pre;
-        }
-        RecRaw ra{}, rb{};
-        if (hasA) ra = st_ld_rec(tv.rec + idA);
-        if (hasB) rb = st_ld_rec(tv.rec + idB);
-        __syncthreads();
-        SmemTables g{tv.stk, tv.brd};
+    if (!slow) {
+        // "low side combined" iff lowdepth <= highdepth; rows_low: row is the low side
+#pragma unroll 4
         for (int i = 0; i < rows; ++i) {
-            const int32_t rid = s_id[i];
-            const dd rrd{s_ph[i], s_pl[i]};
-            double v[2] = {0.0, 0.0};
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const bool has = h ? hasB : hasA;
-                const int32_t cid = h ? idB : idA;
-                const RecRaw &rc = h ? rb : ra;
-                if (has && cid != rid) {
-                    bool ft;
-                    uint64_t key = rid < cid ? st_rmq(tv, g, rid, cid, s_suf[i], rc.pre, &ft)
-                                             : st_rmq(tv, g, cid, rid, rc.suf, s_pre[i], &ft);
-                    dd rm = st_ld_rd(tv.rec + st_key_id(key));
-                    // low-id operand first, as in the pair kernel
-                    v[h] = rid < cid ? st_patristic(rrd, dd{rc.rd_hi, rc.rd_lo}, rm)
-                                     : st_patristic(dd{rc.rd_hi, rc.rd_lo}, rrd, rm);
-                }
-            }
-            mat_store2(out + (r0 + i - row_begin) * n, cA, n, v[0], v[1]);
+            const uint32_t rdp = s_dep[i];
+            const double rc = s_ch[i], rp = s_ph[i];
+            const bool selA = rows_low ? (rdp <= a.depth) : (rdp < a.depth);
+            const bool selB = rows_low ? (rdp <= b.depth) : (rdp < b.depth);
+            // sel true -> row comb + column plain ; false -> row plain + column comb
+            const double v0 = selA ? __dadd_rn(rc, pa.hi) : __dadd_rn(rp, a.comb_hi);
+            const double v1 = selB ? __dadd_rn(rc, pb.hi) : __dadd_rn(rp, b.comb_hi);
+            mat_store2(orow + int64_t(i) * n, cA, n, v0, v1);
         }
         return;
     }
-
-    // ---- ordered tile.  low side = rows (cls 1) or columns (cls 2)
-    const bool rows_low = cls == 1;
-    const int32_t lowmax = rows_low ? mat_id(ids, r1 - 1) : mat_id(ids, c1 - 1);
-    const int32_t highmin = rows_low ? mat_id(ids, c0) : mat_id(ids, r0);
-    if (t == 0) {
-        uint64_t k = mat_query(tv, lowmax, highmin);
-        s_mid = k;
-        s_midrd = st_ld_rd(tv.rec + st_key_id(k));
-    }
-    __syncthreads();
-    const uint64_t mid = s_mid;
-    const dd midrd = s_midrd;
-
-    auto side = [&](int32_t id, bool low) {
-        SideData s;
-        dd rd = st_ld_rd(tv.rec + id);
-        s.plain = rd;
-        if (low) {
-            uint64_t k = mat_query(tv, id, lowmax);
-            if (k <= mid) {
-                s.key = k;
-                s.comb = dd_minus_2x(rd, st_ld_rd(tv.rec + st_key_id(k)));
-            } else {
-                s.key = mid;
-                s.comb = dd_minus_2x(rd, midrd);
-            }
-        } else {
-            uint64_t k = mat_query(tv, highmin, id);
-            s.key = k;
-            s.comb = dd_minus_2x(rd, st_ld_rd(tv.rec + st_key_id(k)));
-        }
-        return s;
-    };
-
-    for (int i = t; i < rows; i += MT) {
-        SideData s = side(mat_id(ids, r0 + i), rows_low);
-        s_key[i] = s.key;
-        s_ch[i] = s.comb.hi;  s_cl[i] = s.comb.lo;
-        s_ph[i] = s.plain.hi; s_pl[i] = s.plain.lo;
-    }
-    SideData a{}, b{};
-    if (hasA) a = side(idA, !rows_low);
-    if (hasB) b = side(idB, !rows_low);
-    __syncthreads();
-
     for (int i = 0; i < rows; ++i) {
-        const uint64_t rk = s_key[i];
+        const uint32_t rdp = s_dep[i];
         const dd rc{s_ch[i], s_cl[i]}, rp{s_ph[i], s_pl[i]};
-        // "low side combined" iff lowkey <= highkey
-        const bool selA = rows_low ? (rk <= a.key) : !(a.key <= rk);
-        const bool selB = rows_low ? (rk <= b.key) : !(b.key <= rk);
-        // selX true -> row comb + column plain ; false -> row plain + column comb
-        double v0 = selA ? dd_add_to_double(rc, a.plain) : dd_add_to_double(rp, a.comb);
-        double v1 = selB ? dd_add_to_double(rc, b.plain) : dd_add_to_double(rp, b.comb);
-        mat_store2(out + (r0 + i - row_begin) * n, cA, n, v0, v1);
+        const bool selA = rows_low ? (rdp <= a.depth) : (rdp < a.depth);
+        const bool selB = rows_low ? (rdp <= b.depth) : (rdp < b.depth);
+        const double v0 = selA ? dd_add_to_double(rc, pa) : dd_add_to_double(rp, dd{a.comb_hi, a.comb_lo});
+        const double v1 = selB ? dd_add_to_double(rc, pb) : dd_add_to_double(rp, dd{b.comb_hi, b.comb_lo});
+        mat_store2(orow + int64_t(i) * n, cA, n, v0, v1);
     }
 }
 
@@ -204,6 +311,8 @@ __global__ void k_narrow_ids(int64_t n, const int64_t *__restrict__ in, int32_t 
     if (i + 1 < n && in[i + 1] <= in[i]) *unsorted = 1;
 }
 
+// Set-up tables + tile kernel on one stream.  The tables live in stream-ordered
+// allocations (cudaMallocAsync), so the call stays asynchronous.
 static int launch_matrix(const st_tree *t, const int32_t *d_ids, bool sorted, int64_t n,
                          int64_t row_begin, int64_t row_end, double *d_out, cudaStream_t s) {
     const int64_t rows = row_end - row_begin;
@@ -213,11 +322,39 @@ static int launch_matrix(const st_tree *t, const int32_t *d_ids, bool sorted, in
         st_set_error("st_distance_matrix: more than 65535*%d rows per call", TR);
         return ST_ERR_INVALID_ARG;
     }
-    if (sorted)
-        k_matrix<true><<<grid, MT, 0, s>>>(t->view, d_ids, n, row_begin, row_end, d_out);
-    else
-        k_matrix<false><<<grid, MT, 0, s>>>(t->view, d_ids, n, row_begin, row_end, d_out);
-    ST_CUDA(cudaGetLastError());
+    MatTables mt{};
+    if (!sorted) {
+        k_matrix_generic<false><<<grid, MT, 0, s>>>(t->view, d_ids, n, row_begin, row_end, d_out);
+        ST_CUDA(cudaGetLastError());
+        return ST_OK;
+    }
+    const int64_t n_rt = grid.y, n_ct = grid.x;
+    auto pad = [](size_t b) { return (b + 255) & ~size_t(255); };  // records are read with 32-byte loads
+    const size_t bytes_rd = pad(size_t(n) * sizeof(double2)), bytes_col = pad(size_t(n) * sizeof(SideRec));
+    const size_t bytes_row = pad(size_t(rows) * sizeof(SideRec)), bytes_mid = pad(size_t(n_rt) * n_ct * sizeof(MidRec));
+    const size_t total = bytes_rd + 2 * bytes_col + 2 * bytes_row + bytes_mid;
+    unsigned char *base = nullptr;
+    ST_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&base), total, s));
+    unsigned char *p = base;
+    double2 *rd = reinterpret_cast<double2 *>(p); p += bytes_rd;
+    SideRec *pcol = reinterpret_cast<SideRec *>(p); p += bytes_col;
+    SideRec *scol = reinterpret_cast<SideRec *>(p); p += bytes_col;
+    SideRec *prow = reinterpret_cast<SideRec *>(p); p += bytes_row;
+    SideRec *srow = reinterpret_cast<SideRec *>(p); p += bytes_row;
+    MidRec *mid = reinterpret_cast<MidRec *>(p);
+    k_matrix_sides<<<unsigned((n + 255) / 256), 256, 0, s>>>(t->view, d_ids, n, row_begin, row_end, rd, pcol,
+                                                            scol, prow, srow);
+    k_matrix_mid<<<unsigned((n_rt * n_ct + 255) / 256), 256, 0, s>>>(t->view, d_ids, n, row_begin, row_end,
+                                                                    int32_t(n_rt), int32_t(n_ct), mid);
+    mt = MatTables{rd, pcol, scol, prow, srow, mid, int32_t(n_ct)};
+    k_matrix_ordered<<<grid, MT, 0, s>>>(t->view, d_ids, mt, n, row_begin, row_end, d_out);
+    k_matrix_generic<true><<<dim3(2, grid.y), MT, 0, s>>>(t->view, d_ids, n, row_begin, row_end, d_out);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(base, s);
+    if (e != cudaSuccess) {
+        st_set_error("st_distance_matrix: launch failed: %s", cudaGetErrorString(e));
+        return ST_ERR_CUDA;
+    }
     return ST_OK;
 }
 
