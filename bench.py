@@ -527,7 +527,7 @@ def run_other_workloads(args, rank, world, local, dev, peak):
     def mat():
         _lib.check(_lib.lib().st_distance_matrix(T._handle, None, n, rb, re_, block.data_ptr(), 1, sptr))
 
-    sec = max_over_ranks(_timed(stream, mat, steps=5))
+    sec = max_over_ranks(_timed(stream, mat, steps=10))
     elems = (re_ - rb) * n
     # spot check against the pair kernel (same index): 4096 random elements of the block
     g = torch.Generator(device="cpu").manual_seed(11 + rank)
@@ -538,10 +538,12 @@ def run_other_workloads(args, rank, world, local, dev, peak):
     T.distances_device(chk_pairs.data_ptr(), 4096, chk.data_ptr(), idx_bits=32, stream=sptr)
     torch.cuda.synchronize()
     same = bool(torch.equal(block[ri.to(dev), ci.to(dev)], chk))
+    fill_sec = _timed(stream, lambda: block.fill_(1.0), steps=10)  # plain write of the same bytes
     res["cfg5_matrix"] = {
         "workload": "rows [%d,%d) of the 100k x 100k all-leaves fp64 matrix per GPU, device-resident" % (rb, re_),
         "elements_per_s": world * elems / sec, "ms_per_block": sec * 1e3, "bytes_written_per_gpu": 8 * elems,
         "hbm_frac": 8.0 * elems / sec / 1e9 / peak, "matches_pair_kernel_on_4096_samples": same,
+        "plain_fill_gbs": 8.0 * elems / fill_sec / 1e9, "frac_of_plain_fill": fill_sec / sec,
     }
     del block
     torch.cuda.empty_cache()

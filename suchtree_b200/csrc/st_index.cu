@@ -339,6 +339,14 @@ extern "C" int st_tree_create(int device, int64_t n_nodes, const int32_t *parent
         return ST_ERR_CUDA;
     }
     t->sm_count = prop.multiProcessorCount;
+    {   // stream-ordered scratch (matrix set-up tables) should be recycled, not returned
+        // to the driver at every synchronisation
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            uint64_t keep = uint64_t(1) << 30;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
 
     // block geometry: smallest power-of-two block (>= micro block) with <= ST_MAX_BLOCKS blocks
     const int32_t n = int32_t(n_nodes);

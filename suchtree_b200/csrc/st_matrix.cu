@@ -154,19 +154,130 @@ __device__ __forceinline__ void mat_apply_mid(SideRec &s, dd plain, uint32_t mde
     }
 }
 
+// ------------------------------------------------ tiles on the diagonal -----
+// grid = (2, row tiles): CTA x handles the x-th column tile overlapping its row tile
+// [r0,r1).  Columns left of r0 are a low side against the rows (split point between
+// indices r0-1 and r0), columns from r1 on a high side (split between r1-1 and r1):
+// both use the rows' precomputed prow/srow tables and two in-kernel queries per
+// column.  Only the <= TR x TR block on the diagonal itself takes per-element
+// queries, spread over all threads of the CTA.
+__global__ void __launch_bounds__(MT)
+k_matrix_diag(const TreeView tv, const int32_t *__restrict__ ids, const MatTables mt, int64_t n,
+              int64_t row_begin, int64_t row_end, double *__restrict__ out) {
+    __shared__ double s_hch[TR], s_hcl[TR], s_lch[TR], s_lcl[TR], s_ph[TR], s_pl[TR];
+    __shared__ uint32_t s_hdep[TR], s_ldep[TR];
+    __shared__ int32_t s_id[TR];
+    __shared__ uint64_t s_suf[TR], s_pre[TR];
+    __shared__ MidRec s_mid[2];
+
+    const int64_t r0 = row_begin + int64_t(blockIdx.y) * TR;
+    const int rows = int(row_end - r0 < TR ? row_end - r0 : TR);
+    if (rows <= 0) return;
+    const int64_t r1 = r0 + rows;
+    const int64_t c0 = (r0 / TC + blockIdx.x) * TC;
+    if (c0 >= n || c0 >= r1) return;
+    const int64_t c1 = c0 + TC < n ? c0 + TC : n;
+    const int t = threadIdx.x;
+
+    if (t < 2) {  // middle ranges of the two split points
+        MidRec m{0.0, 0.0, 0u, 0u, 0ull};
+        const int64_t lowmax = t == 0 ? r0 - 1 : r1 - 1;
+        if (lowmax >= 0 && lowmax + 1 < n) {
+            const uint64_t k = mat_query(tv, mat_id(ids, lowmax), mat_id(ids, lowmax + 1));
+            const dd r = st_ld_rd(tv.rec + st_key_id(k));
+            m = MidRec{r.hi, r.lo, uint32_t(k >> 32), 1u, 0ull};
+        }
+        s_mid[t] = m;
+    }
+    __syncthreads();
+    if (t < rows) {
+        const int64_t k = r0 + t;
+        const int32_t id = mat_id(ids, k);
+        const RecRaw r = st_ld_rec(tv.rec + id);
+        s_id[t] = id; s_suf[t] = r.suf; s_pre[t] = r.pre;
+        s_ph[t] = r.rd_hi; s_pl[t] = r.rd_lo;
+        const SideRec h = ld_side(mt.prow + (k - row_begin));  // rows as the high side
+        s_hdep[t] = h.depth; s_hch[t] = h.comb_hi; s_hcl[t] = h.comb_lo;
+        SideRec l = ld_side(mt.srow + (k - row_begin));        // rows as the low side
+        const MidRec m = s_mid[1];
+        if (m.valid) mat_apply_mid(l, dd{r.rd_hi, r.rd_lo}, m.depth, dd{m.rd_hi, m.rd_lo});
+        s_ldep[t] = l.depth; s_lch[t] = l.comb_hi; s_lcl[t] = l.comb_lo;
+    }
+    // this thread's two columns: 0 = on the diagonal block, 1 = low side (left), 2 = high side (right)
+    const int64_t cA = c0 + 2 * t;
+    SideRec sd[2];
+    dd pl[2];
+    int role[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int64_t c = cA + h;
+        role[h] = 0;
+        sd[h] = SideRec{0.0, 0.0, 0u, 0u, 0ull};
+        pl[h] = dd{0.0, 0.0};
+        if (c >= c1) { role[h] = -1; continue; }
+        if (c >= r0 && c < r1) continue;
+        const int32_t id = mat_id(ids, c);
+        pl[h] = st_ld_rd(tv.rec + id);
+        if (c < r0) {
+            role[h] = 1;
+            sd[h] = mat_side(tv, pl[h], id, mat_id(ids, r0 - 1));
+            const MidRec m = s_mid[0];
+            mat_apply_mid(sd[h], pl[h], m.depth, dd{m.rd_hi, m.rd_lo});
+        } else {
+            role[h] = 2;
+            sd[h] = mat_side(tv, pl[h], mat_id(ids, r1), id);
+        }
+    }
+    __syncthreads();
+    double *orow = out + (r0 - row_begin) * n;
+    for (int i = 0; i < rows; ++i) {
+        const dd rp{s_ph[i], s_pl[i]};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (role[h] <= 0) continue;
+            double v;
+            if (role[h] == 1) {  // column low, row high: low combined iff coldepth <= rowdepth
+                v = sd[h].depth <= s_hdep[i] ? dd_add_to_double(dd{sd[h].comb_hi, sd[h].comb_lo}, rp)
+                                             : dd_add_to_double(pl[h], dd{s_hch[i], s_hcl[i]});
+            } else {             // row low, column high
+                v = s_ldep[i] <= sd[h].depth ? dd_add_to_double(dd{s_lch[i], s_lcl[i]}, pl[h])
+                                             : dd_add_to_double(rp, dd{sd[h].comb_hi, sd[h].comb_lo});
+            }
+            st_st_stream_f64(orow + int64_t(i) * n + cA + h, v);
+        }
+    }
+    // the block on the diagonal: rows x [d0, d1), per-element queries, all threads
+    const int64_t d0 = r0 > c0 ? r0 : c0, d1 = r1 < c1 ? r1 : c1;
+    const int dcols = int(d1 - d0);
+    if (dcols <= 0) return;
+    SmemTables g{tv.stk, tv.brd};
+    for (int e = t; e < rows * dcols; e += MT) {
+        const int i = e / dcols, j = e % dcols;
+        const int jr = int(d0 - r0) + j;  // the column's index among this tile's rows
+        const int32_t rid = s_id[i], cid = s_id[jr];
+        double v = 0.0;
+        if (rid != cid) {
+            bool ft;
+            const bool row_lo = rid < cid;
+            const int a = row_lo ? i : jr, b = row_lo ? jr : i;  // a: low id, b: high id
+            const uint64_t key = st_rmq(tv, g, s_id[a], s_id[b], s_suf[a], s_pre[b], &ft);
+            const dd rm = st_ld_rd(tv.rec + st_key_id(key));
+            v = st_patristic(dd{s_ph[a], s_pl[a]}, dd{s_ph[b], s_pl[b]}, rm);
+        }
+        st_st_stream_f64(orow + int64_t(i) * n + d0 + j, v);
+    }
+}
+
 // ---------------------------------------------------- generic (slow) tile ---
 // per-element RMQ + one rd gather: diagonal tiles and unsorted id lists
-// DIAG_ONLY: grid = (2, row tiles); CTA x handles the x-th column tile that overlaps its
-// row tile (ascending lists: the ordered kernel has written everything else).
-template <bool DIAG_ONLY>
 __global__ void __launch_bounds__(MT)
 k_matrix_generic(const TreeView tv, const int32_t *__restrict__ ids, int64_t n, int64_t row_begin,
                  int64_t row_end, double *__restrict__ out) {
     const int64_t r0 = row_begin + int64_t(blockIdx.y) * TR;
     const int rows = int(row_end - r0 < TR ? row_end - r0 : TR);
     if (rows <= 0) return;
-    const int64_t c0 = DIAG_ONLY ? (r0 / TC + blockIdx.x) * TC : int64_t(blockIdx.x) * TC;
-    if (c0 >= n || (DIAG_ONLY && c0 >= r0 + rows)) return;
+    const int64_t c0 = int64_t(blockIdx.x) * TC;
+    if (c0 >= n) return;
     const int64_t c1 = c0 + TC < n ? c0 + TC : n;
     __shared__ int32_t s_id[TR];
     __shared__ double s_ph[TR], s_pl[TR];
@@ -232,7 +343,7 @@ k_matrix_ordered(const TreeView tv, const int32_t *__restrict__ ids, const MatTa
     const int t = threadIdx.x;
 
     // rows are the low side (above the diagonal), or the columns are; tiles that
-    // overlap the diagonal belong to k_matrix_generic
+    // overlap the diagonal belong to k_matrix_diag
     if (!(r1 <= c0) && !(c1 <= r0)) return;
     const bool rows_low = r1 <= c0;
     const MidRec mid = mt.mid[int64_t(blockIdx.y) * mt.n_ct + blockIdx.x];
@@ -324,7 +435,7 @@ static int launch_matrix(const st_tree *t, const int32_t *d_ids, bool sorted, in
     }
     MatTables mt{};
     if (!sorted) {
-        k_matrix_generic<false><<<grid, MT, 0, s>>>(t->view, d_ids, n, row_begin, row_end, d_out);
+        k_matrix_generic<<<grid, MT, 0, s>>>(t->view, d_ids, n, row_begin, row_end, d_out);
         ST_CUDA(cudaGetLastError());
         return ST_OK;
     }
@@ -348,7 +459,7 @@ static int launch_matrix(const st_tree *t, const int32_t *d_ids, bool sorted, in
                                                                     int32_t(n_rt), int32_t(n_ct), mid);
     mt = MatTables{rd, pcol, scol, prow, srow, mid, int32_t(n_ct)};
     k_matrix_ordered<<<grid, MT, 0, s>>>(t->view, d_ids, mt, n, row_begin, row_end, d_out);
-    k_matrix_generic<true><<<dim3(2, grid.y), MT, 0, s>>>(t->view, d_ids, n, row_begin, row_end, d_out);
+    k_matrix_diag<<<dim3(2, grid.y), MT, 0, s>>>(t->view, d_ids, mt, n, row_begin, row_end, d_out);
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(base, s);
     if (e != cudaSuccess) {
