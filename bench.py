@@ -569,7 +569,7 @@ def run_other_workloads(args, rank, world, local, dev, peak):
     sample()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    reps = 3
+    reps = 10
     for _ in range(reps):
         m = sample()
     sec = max_over_ranks((time.perf_counter() - t0) / reps)

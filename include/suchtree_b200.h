@@ -60,6 +60,8 @@ typedef struct st_tree_info {
     int64_t index_bytes;  /* device bytes held by the index */
     int32_t query_smem_bytes;
     int32_t sm_count;
+    int32_t layout;       /* 0 = wide records (32 B/node, double-double root distance),
+                             1 = compact records (16 B/node; every root distance exact in fp64) */
 } st_tree_info;
 
 /* thread-local text of the last error raised on this thread ("" if none) */
@@ -82,6 +84,13 @@ ST_API int st_device_count(int *count);
 ST_API int st_tree_create(int device, int64_t n_nodes, const int32_t *parent, const int32_t *left,
                    const int32_t *right, const float *edge_len, int block_shift, int micro_shift,
                    st_tree **out);
+/* same, with flags: ST_TREE_WIDE_LAYOUT keeps the 32-byte records even when the
+ * compact 16-byte layout (chosen automatically when every root distance is exact
+ * in fp64; results are bit-identical either way) would apply. */
+#define ST_TREE_WIDE_LAYOUT 1
+ST_API int st_tree_create_ex(int device, int64_t n_nodes, const int32_t *parent, const int32_t *left,
+                      const int32_t *right, const float *edge_len, int block_shift, int micro_shift,
+                      int flags, st_tree **out);
 ST_API void st_tree_destroy(st_tree *tree);
 ST_API int st_tree_get_info(const st_tree *tree, st_tree_info *info);
 /* copies the device-built per-node arrays back (any pointer may be NULL):

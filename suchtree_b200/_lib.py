@@ -34,6 +34,7 @@ class TreeInfo(C.Structure):
         ("index_bytes", C.c_int64),
         ("query_smem_bytes", C.c_int32),
         ("sm_count", C.c_int32),
+        ("layout", C.c_int32),
     ]
 
 
@@ -51,6 +52,7 @@ SIGNATURES = {
     "st_version": (_int, []),
     "st_device_count": (_int, [C.POINTER(_int)]),
     "st_tree_create": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _int, _int, C.POINTER(_vp)]),
+    "st_tree_create_ex": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _int, _int, _int, C.POINTER(_vp)]),
     "st_tree_destroy": (None, [_vp]),
     "st_tree_get_info": (_int, [_vp, C.POINTER(TreeInfo)]),
     "st_tree_export": (_int, [_vp, _vp, _vp, _vp]),

@@ -90,35 +90,62 @@ __device__ __forceinline__ void st_st_stream_i32(int32_t *p, int32_t a) {
                  "l"(st_policy_evict_first())
                  : "memory");
 }
-// one 32-byte node record = one sector, fetched with ONE 256-bit load
-// (ld.global.v4.b64, sm_100+), marked evict-last so the index outlives the streams in L2
+// Layout mode of the accessors below: 0 = wide records (32 B, double-double rd,
+// 64-bit keys), 1 = compact records (16 B), 2 = decided at run time from tv.compact
+// (kernels off the headline path).
+template <int M>
+__device__ __forceinline__ bool st_compact(const TreeView &tv) {
+    return M == 2 ? tv.compact != 0 : M == 1;
+}
+
+// one node record = one sector (or half of one), fetched with ONE 256-bit load
+// (ld.global.v4.b64, sm_100+) or one 128-bit load, marked evict-last so the index
+// outlives the streams in L2.  Compact keys are widened to the common form.
 struct RecRaw {
     double rd_hi, rd_lo;
     uint64_t suf, pre;
 };
-__device__ __forceinline__ RecRaw st_ld_rec(const NodeRec *p) {
+template <int M = 2>
+__device__ __forceinline__ RecRaw st_ld_rec(const TreeView &tv, int32_t id) {
     RecRaw r;
     uint64_t a, b;
-    asm volatile("ld.global.nc.L2::evict_last.v4.b64 {%0,%1,%2,%3}, [%4];"
-                 : "=l"(a), "=l"(b), "=l"(r.suf), "=l"(r.pre)
-                 : "l"(p));
+    if (st_compact<M>(tv)) {
+        asm volatile("ld.global.nc.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(tv.rec16 + id));
+        const uint32_t mask = (1u << tv.block_shift) - 1u, base = uint32_t(id) & ~mask;
+        const uint32_t sf = uint32_t(b), pr = uint32_t(b >> 32);
+        r.rd_lo = 0.0;
+        r.suf = (uint64_t(sf >> tv.block_shift) << 32) | (base + (sf & mask));
+        r.pre = (uint64_t(pr >> tv.block_shift) << 32) | (base + (pr & mask));
+    } else {
+        asm volatile("ld.global.nc.L2::evict_last.v4.b64 {%0,%1,%2,%3}, [%4];"
+                     : "=l"(a), "=l"(b), "=l"(r.suf), "=l"(r.pre)
+                     : "l"(tv.rec + id));
+        r.rd_lo = __longlong_as_double((long long)b);
+    }
     r.rd_hi = __longlong_as_double((long long)a);
-    r.rd_lo = __longlong_as_double((long long)b);
     return r;
 }
-__device__ __forceinline__ dd st_ld_rd(const NodeRec *p) {
-    double2 a = __ldg(reinterpret_cast<const double2 *>(p));
+template <int M = 2>
+__device__ __forceinline__ dd st_ld_rd(const TreeView &tv, int32_t id) {
+    if (st_compact<M>(tv)) return dd{__ldg(&tv.rec16[id].rd), 0.0};
+    double2 a = __ldg(reinterpret_cast<const double2 *>(tv.rec + id));
     return dd{a.x, a.y};
 }
 
 // ------------------------------------------------------------- RMQ ----------
 // Block-level tables (shared memory in the query kernels, global memory in the
-// matrix kernel's few set-up queries): sparse table of packed keys over blocks and
-// the root distance of every block minimum.
+// matrix kernels' few set-up queries): sparse table of keys over blocks and the
+// root distance of every block minimum.
 struct SmemTables {
-    const uint64_t *stk;  // [levels][n_blocks]
-    const double2 *brd;   // [n_blocks]
+    const uint64_t *stk;   // wide: [levels][n_blocks] (depth << 32 | id)
+    const double2 *brd;    // wide: [n_blocks]
+    const uint32_t *stk32; // compact: [levels][n_blocks] (depth << table_shift | block)
+    const double *brd8;    // compact: [n_blocks]
+    const int32_t *bid;    // compact: [n_blocks]
 };
+__device__ __forceinline__ SmemTables st_global_tables(const TreeView &tv) {
+    return SmemTables{tv.stk, tv.brd, tv.stk32, tv.brd8, tv.bid};
+}
 
 __device__ __forceinline__ uint64_t st_scan_depth(const int32_t *__restrict__ depth, int32_t s,
                                                   int32_t e) {
@@ -149,7 +176,10 @@ static __device__ __noinline__ uint64_t st_rmq_inblock(const int32_t *__restrict
 
 // key of the MRCA given both endpoint records (already loaded).  *from_table is set
 // when the winner is a block minimum taken from the block table: its root distance
-// is then tables.brd[id >> block_shift] and no third gather is needed.
+// and id then come from the table (st_mrca_rd / st_mrca_id) and no third gather is
+// needed.  The low word of the returned key is the node id, except for a compact
+// table winner, where it is the BLOCK index.
+template <int M = 2>
 __device__ __forceinline__ uint64_t st_rmq(const TreeView &tv, const SmemTables &sm, int32_t lo,
                                            int32_t hi, uint64_t suf_lo, uint64_t pre_hi,
                                            bool *from_table) {
@@ -160,40 +190,74 @@ __device__ __forceinline__ uint64_t st_rmq(const TreeView &tv, const SmemTables 
     int32_t span = bhi - blo - 1;
     if (span > 0) {
         int k = 31 - __clz(span);
-        const uint64_t *lvl = sm.stk + k * tv.n_blocks;
-        uint64_t mid = st_min64(lvl[blo + 1], lvl[bhi - (1 << k)]);
-        if (mid < best) {
-            best = mid;
-            *from_table = true;
+        if (st_compact<M>(tv)) {
+            const uint32_t *lvl = sm.stk32 + k * tv.n_blocks;
+            const uint32_t mid = min(lvl[blo + 1], lvl[bhi - (1 << k)]);
+            // candidates are distinct nodes and the minimum depth is unique: no ties
+            if ((mid >> tv.table_shift) < uint32_t(best >> 32)) {
+                best = (uint64_t(mid >> tv.table_shift) << 32) | (mid & ((1u << tv.table_shift) - 1u));
+                *from_table = true;
+            }
+        } else {
+            const uint64_t *lvl = sm.stk + k * tv.n_blocks;
+            uint64_t mid = st_min64(lvl[blo + 1], lvl[bhi - (1 << k)]);
+            if (mid < best) {
+                best = mid;
+                *from_table = true;
+            }
         }
     }
     return best;
 }
 
-// root distance of the MRCA: shared-memory copy for block minima, one gather otherwise
+// root distance of the MRCA: table copy for block minima, one gather otherwise
+template <int M = 2>
 __device__ __forceinline__ dd st_mrca_rd(const TreeView &tv, const SmemTables &sm, uint64_t key,
                                          bool from_table) {
     int32_t id = st_key_id(key);
     if (from_table) {
+        if (st_compact<M>(tv)) return dd{sm.brd8[id], 0.0};
         double2 r = sm.brd[id >> tv.block_shift];
         return dd{r.x, r.y};
     }
-    return st_ld_rd(tv.rec + id);
+    return st_ld_rd<M>(tv, id);
+}
+// node id of the MRCA
+template <int M = 2>
+__device__ __forceinline__ int32_t st_mrca_id(const TreeView &tv, const SmemTables &sm, uint64_t key,
+                                              bool from_table) {
+    if (from_table && st_compact<M>(tv)) return sm.bid[st_key_id(key)];
+    return st_key_id(key);
 }
 
-__host__ __device__ __forceinline__ int st_table_bytes(int n_blocks, int st_levels) {
-    return n_blocks * (8 * st_levels + 16);
+__host__ __device__ __forceinline__ int st_table_bytes(int n_blocks, int st_levels, int compact) {
+    return compact ? n_blocks * (4 * st_levels + 12) : n_blocks * (8 * st_levels + 16);
 }
 
 // cooperative copy of the block tables into dynamic shared memory (16-byte aligned)
+template <int M = 2>
 __device__ __forceinline__ SmemTables st_load_tables(const TreeView &tv, unsigned char *smem) {
-    double2 *brd = reinterpret_cast<double2 *>(smem);
-    uint64_t *stk = reinterpret_cast<uint64_t *>(brd + tv.n_blocks);
-    for (int i = threadIdx.x; i < tv.n_blocks; i += blockDim.x) brd[i] = tv.brd[i];
-    int tot = tv.st_levels * tv.n_blocks;
-    for (int i = threadIdx.x; i < tot; i += blockDim.x) stk[i] = tv.stk[i];
+    SmemTables sm{nullptr, nullptr, nullptr, nullptr, nullptr};
+    const int nb = tv.n_blocks, tot = tv.st_levels * nb;
+    if (st_compact<M>(tv)) {
+        double *brd8 = reinterpret_cast<double *>(smem);
+        int32_t *bid = reinterpret_cast<int32_t *>(brd8 + nb);
+        uint32_t *stk32 = reinterpret_cast<uint32_t *>(bid + nb);
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+            brd8[i] = tv.brd8[i];
+            bid[i] = tv.bid[i];
+        }
+        for (int i = threadIdx.x; i < tot; i += blockDim.x) stk32[i] = tv.stk32[i];
+        sm.stk32 = stk32; sm.brd8 = brd8; sm.bid = bid;
+    } else {
+        double2 *brd = reinterpret_cast<double2 *>(smem);
+        uint64_t *stk = reinterpret_cast<uint64_t *>(brd + nb);
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) brd[i] = tv.brd[i];
+        for (int i = threadIdx.x; i < tot; i += blockDim.x) stk[i] = tv.stk[i];
+        sm.stk = stk; sm.brd = brd;
+    }
     __syncthreads();
-    return SmemTables{stk, brd};
+    return sm;
 }
 
 // ------------------------------------------------------------ Philox --------

@@ -170,6 +170,39 @@ __global__ void k_micro_level(int32_t n_micro, int half, const uint64_t *__restr
     cur[j] = st_min64(prev[j], prev[min(j + half, n_micro - 1)]);
 }
 
+// ------------------------------------------------------------ compaction ----
+__global__ void k_any_nonzero(int32_t n, const double *__restrict__ v, int *__restrict__ flag) {
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && v[i] != 0.0) *flag = 1;
+}
+
+__global__ void k_compact_records(int32_t n, int bs, const NodeRec *__restrict__ rec,
+                                  NodeRec16 *__restrict__ rec16) {
+    int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const NodeRec r = rec[v];
+    const uint32_t mask = (1u << bs) - 1u;
+    NodeRec16 c;
+    c.rd = r.rd_hi;
+    c.suf = (uint32_t(r.suf >> 32) << bs) | (uint32_t(r.suf) & mask);
+    c.pre = (uint32_t(r.pre >> 32) << bs) | (uint32_t(r.pre) & mask);
+    rec16[v] = c;
+}
+
+__global__ void k_compact_tables(int nb, int levels, int bs, int ts, const uint64_t *__restrict__ stk,
+                                 const double2 *__restrict__ brd, uint32_t *__restrict__ stk32,
+                                 double *__restrict__ brd8, int32_t *__restrict__ bid) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < levels * nb) {
+        const uint64_t k = stk[i];
+        stk32[i] = (uint32_t(k >> 32) << ts) | (uint32_t(k) >> bs);
+    }
+    if (i < nb) {
+        brd8[i] = brd[i].x;
+        bid[i] = st_key_id(stk[i]);
+    }
+}
+
 // ------------------------------------------------------------ validation ----
 // Host check that (parent,left,right) describe ONE strictly binary tree whose
 // ids are in-order ranks (the property every query relies on).  Iterative.
@@ -277,6 +310,10 @@ extern "C" void st_tree_destroy(st_tree *t) {
     if (!t) return;
     DeviceGuard g(t->device);
     cudaFree(t->d_rec);
+    cudaFree(t->d_rec16);
+    cudaFree(t->d_stk32);
+    cudaFree(t->d_brd8);
+    cudaFree(t->d_bid);
     cudaFree(t->d_depth);
     cudaFree(t->d_stk);
     cudaFree(t->d_brd);
@@ -296,6 +333,13 @@ extern "C" void st_tree_destroy(st_tree *t) {
 extern "C" int st_tree_create(int device, int64_t n_nodes, const int32_t *parent,
                               const int32_t *left, const int32_t *right, const float *edge_len,
                               int block_shift, int micro_shift, st_tree **out) {
+    return st_tree_create_ex(device, n_nodes, parent, left, right, edge_len, block_shift, micro_shift, 0,
+                             out);
+}
+
+extern "C" int st_tree_create_ex(int device, int64_t n_nodes, const int32_t *parent,
+                                 const int32_t *left, const int32_t *right, const float *edge_len,
+                                 int block_shift, int micro_shift, int flags, st_tree **out) {
     if (!out) return ST_ERR_INVALID_ARG;
     *out = nullptr;
     if (!parent || !left || !right || !edge_len || n_nodes < 1) {
@@ -479,10 +523,48 @@ extern "C" int st_tree_create(int device, int64_t n_nodes, const int32_t *parent
                                              t->d_mst + size_t(k) * t->n_micro);
     }
     ST_TRY2_CUDA(cudaGetLastError());
+
+    // ---- compact layout when it loses nothing: every root distance exact in fp64
+    //      (all low words zero) and (depth, offset) / (depth, block) fit 32 bits
+    int ts = 1;
+    while ((1 << ts) < t->n_blocks) ++ts;
+    bool want_compact = !(flags & ST_TREE_WIDE_LAYOUT);
+    if (const char *e = getenv("SUCHTREE_B200_LAYOUT")) want_compact = want_compact && e[0] != 'w';
+    if (want_compact && (uint64_t(maxd) >> (32 - std::max(bs, ts))) == 0) {
+        ST_TRY2_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), s));
+        k_any_nonzero<<<grid, TPB, 0, s>>>(n, d_rlo[cur], d_flag);
+        int inexact = 0;
+        ST_TRY2_CUDA(cudaMemcpy(&inexact, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+        if (!inexact) {
+            int64_t cbytes = 0;
+            ST_TRY2(dev_alloc(&t->d_rec16, size_t(n), &cbytes));
+            ST_TRY2(dev_alloc(&t->d_stk32, size_t(t->st_levels) * t->n_blocks, &cbytes));
+            ST_TRY2(dev_alloc(&t->d_brd8, size_t(t->n_blocks), &cbytes));
+            ST_TRY2(dev_alloc(&t->d_bid, size_t(t->n_blocks), &cbytes));
+            k_compact_records<<<grid, TPB, 0, s>>>(n, bs, t->d_rec, t->d_rec16);
+            const int tot = t->st_levels * t->n_blocks;
+            k_compact_tables<<<(tot + TPB - 1) / TPB, TPB, 0, s>>>(t->n_blocks, t->st_levels, bs, ts, t->d_stk,
+                                                                  t->d_brd, t->d_stk32, t->d_brd8, t->d_bid);
+            ST_TRY2_CUDA(cudaGetLastError());
+            ST_TRY2_CUDA(cudaDeviceSynchronize());
+            t->index_bytes += cbytes - int64_t(size_t(n) * sizeof(NodeRec)) -
+                              int64_t(size_t(t->st_levels) * t->n_blocks * 8) - int64_t(size_t(t->n_blocks) * 16);
+            cudaFree(t->d_rec); t->d_rec = nullptr;
+            cudaFree(t->d_stk); t->d_stk = nullptr;
+            cudaFree(t->d_brd); t->d_brd = nullptr;
+            t->compact = 1;
+        }
+    }
     ST_TRY2_CUDA(cudaDeviceSynchronize());
     free_tmp();
 
-    t->query_smem_bytes = st_table_bytes(t->n_blocks, t->st_levels);
+    t->query_smem_bytes = st_table_bytes(t->n_blocks, t->st_levels, t->compact);
+    t->view.rec16 = t->d_rec16;
+    t->view.stk32 = t->d_stk32;
+    t->view.brd8 = t->d_brd8;
+    t->view.bid = t->d_bid;
+    t->view.compact = t->compact;
+    t->view.table_shift = ts;
     t->view.rec = t->d_rec;
     t->view.depth = t->d_depth;
     t->view.stk = t->d_stk;
@@ -517,15 +599,16 @@ extern "C" int st_tree_get_info(const st_tree *t, st_tree_info *info) {
     info->index_bytes = t->index_bytes;
     info->query_smem_bytes = t->query_smem_bytes;
     info->sm_count = t->sm_count;
+    info->layout = t->compact;
     return ST_OK;
 }
 
-__global__ void k_export_rd(int32_t n, const NodeRec *__restrict__ rec, double *__restrict__ hi,
-                            double *__restrict__ lo) {
+__global__ void k_export_rd(const TreeView tv, double *__restrict__ hi, double *__restrict__ lo) {
     int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n) return;
-    if (hi) hi[v] = rec[v].rd_hi;
-    if (lo) lo[v] = rec[v].rd_lo;
+    if (v >= tv.n_nodes) return;
+    const dd r = st_ld_rd(tv, v);
+    if (hi) hi[v] = r.hi;
+    if (lo) lo[v] = r.lo;
 }
 
 extern "C" int st_tree_export(const st_tree *t, int32_t *depth, double *rd_hi, double *rd_lo) {
@@ -541,7 +624,7 @@ extern "C" int st_tree_export(const st_tree *t, int32_t *depth, double *rd_hi, d
             st_set_error("cudaMalloc failed in st_tree_export");
             return ST_ERR_NOMEM;
         }
-        k_export_rd<<<(n + 255) / 256, 256>>>(n, t->d_rec, d_hi, d_lo);
+        k_export_rd<<<(n + 255) / 256, 256>>>(t->view, d_hi, d_lo);
         cudaError_t e = cudaDeviceSynchronize();
         if (e == cudaSuccess && rd_hi) e = cudaMemcpy(rd_hi, d_hi, size_t(n) * 8, cudaMemcpyDeviceToHost);
         if (e == cudaSuccess && rd_lo) e = cudaMemcpy(rd_lo, d_lo, size_t(n) * 8, cudaMemcpyDeviceToHost);

@@ -19,7 +19,7 @@ __device__ __forceinline__ double linked_query(const TreeView &tv, const SmemTab
                                                int32_t b) {
     int32_t lo = min(a, b), hi = max(a, b);
     if (lo == hi) return 0.0;
-    RecRaw l = st_ld_rec(tv.rec + lo), h = st_ld_rec(tv.rec + hi);
+    RecRaw l = st_ld_rec(tv, lo), h = st_ld_rec(tv, hi);
     bool ft;
     uint64_t key = st_rmq(tv, sm, lo, hi, l.suf, h.pre, &ft);
     return st_patristic(dd{l.rd_hi, l.rd_lo}, dd{h.rd_hi, h.rd_lo}, st_mrca_rd(tv, sm, key, ft));
@@ -53,18 +53,22 @@ k_linked(const TreeView tv, const int32_t *__restrict__ col, int64_t k0, int64_t
 }
 
 // ------------------------------------------------------------ link upload ---
+// Stream-ordered allocations (recycled by the device's default pool, see
+// st_tree_create): no driver-level malloc/free on the per-call path.
 struct DevLinks {
     int32_t *col_a = nullptr, *col_b = nullptr;  // linklist[:,1] (TreeA ids), linklist[:,0] (TreeB ids)
     int2 *rows = nullptr;                        // (b, a) per link, for the samplers
+    cudaStream_t stream = nullptr;
     ~DevLinks() {
-        cudaFree(col_a);
-        cudaFree(col_b);
-        cudaFree(rows);
+        if (col_a) cudaFreeAsync(col_a, stream);
+        if (col_b) cudaFreeAsync(col_b, stream);
+        if (rows) cudaFreeAsync(rows, stream);
     }
 };
 
 static int upload_links(const st_tree *ta, const st_tree *tb, const int64_t *linklist, int64_t L,
-                        DevLinks &d) {
+                        DevLinks &d, bool want_cols = true, bool want_rows = true) {
+    d.stream = ta->streams[0];
     std::vector<int32_t> a(L), b(L);
     std::vector<int2> rows(L);
     for (int64_t i = 0; i < L; ++i) {
@@ -83,12 +87,19 @@ static int upload_links(const st_tree *ta, const st_tree *tb, const int64_t *lin
         b[i] = int32_t(vb);
         rows[i] = make_int2(int32_t(vb), int32_t(va));
     }
-    ST_CUDA(cudaMalloc(&d.col_a, size_t(L) * 4));
-    ST_CUDA(cudaMalloc(&d.col_b, size_t(L) * 4));
-    ST_CUDA(cudaMalloc(&d.rows, size_t(L) * 8));
-    ST_CUDA(cudaMemcpy(d.col_a, a.data(), size_t(L) * 4, cudaMemcpyHostToDevice));
-    ST_CUDA(cudaMemcpy(d.col_b, b.data(), size_t(L) * 4, cudaMemcpyHostToDevice));
-    ST_CUDA(cudaMemcpy(d.rows, rows.data(), size_t(L) * 8, cudaMemcpyHostToDevice));
+    cudaStream_t s = d.stream;
+    if (want_cols) {
+        ST_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d.col_a), size_t(L) * 4, s));
+        ST_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d.col_b), size_t(L) * 4, s));
+        ST_CUDA(cudaMemcpyAsync(d.col_a, a.data(), size_t(L) * 4, cudaMemcpyHostToDevice, s));
+        ST_CUDA(cudaMemcpyAsync(d.col_b, b.data(), size_t(L) * 4, cudaMemcpyHostToDevice, s));
+    }
+    if (want_rows) {
+        ST_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d.rows), size_t(L) * 8, s));
+        ST_CUDA(cudaMemcpyAsync(d.rows, rows.data(), size_t(L) * 8, cudaMemcpyHostToDevice, s));
+    }
+    // the host vectors die with this frame: the copies (pageable source) must have left them
+    ST_CUDA(cudaStreamSynchronize(s));
     return ST_OK;
 }
 
@@ -125,7 +136,7 @@ extern "C" int st_linked_distances(const st_tree *ta, const st_tree *tb, const i
     }
     DeviceGuard g(ta->device);
     DevLinks dl;
-    rc = upload_links(ta, tb, linklist, L, dl);
+    rc = upload_links(ta, tb, linklist, L, dl, true, false);
     if (rc != ST_OK) return rc;
     rc = set_smem(k_linked, std::max(ta->query_smem_bytes, tb->query_smem_bytes));
     if (rc != ST_OK) return rc;
@@ -280,7 +291,7 @@ extern "C" int st_sample_linked_cycle(const st_tree *ta, const st_tree *tb, cons
     }
     DeviceGuard g(ta->device);
     DevLinks dl;
-    rc = upload_links(ta, tb, linklist, L, dl);
+    rc = upload_links(ta, tb, linklist, L, dl, false, true);
     if (rc != ST_OK) return rc;
     rc = set_smem(k_sample_xs, std::max(ta->query_smem_bytes, tb->query_smem_bytes));
     if (rc != ST_OK) return rc;
@@ -355,7 +366,7 @@ k_sample_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // two table sets back to back (second one 16-byte aligned)
     const SmemTables sa = st_load_tables(ta, smem_raw);
-    const int offs = (st_table_bytes(ta.n_blocks, ta.st_levels) + 15) & ~15;
+    const int offs = (st_table_bytes(ta.n_blocks, ta.st_levels, ta.compact) + 15) & ~15;
     const SmemTables sb = st_load_tables(tb, smem_raw + offs);
     __shared__ double red[5][MLT / 32];
 
@@ -419,7 +430,7 @@ extern "C" int st_sample_moments(const st_tree *ta, const st_tree *tb, const int
     if (n_samples == 0) return ST_OK;
     DeviceGuard g(ta->device);
     DevLinks dl;
-    rc = upload_links(ta, tb, linklist, L, dl);
+    rc = upload_links(ta, tb, linklist, L, dl, false, true);
     if (rc != ST_OK) return rc;
     const int smem = ((ta->query_smem_bytes + 15) & ~15) + tb->query_smem_bytes;
     rc = set_smem(k_sample_moments, smem);
@@ -429,22 +440,18 @@ extern "C" int st_sample_moments(const st_tree *ta, const st_tree *tb, const int
     if (per_sm < 1) per_sm = 1;
     const int64_t calls = (n_samples + 1) / 2 + 1;
     int grid = int(std::min<int64_t>((calls + MLT - 1) / MLT, int64_t(ta->sm_count) * per_sm));
-    double *d_part = nullptr, *d_out = nullptr;
-    ST_CUDA(cudaMalloc(&d_part, size_t(grid) * 5 * 8));
-    if (cudaMalloc(&d_out, 5 * 8) != cudaSuccess) {
-        cudaFree(d_part);
-        return ST_ERR_NOMEM;
-    }
     cudaStream_t s = ta->streams[0];
+    double *d_part = nullptr;  // [grid][5] partials, then 5 folded sums
+    ST_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d_part), size_t(grid + 1) * 5 * 8, s));
+    double *d_out = d_part + size_t(grid) * 5;
     k_sample_moments<<<grid, MLT, smem, s>>>(ta->view, tb->view, dl.rows, uint32_t(L), seed, first_sample,
                                            n_samples, x0, y0, d_part);
     k_reduce_partials<<<1, 160, 0, s>>>(grid, d_part, d_out);
     double h[5];
     cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, s);
+    cudaFreeAsync(d_part, s);
     cudaError_t e = cudaStreamSynchronize(s);
     if (e == cudaSuccess) e = cudaGetLastError();
-    cudaFree(d_part);
-    cudaFree(d_out);
     if (e != cudaSuccess) {
         st_set_error("st_sample_moments: %s", cudaGetErrorString(e));
         return ST_ERR_CUDA;

@@ -34,10 +34,11 @@ __device__ __forceinline__ int32_t mat_id(const int32_t *__restrict__ ids, int64
 __device__ __forceinline__ uint64_t mat_query(const TreeView &tv, int32_t a, int32_t b) {
     int32_t lo = min(a, b), hi = max(a, b);
     if (lo == hi) return st_key(__ldg(tv.depth + lo), lo);
-    RecRaw rl = st_ld_rec(tv.rec + lo), rh = st_ld_rec(tv.rec + hi);
-    SmemTables g{tv.stk, tv.brd};
+    RecRaw rl = st_ld_rec(tv, lo), rh = st_ld_rec(tv, hi);
+    const SmemTables g = st_global_tables(tv);
     bool ft;
-    return st_rmq(tv, g, lo, hi, rl.suf, rh.pre, &ft);
+    const uint64_t k = st_rmq(tv, g, lo, hi, rl.suf, rh.pre, &ft);
+    return (k & 0xffffffff00000000ull) | uint32_t(st_mrca_id(tv, g, k, ft));  // always (depth, node id)
 }
 
 __device__ __forceinline__ dd dd_minus_2x(dd a, dd m) {  // a - 2m
@@ -92,7 +93,7 @@ struct MatTables {
 
 __device__ __forceinline__ SideRec mat_side(const TreeView &tv, dd rd, int32_t a, int32_t b) {
     const uint64_t k = mat_query(tv, a, b);
-    const dd c = dd_minus_2x(rd, st_ld_rd(tv.rec + st_key_id(k)));
+    const dd c = dd_minus_2x(rd, st_ld_rd(tv, st_key_id(k)));
     return SideRec{c.hi, c.lo, uint32_t(k >> 32), 0u, 0ull};
 }
 
@@ -103,7 +104,7 @@ __global__ void k_matrix_sides(const TreeView tv, const int32_t *__restrict__ id
     const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int32_t id = mat_id(ids, k);
-    const dd rd = st_ld_rd(tv.rec + id);
+    const dd rd = st_ld_rd(tv, id);
     rd_out[k] = make_double2(rd.hi, rd.lo);
     const int64_t c0 = k / TC * TC, c1 = min(c0 + TC, n);
     pcol[k] = mat_side(tv, rd, mat_id(ids, c0), id);
@@ -129,7 +130,7 @@ __global__ void k_matrix_mid(const TreeView tv, const int32_t *__restrict__ ids,
     else if (c1 <= r0) { a = mat_id(ids, c1 - 1); b = mat_id(ids, r0); }
     if (a >= 0) {
         const uint64_t k = mat_query(tv, a, b);
-        const dd r = st_ld_rd(tv.rec + st_key_id(k));
+        const dd r = st_ld_rd(tv, st_key_id(k));
         m = MidRec{r.hi, r.lo, uint32_t(k >> 32), 1u, 0ull};
     }
     mid[q] = m;
@@ -184,7 +185,7 @@ k_matrix_diag(const TreeView tv, const int32_t *__restrict__ ids, const MatTable
         const int64_t lowmax = t == 0 ? r0 - 1 : r1 - 1;
         if (lowmax >= 0 && lowmax + 1 < n) {
             const uint64_t k = mat_query(tv, mat_id(ids, lowmax), mat_id(ids, lowmax + 1));
-            const dd r = st_ld_rd(tv.rec + st_key_id(k));
+            const dd r = st_ld_rd(tv, st_key_id(k));
             m = MidRec{r.hi, r.lo, uint32_t(k >> 32), 1u, 0ull};
         }
         s_mid[t] = m;
@@ -193,7 +194,7 @@ k_matrix_diag(const TreeView tv, const int32_t *__restrict__ ids, const MatTable
     if (t < rows) {
         const int64_t k = r0 + t;
         const int32_t id = mat_id(ids, k);
-        const RecRaw r = st_ld_rec(tv.rec + id);
+        const RecRaw r = st_ld_rec(tv, id);
         s_id[t] = id; s_suf[t] = r.suf; s_pre[t] = r.pre;
         s_ph[t] = r.rd_hi; s_pl[t] = r.rd_lo;
         const SideRec h = ld_side(mt.prow + (k - row_begin));  // rows as the high side
@@ -217,7 +218,7 @@ k_matrix_diag(const TreeView tv, const int32_t *__restrict__ ids, const MatTable
         if (c >= c1) { role[h] = -1; continue; }
         if (c >= r0 && c < r1) continue;
         const int32_t id = mat_id(ids, c);
-        pl[h] = st_ld_rd(tv.rec + id);
+        pl[h] = st_ld_rd(tv, id);
         if (c < r0) {
             role[h] = 1;
             sd[h] = mat_side(tv, pl[h], id, mat_id(ids, r0 - 1));
@@ -250,7 +251,7 @@ k_matrix_diag(const TreeView tv, const int32_t *__restrict__ ids, const MatTable
     const int64_t d0 = r0 > c0 ? r0 : c0, d1 = r1 < c1 ? r1 : c1;
     const int dcols = int(d1 - d0);
     if (dcols <= 0) return;
-    SmemTables g{tv.stk, tv.brd};
+    const SmemTables g = st_global_tables(tv);
     for (int e = t; e < rows * dcols; e += MT) {
         const int i = e / dcols, j = e % dcols;
         const int jr = int(d0 - r0) + j;  // the column's index among this tile's rows
@@ -261,7 +262,7 @@ k_matrix_diag(const TreeView tv, const int32_t *__restrict__ ids, const MatTable
             const bool row_lo = rid < cid;
             const int a = row_lo ? i : jr, b = row_lo ? jr : i;  // a: low id, b: high id
             const uint64_t key = st_rmq(tv, g, s_id[a], s_id[b], s_suf[a], s_pre[b], &ft);
-            const dd rm = st_ld_rd(tv.rec + st_key_id(key));
+            const dd rm = st_mrca_rd(tv, g, key, ft);
             v = st_patristic(dd{s_ph[a], s_pl[a]}, dd{s_ph[b], s_pl[b]}, rm);
         }
         st_st_stream_f64(orow + int64_t(i) * n + d0 + j, v);
@@ -288,16 +289,16 @@ k_matrix_generic(const TreeView tv, const int32_t *__restrict__ ids, int64_t n, 
     const int32_t idA = hasA ? mat_id(ids, cA) : 0, idB = hasB ? mat_id(ids, cB) : 0;
     for (int i = t; i < rows; i += MT) {
         int32_t id = mat_id(ids, r0 + i);
-        RecRaw r = st_ld_rec(tv.rec + id);
+        RecRaw r = st_ld_rec(tv, id);
         s_id[i] = id;
         s_ph[i] = r.rd_hi; s_pl[i] = r.rd_lo;
         s_suf[i] = r.suf;  s_pre[i] = r.pre;
     }
     RecRaw ra{}, rb{};
-    if (hasA) ra = st_ld_rec(tv.rec + idA);
-    if (hasB) rb = st_ld_rec(tv.rec + idB);
+    if (hasA) ra = st_ld_rec(tv, idA);
+    if (hasB) rb = st_ld_rec(tv, idB);
     __syncthreads();
-    SmemTables g{tv.stk, tv.brd};
+    const SmemTables g = st_global_tables(tv);
     for (int i = 0; i < rows; ++i) {
         const int32_t rid = s_id[i];
         const dd rrd{s_ph[i], s_pl[i]};
@@ -311,7 +312,7 @@ k_matrix_generic(const TreeView tv, const int32_t *__restrict__ ids, int64_t n, 
                 bool ft;
                 uint64_t key = rid < cid ? st_rmq(tv, g, rid, cid, s_suf[i], rc.pre, &ft)
                                          : st_rmq(tv, g, cid, rid, rc.suf, s_pre[i], &ft);
-                dd rm = st_ld_rd(tv.rec + st_key_id(key));
+                dd rm = st_mrca_rd(tv, g, key, ft);
                 // low-id operand first, as in the pair kernel
                 v[h] = rid < cid ? st_patristic(rrd, dd{rc.rd_hi, rc.rd_lo}, rm)
                                  : st_patristic(dd{rc.rd_hi, rc.rd_lo}, rrd, rm);

@@ -77,79 +77,75 @@ __device__ __forceinline__ PairQ st_make_query(const TreeView &tv, long long a, 
     return q;
 }
 
-__device__ __forceinline__ uint64_t st_query_key(const TreeView &tv, const SmemTables &sm,
-                                                 const PairQ &q, const RecRaw &rl,
-                                                 const RecRaw &rh, bool *from_table) {
-    *from_table = false;
-    if (q.lo == q.hi) return uint64_t(uint32_t(q.lo));  // MRCA(a,a) = a
-    return st_rmq(tv, sm, q.lo, q.hi, rl.suf, rh.pre, from_table);
+// One pair: both endpoint records, the block table, the distance and/or the MRCA id.
+template <int M>
+__device__ __forceinline__ void st_pair(const TreeView &tv, const SmemTables &sm, const PairQ &q,
+                                        const RecRaw &l, const RecRaw &h, bool want_d, bool want_m,
+                                        double &d, int32_t &m) {
+    bool ft = false;
+    // MRCA(a,a) = a
+    const uint64_t k = q.lo == q.hi ? uint64_t(uint32_t(q.lo))
+                                    : st_rmq<M>(tv, sm, q.lo, q.hi, l.suf, h.pre, &ft);
+    if (want_d) d = st_patristic(dd{l.rd_hi, l.rd_lo}, dd{h.rd_hi, h.rd_lo}, st_mrca_rd<M>(tv, sm, k, ft));
+    if (want_m) m = st_mrca_id<M>(tv, sm, k, ft);
 }
 
-template <typename IdxT, bool VEC>
+template <typename IdxT, bool VEC, int M>
 __global__ void __launch_bounds__(QT, 2)
 k_pairs(const TreeView tv, const IdxT *__restrict__ pairs, int64_t n, double *__restrict__ out,
         int32_t *__restrict__ mrca_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const SmemTables sm = st_load_tables(tv, smem_raw);
+    const SmemTables sm = st_load_tables<M>(tv, smem_raw);
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    const bool want_d = out != nullptr, want_m = mrca_out != nullptr;
 
     if (VEC) {
         const int64_t n2 = n >> 1;  // pair-of-pairs
         for (int64_t i = int64_t(blockIdx.x) * QT + threadIdx.x; i < n2; i += int64_t(gridDim.x) * QT) {
             long long a0, b0, a1, b1;
             PairIO<IdxT>::load2(pairs, 2 * i, a0, b0, a1, b1);
-            PairQ q0 = st_make_query(tv, a0, b0), q1 = st_make_query(tv, a1, b1);
-            RecRaw l0 = st_ld_rec(tv.rec + q0.lo), h0 = st_ld_rec(tv.rec + q0.hi);
-            RecRaw l1 = st_ld_rec(tv.rec + q1.lo), h1 = st_ld_rec(tv.rec + q1.hi);
-            bool t0, t1;
-            const uint64_t k0 = st_query_key(tv, sm, q0, l0, h0, &t0);
-            const uint64_t k1 = st_query_key(tv, sm, q1, l1, h1, &t1);
-            const int32_t m0 = st_key_id(k0), m1 = st_key_id(k1);
-            if (out) {
-                dd r0 = st_mrca_rd(tv, sm, k0, t0), r1 = st_mrca_rd(tv, sm, k1, t1);
-                double d0 = st_patristic(dd{l0.rd_hi, l0.rd_lo}, dd{h0.rd_hi, h0.rd_lo}, r0);
-                double d1 = st_patristic(dd{l1.rd_hi, l1.rd_lo}, dd{h1.rd_hi, h1.rd_lo}, r1);
-                st_st_stream_f64x2(out + 2 * i, q0.bad ? nan : d0, q1.bad ? nan : d1);
-            }
-            if (mrca_out) st_st_stream_i32x2(mrca_out + 2 * i, q0.bad ? -1 : m0, q1.bad ? -1 : m1);
+            const PairQ q0 = st_make_query(tv, a0, b0), q1 = st_make_query(tv, a1, b1);
+            // four independent gathers in flight before anything depends on them
+            const RecRaw l0 = st_ld_rec<M>(tv, q0.lo), h0 = st_ld_rec<M>(tv, q0.hi);
+            const RecRaw l1 = st_ld_rec<M>(tv, q1.lo), h1 = st_ld_rec<M>(tv, q1.hi);
+            double d0 = 0.0, d1 = 0.0;
+            int32_t m0 = 0, m1 = 0;
+            st_pair<M>(tv, sm, q0, l0, h0, want_d, want_m, d0, m0);
+            st_pair<M>(tv, sm, q1, l1, h1, want_d, want_m, d1, m1);
+            if (want_d) st_st_stream_f64x2(out + 2 * i, q0.bad ? nan : d0, q1.bad ? nan : d1);
+            if (want_m) st_st_stream_i32x2(mrca_out + 2 * i, q0.bad ? -1 : m0, q1.bad ? -1 : m1);
         }
         if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
             long long a, b;
             PairIO<IdxT>::load1(pairs, n - 1, a, b);
-            PairQ q = st_make_query(tv, a, b);
-            RecRaw l = st_ld_rec(tv.rec + q.lo), h = st_ld_rec(tv.rec + q.hi);
-            bool ft;
-            const uint64_t k = st_query_key(tv, sm, q, l, h, &ft);
-            const int32_t m = st_key_id(k);
-            if (out) {
-                double d = st_patristic(dd{l.rd_hi, l.rd_lo}, dd{h.rd_hi, h.rd_lo}, st_mrca_rd(tv, sm, k, ft));
-                out[n - 1] = q.bad ? nan : d;
-            }
-            if (mrca_out) mrca_out[n - 1] = q.bad ? -1 : m;
+            const PairQ q = st_make_query(tv, a, b);
+            const RecRaw l = st_ld_rec<M>(tv, q.lo), h = st_ld_rec<M>(tv, q.hi);
+            double d = 0.0;
+            int32_t m = 0;
+            st_pair<M>(tv, sm, q, l, h, want_d, want_m, d, m);
+            if (want_d) out[n - 1] = q.bad ? nan : d;
+            if (want_m) mrca_out[n - 1] = q.bad ? -1 : m;
         }
     } else {
         for (int64_t i = int64_t(blockIdx.x) * QT + threadIdx.x; i < n; i += int64_t(gridDim.x) * QT) {
             long long a, b;
             PairIO<IdxT>::load1(pairs, i, a, b);
-            PairQ q = st_make_query(tv, a, b);
-            RecRaw l = st_ld_rec(tv.rec + q.lo), h = st_ld_rec(tv.rec + q.hi);
-            bool ft;
-            const uint64_t k = st_query_key(tv, sm, q, l, h, &ft);
-            const int32_t m = st_key_id(k);
-            if (out) {
-                double d = st_patristic(dd{l.rd_hi, l.rd_lo}, dd{h.rd_hi, h.rd_lo}, st_mrca_rd(tv, sm, k, ft));
-                st_st_stream_f64(out + i, q.bad ? nan : d);
-            }
-            if (mrca_out) st_st_stream_i32(mrca_out + i, q.bad ? -1 : m);
+            const PairQ q = st_make_query(tv, a, b);
+            const RecRaw l = st_ld_rec<M>(tv, q.lo), h = st_ld_rec<M>(tv, q.hi);
+            double d = 0.0;
+            int32_t m = 0;
+            st_pair<M>(tv, sm, q, l, h, want_d, want_m, d, m);
+            if (want_d) st_st_stream_f64(out + i, q.bad ? nan : d);
+            if (want_m) st_st_stream_i32(mrca_out + i, q.bad ? -1 : m);
         }
     }
 }
 
 // ------------------------------------------------------------------ launch --
-template <typename IdxT, bool VEC>
-static int launch_variant(const st_tree *t, const void *d_pairs, int64_t n, double *d_out,
+template <typename IdxT, bool VEC, int M>
+static int launch_variant_m(const st_tree *t, const void *d_pairs, int64_t n, double *d_out,
                           int32_t *d_mrca, cudaStream_t stream) {
-    auto kern = k_pairs<IdxT, VEC>;
+    auto kern = k_pairs<IdxT, VEC, M>;
     static thread_local int configured_smem[64] = {0};  // per device, per thread: cheap re-check
     const int smem = t->query_smem_bytes;
     if (smem > 48 * 1024 && configured_smem[t->device & 63] < smem) {
@@ -166,6 +162,13 @@ static int launch_variant(const st_tree *t, const void *d_pairs, int64_t n, doub
     kern<<<grid, QT, smem, stream>>>(t->view, static_cast<const IdxT *>(d_pairs), n, d_out, d_mrca);
     ST_CUDA(cudaGetLastError());
     return ST_OK;
+}
+
+template <typename IdxT, bool VEC>
+static int launch_variant(const st_tree *t, const void *d_pairs, int64_t n, double *d_out,
+                          int32_t *d_mrca, cudaStream_t stream) {
+    return t->compact ? launch_variant_m<IdxT, VEC, 1>(t, d_pairs, n, d_out, d_mrca, stream)
+                      : launch_variant_m<IdxT, VEC, 0>(t, d_pairs, n, d_out, d_mrca, stream);
 }
 
 int st_launch_pairs(const st_tree *t, const void *d_pairs, int idx_bits, int64_t n, double *d_out,

@@ -58,7 +58,7 @@ class SuchTree:
     0), and SuchTree.from_arrays() builds from node arrays directly.
     """
 
-    def __init__(self, tree_input, device=None, _flat=None, _block_shift=0, _micro_shift=0):
+    def __init__(self, tree_input, device=None, _flat=None, _block_shift=0, _micro_shift=0, _wide=False):
         ft = _flat if _flat is not None else newick.flatten(_read_tree_input(tree_input))
         self._ft = ft
         self._epsilon = float(np.finfo(np.float64).eps)  # MuchTree.pyx:136
@@ -73,9 +73,9 @@ class SuchTree:
         left = np.ascontiguousarray(ft.left, np.int32)
         right = np.ascontiguousarray(ft.right, np.int32)
         dist = np.ascontiguousarray(ft.distance, np.float32)
-        rc = L.st_tree_create(
+        rc = L.st_tree_create_ex(
             int(device), int(ft.size), parent.ctypes.data, left.ctypes.data, right.ctypes.data,
-            dist.ctypes.data, int(_block_shift), int(_micro_shift), C.byref(self._handle),
+            dist.ctypes.data, int(_block_shift), int(_micro_shift), 1 if _wide else 0, C.byref(self._handle),
         )
         _lib.check(rc)
         info = _lib.TreeInfo()

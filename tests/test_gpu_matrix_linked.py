@@ -57,13 +57,14 @@ def test_matrix_reference_api():
     assert len(nn) == 3 and nn[0][1] <= nn[1][1] <= nn[2][1]
 
 
+@pytest.mark.parametrize("wide", [False, True])
 @pytest.mark.parametrize("gen,n_leaves", [(synth.yule_tree, 3001), (synth.caterpillar_tree, 2500), (synth.balanced_tree, 4096)])
-def test_matrix_mid_size_exact(gen, n_leaves):
+def test_matrix_mid_size_exact(gen, n_leaves, wide):
     """Every tile class (ordered upper/lower, diagonal) against the pair kernel; odd n
     exercises the unaligned store path.  Synthetic edges: exact, so bitwise equality
     and exact symmetry."""
     ft = gen(n_leaves, seed=4)
-    T = SuchTree.from_flat(ft)
+    T = SuchTree.from_flat(ft, _wide=wide)
     D = T.pairwise_distances()
     ids = np.arange(0, 2 * n_leaves, 2, dtype=np.int64)
     want = T.distances_bulk(_pairs_of(ids)).reshape(n_leaves, n_leaves)

@@ -37,10 +37,13 @@ def _all_pairs(n):
     return np.array([(a, b) for a in range(n) for b in range(n)], dtype=np.int64)
 
 
+@pytest.mark.parametrize("wide", [False, True])
 @pytest.mark.parametrize("geom", GEOMETRIES)
-def test_small_trees_against_reference_and_oracle(golden_trees, geom):
+def test_small_trees_against_reference_and_oracle(golden_trees, geom, wide):
+    layouts = set()
     for name, rec in golden_trees.items():
-        T = SuchTree(tree_source(name, rec), _block_shift=geom[0], _micro_shift=geom[1])
+        T = SuchTree(tree_source(name, rec), _block_shift=geom[0], _micro_shift=geom[1], _wide=wide)
+        layouts.add(T.index_info["layout"])
         assert (T.size, T.depth, T.num_leaves, T.root_node) == (
             rec["size"], rec["depth"], rec["num_leaves"], rec["root"]), name
         assert T.leaves == rec["leaves"], name
@@ -60,6 +63,8 @@ def test_small_trees_against_reference_and_oracle(golden_trees, geom):
         pr = np.stack([np.arange(T.size), np.full(T.size, T.root_node)], axis=1).astype(np.int64)
         rd64, rl1 = ot.distances_f64(pr, with_l1=True)
         _check_distances(hi + lo, rd64, rl1, name + " rd")
+    # the fixtures exercise both layouts: epsilon edges force the wide one
+    assert layouts == ({0} if wide else {0, 1})
 
 
 @pytest.mark.parametrize("name", ["ml", "nj"])
@@ -102,11 +107,14 @@ def test_reference_test_matrix():
         (synth.yule_tree, 1000000, 200000, True),        # cfg 3 size
     ],
 )
-def test_synthetic_trees_exact(gen, n_leaves, n_pairs, literal):
+@pytest.mark.parametrize("wide", [False, True])
+def test_synthetic_trees_exact(gen, n_leaves, n_pairs, literal, wide):
     """fp32 edges in [0.5,1): fp64 path sums are exact, so the kernel must agree with
-    the oracle bit for bit, not merely to 1e-12."""
+    the oracle bit for bit, not merely to 1e-12 -- in the compact 16-byte layout the
+    library picks for such trees and in the wide (double-double) layout alike."""
     ft = gen(n_leaves, seed=1)
-    T = SuchTree.from_flat(ft)
+    T = SuchTree.from_flat(ft, _wide=wide)
+    assert T.index_info["layout"] == (0 if wide else 1)
     ot = O.OracleTree(ft.parent, ft.distance)
     assert T.depth == ot.depth
     rng = np.random.default_rng(11)
