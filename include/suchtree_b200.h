@@ -124,6 +124,22 @@ ST_API int st_distances_device(const st_tree *tree, const void *d_pairs, int idx
  * check saw an out-of-range id (st_bad_node() then reports it), and resets. */
 ST_API int st_check_range(const st_tree *tree, void *stream);
 
+/* ---- quartet topologies: replaces SuchTree._quartet_topologies (MuchTree.pyx:1331-1376)
+ *      as called from quartet_topologies_bulk (:1271-1329).
+ * quartets: int64 [n,4] node ids (any nodes, arbitrary order) with element strides
+ * (stride0, stride1); out: int64 [n,4], contiguous: each quartet reordered so that
+ * (out[i,0], out[i,1]) and (out[i,2], out[i,3]) are the sister pairs -- the pair
+ * (of the six, in the order ab ac ad bc bd cd) whose MRCA occurs once among the six
+ * MRCAs comes first; without one the reference's fall-through order (c d a b).
+ * Out-of-range ids -> ST_ERR_NODE_RANGE (st_bad_node(): max id if >= size, else min). */
+ST_API int st_quartet_topologies(const st_tree *tree, const int64_t *quartets, int64_t stride0,
+                          int64_t stride1, int64_t n, int64_t *out);
+/* device-resident variant: d_quartets / d_out contiguous int64 [n,4] on the tree's
+ * device, asynchronous on `stream`; out-of-range ids give a row of -1 and are
+ * reported by the next st_check_range(). */
+ST_API int st_quartet_topologies_device(const st_tree *tree, const int64_t *d_quartets, int64_t n,
+                                 int64_t *d_out, void *stream);
+
 /* deterministic synthetic input: n random leaf-id pairs (ids 2*k, k uniform in
  * [0, n_leaves)), Philox4x32-10 keyed by `seed`, counter = first_pair + i, as
  * int32 (idx_bits = 32) or int64 pairs on the device. */

@@ -39,6 +39,7 @@ def lib():
         L.oracle_distances_f32.argtypes = [i32p, f32p, i64p, i64p, C.c_uint64, f64p]
         L.oracle_distances_f64.argtypes = [i32p, f32p, i64p, i64p, C.c_uint64, f64p, C.c_void_p]
         L.oracle_distances_f64_climb.argtypes = [i32p, i32p, f32p, i64p, C.c_uint64, f64p, C.c_void_p]
+        L.oracle_quartet_topologies.argtypes = [i32p, i64p, i64p, C.c_uint64, i64p]
         L.oracle_tree_depth.restype = C.c_uint
         L.oracle_tree_depth.argtypes = [i32p, i64p, C.c_uint64]
         L.oracle_node_depths.argtypes = [i32p, C.c_uint64, i32p]
@@ -103,6 +104,14 @@ class OracleTree:
         ids = _pairs(ids)
         out = np.empty(ids.shape[0], np.int32)
         lib().oracle_mrca_bulk(self.parent, self._visited(), ids, ids.shape[0], out)
+        return out
+
+    def quartet_topologies(self, quartets):
+        """MuchTree.pyx:1331-1376."""
+        q = np.ascontiguousarray(quartets, dtype=np.int64)
+        assert q.ndim == 2 and q.shape[1] == 4
+        out = np.zeros_like(q)
+        lib().oracle_quartet_topologies(self.parent, self._visited(), q, q.shape[0], out)
         return out
 
     def distances_f32(self, ids):

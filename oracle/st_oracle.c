@@ -93,6 +93,38 @@ void oracle_distances_f64(const int32_t *parent, const float *dist, int64_t *vis
     }
 }
 
+/* ---- MuchTree.pyx:1331-1376  _quartet_topologies ---------------------------
+ * Six MRCAs per quartet (a,b),(a,c),(a,d),(b,c),(b,d),(c,d); C[j] = how many of
+ * the six equal M[j]; j = first index with C[j] == 1 (5 if there is none: the
+ * loop variable keeps its last value); row i of the output is the quartet
+ * permuted by row j of the table I (:1319-1320; named PERM here, complex.h owns I).  `cdef int a, b, c, d` truncates the ids. */
+void oracle_quartet_topologies(const int32_t *parent, int64_t *visited, const int64_t *quartets,
+                               uint64_t n, int64_t *topologies)
+{
+    static const int PERM[6][4] = {{0, 1, 2, 3}, {0, 2, 1, 3}, {0, 3, 1, 2},
+                                {1, 2, 0, 3}, {1, 3, 0, 2}, {2, 3, 0, 1}};
+    int64_t M[6], C[6];
+    for (uint64_t i = 0; i < n; ++i) {
+        int a = (int)quartets[4 * i], b = (int)quartets[4 * i + 1];
+        int c = (int)quartets[4 * i + 2], d = (int)quartets[4 * i + 3];
+        int j, k;
+        M[0] = oracle_mrca(parent, visited, a, b);
+        M[1] = oracle_mrca(parent, visited, a, c);
+        M[2] = oracle_mrca(parent, visited, a, d);
+        M[3] = oracle_mrca(parent, visited, b, c);
+        M[4] = oracle_mrca(parent, visited, b, d);
+        M[5] = oracle_mrca(parent, visited, c, d);
+        for (j = 0; j < 6; ++j) C[j] = 0;
+        for (j = 0; j < 6; ++j)
+            for (k = 0; k < 6; ++k)
+                if (M[j] == M[k]) C[j] = C[j] + 1;
+        for (j = 0; j < 6; ++j)
+            if (C[j] == 1) break;
+        if (j == 6) j = 5; /* Cython's `for j in range(6)` leaves j at 5 without a break */
+        for (k = 0; k < 4; ++k) topologies[4 * i + k] = quartets[4 * i + PERM[j][k]];
+    }
+}
+
 /* ---- NOT a restatement: O(depth) MRCA by depth-levelled climbing, for trees
  * on which the reference's O(depth^2) scan cannot finish (10^6-deep
  * caterpillar).  Cross-checked against oracle_mrca on every

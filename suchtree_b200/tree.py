@@ -378,6 +378,81 @@ class SuchTree:
         _lib.check(rc, self.size)
         return out
 
+    # ====== quartet topologies (MuchTree.pyx:1203-1421) ======
+    def quartet_topologies_bulk(self, quartets):
+        """(n,4) node ids in arbitrary order -> (n,4) int64 rows ordered so that
+        {row[0],row[1]} and {row[2],row[3]} are the sister pairs; MuchTree.pyx:1271-1329.
+        Six range-minimum MRCA lookups per quartet on the GPU."""
+        if not isinstance(quartets, np.ndarray):
+            quartets = np.array(quartets, dtype=np.int64)
+        if quartets.ndim != 2 or quartets.shape[1] != 4:
+            raise ValueError("Expected (n, 4) array, got shape {shape}".format(shape=quartets.shape))
+        if quartets.dtype != np.int64:
+            raise ValueError("Buffer dtype mismatch, expected 'long' but got '%s'" % quartets.dtype.name)
+        if quartets.shape[0] == 0:
+            # the reference fails in quartets.max() on an empty array (MuchTree.pyx:1303)
+            raise ValueError("zero-size array to reduction operation maximum which has no identity")
+        if any(s % 8 for s in quartets.strides):
+            quartets = np.ascontiguousarray(quartets)
+        n = quartets.shape[0]
+        out = np.zeros((n, 4), dtype=np.int64)
+        s0, s1 = quartets.strides[0] // 8, quartets.strides[1] // 8
+        rc = _lib.lib().st_quartet_topologies(self._handle, quartets.ctypes.data, s0, s1, n, out.ctypes.data)
+        _lib.check(rc, self.size)
+        return out
+
+    def quartet_topology(self, a, b, c, d):
+        """Topology of one quartet as a frozenset of two frozensets of sisters
+        (MuchTree.pyx:1203-1247): the pairs whose MRCA is unique among the six pair
+        MRCAs are sisters; leaf names come back when any input was a name."""
+        from itertools import combinations
+
+        nodes = [a, b, c, d]
+        node_ids = [self._validate_node(node) for node in nodes]
+        has_strings = any(isinstance(node, str) for node in nodes)
+        pairs = [frozenset((x, y)) for x, y in combinations(node_ids, 2)]
+        M = [int(m) for m in self.common_ancestors_bulk(
+            np.array(list(combinations(node_ids, 2)), dtype=np.int64))]
+        sisters = [pairs[M.index(i)] for i in M if M.count(i) == 1]
+        if len(sisters) == 1:
+            sisters.append(sisters[0] ^ frozenset(node_ids))
+        if has_strings:
+            (w, x), (y, z) = sisters
+            return frozenset((frozenset((self.leaf_nodes[w], self.leaf_nodes[x])),
+                              frozenset((self.leaf_nodes[y], self.leaf_nodes[z]))))
+        return frozenset(sisters)
+
+    def quartet_topologies_by_name(self, quartets):
+        """MuchTree.pyx:1378-1421 (the later of the reference's two definitions)."""
+        quartet_ids = []
+        for i, (a, b, c, d) in enumerate(quartets):
+            if not all(isinstance(name, str) for name in (a, b, c, d)):
+                raise TypeError(f"Quartet {i}: all elements must be strings")
+            try:
+                quartet_ids.append([self.leaves[a], self.leaves[b], self.leaves[c], self.leaves[d]])
+            except KeyError as e:
+                raise NodeNotFoundError(str(e).strip("'"))
+        topologies = self.quartet_topologies_bulk(np.array(quartet_ids, dtype=np.int64))
+        result = []
+        for a, b, c, d in topologies:
+            result.append(frozenset((frozenset((self.leaf_nodes[a], self.leaf_nodes[b])),
+                                     frozenset((self.leaf_nodes[c], self.leaf_nodes[d])))))
+        return result
+
+    # deprecated names (MuchTree.pyx:2461-2475)
+    def get_quartet_topology(self, a, b, c, d):
+        _deprecation_warning("get_quartet_topology()", "quartet_topology()")
+        return self.quartet_topology(a, b, c, d)
+
+    def quartet_topologies(self, quartets):
+        _deprecation_warning("quartet_topologies()", "quartet_topologies_bulk()")
+        return self.quartet_topologies_bulk(quartets)
+
+    def quartet_topologies_device(self, d_quartets_ptr, n, d_out_ptr, stream=None):
+        """Device-resident variant: contiguous int64 (n,4) in and out."""
+        rc = _lib.lib().st_quartet_topologies_device(self._handle, d_quartets_ptr, n, d_out_ptr, stream)
+        _lib.check(rc, self.size)
+
     def nearest_neighbors(self, node, k=1, from_nodes=None):
         """MuchTree.pyx:1032-1080."""
         if k <= 0:
