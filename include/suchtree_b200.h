@@ -97,6 +97,25 @@ ST_API int st_tree_get_info(const st_tree *tree, st_tree_info *info);
  * node depth (root = 0) and root distance as a double-double (hi + lo). */
 ST_API int st_tree_export(const st_tree *tree, int32_t *depth, double *rd_hi, double *rd_lo);
 
+/* ---- NEWICK loader (host code): replaces the dendropy calls and the two fill passes
+ *      of SuchTree.__init__ (MuchTree.pyx:138-157, 171-216): parse, resolve polytomies
+ *      the way dendropy's resolve_polytomies() does, assign in-order ids, substitute
+ *      epsilon for missing / zero lengths, quantise to fp32.  Iterative and O(n).
+ * text: NEWICK bytes (UTF-8; need not be NUL-terminated).  Structural errors ->
+ * ST_ERR_NOT_BINARY with the message in st_last_error().  The arrays it returns are
+ * what st_tree_create() takes. */
+typedef struct st_newick st_newick;
+ST_API int st_newick_parse(const char *text, int64_t len, st_newick **out);
+ST_API void st_newick_free(st_newick *nw);
+ST_API int st_newick_info(const st_newick *nw, int64_t *n_nodes, int64_t *n_leaves, int32_t *root,
+                   int64_t *names_bytes);
+/* copies out the node arrays (n_nodes entries each; any pointer may be NULL) */
+ST_API int st_newick_arrays(const st_newick *nw, int32_t *parent, int32_t *left, int32_t *right,
+                     float *distance, float *support);
+/* leaves in ascending id: ids [n_leaves], name offsets [n_leaves + 1] into `names`
+ * (names_bytes bytes, no separators) */
+ST_API int st_newick_leaves(const st_newick *nw, int32_t *leaf_ids, int64_t *name_offsets, char *names);
+
 /* after ST_ERR_NODE_RANGE: the id SuchTree.distances_bulk would report in its
  * InvalidNodeError (max id if it is >= size, else min id; MuchTree.pyx:897-903) */
 ST_API int64_t st_bad_node(void);

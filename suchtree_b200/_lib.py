@@ -56,6 +56,11 @@ SIGNATURES = {
     "st_tree_destroy": (None, [_vp]),
     "st_tree_get_info": (_int, [_vp, C.POINTER(TreeInfo)]),
     "st_tree_export": (_int, [_vp, _vp, _vp, _vp]),
+    "st_newick_parse": (_int, [C.c_char_p, _i64, C.POINTER(_vp)]),
+    "st_newick_free": (None, [_vp]),
+    "st_newick_info": (_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i32), C.POINTER(_i64)]),
+    "st_newick_arrays": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "st_newick_leaves": (_int, [_vp, _vp, _vp, _vp]),
     "st_bad_node": (_i64, []),
     "st_distances": (_int, [_vp, _vp, _i64, _i64, _i64, _vp]),
     "st_mrca": (_int, [_vp, _vp, _i64, _i64, _i64, _vp]),

@@ -18,8 +18,10 @@ must stay bit-identical:
     (:136, :188-194); lengths are stored as fp32 (:55-60); the root gets the -1
     sentinel (:183-186); support = float(label) or -1 (:207-210).
 
-Unlike oracle/newick_ref.py (objects, used only by the tests) this flattener is
-array-based and never recurses, so a 10^6-deep caterpillar loads fine.
+flatten() runs the native loader of libsuchtree_b200.so (csrc/st_newick.cu, host
+C++, O(n), iterative: ml.tree's 108,653 nodes in ~20 ms, a 10^6-deep caterpillar
+loads fine).  flatten_py() is the same algorithm in Python, kept as an independent
+statement of the rules that the CPU tests compare the native loader against.
 """
 import re
 
@@ -120,7 +122,45 @@ def _resolve_polytomies(children, label, length):
 
 
 def flatten(text):
-    """NEWICK text -> FlatTree with the reference's ids and field values."""
+    """NEWICK text -> FlatTree with the reference's ids and field values (native loader)."""
+    import ctypes as C
+
+    from . import _lib
+
+    L = _lib.lib()
+    raw = text.encode("utf-8") if isinstance(text, str) else bytes(text)
+    h = C.c_void_p()
+    rc = L.st_newick_parse(raw, len(raw), C.byref(h))
+    if rc != 0:
+        raise TreeStructureError(_lib.last_error())
+    try:
+        n, nl, root, nb = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int64()
+        L.st_newick_info(h, C.byref(n), C.byref(nl), C.byref(root), C.byref(nb))
+        ft = FlatTree()
+        ft.size, ft.n_leaves, ft.root = int(n.value), int(nl.value), int(root.value)
+        ft.parent = np.empty(ft.size, np.int32)
+        ft.left = np.empty(ft.size, np.int32)
+        ft.right = np.empty(ft.size, np.int32)
+        ft.distance = np.empty(ft.size, np.float32)
+        ft.support = np.empty(ft.size, np.float32)
+        L.st_newick_arrays(h, ft.parent.ctypes.data, ft.left.ctypes.data, ft.right.ctypes.data,
+                           ft.distance.ctypes.data, ft.support.ctypes.data)
+        ids = np.empty(ft.n_leaves, np.int32)
+        offs = np.empty(ft.n_leaves + 1, np.int64)
+        names = C.create_string_buffer(max(int(nb.value), 1))
+        L.st_newick_leaves(h, ids.ctypes.data, offs.ctypes.data, names)
+    finally:
+        L.st_newick_free(h)
+    blob = names.raw[: int(nb.value)]
+    o = offs.tolist()
+    # same insertion order (ascending id) and overwrite-on-duplicate as the reference's dict
+    ft.leaves = {blob[o[k]:o[k + 1]].decode("utf-8", "replace"): i for k, i in enumerate(ids.tolist())}
+    ft.internal_nodes = np.nonzero(ft.left != -1)[0].astype(np.int64)
+    return ft
+
+
+def flatten_py(text):
+    """The same rules in pure Python (independent restatement for the tests)."""
     children, label, length = parse_newick(text)
     _resolve_polytomies(children, label, length)
     n = len(children)

@@ -68,6 +68,48 @@ def test_flattener_rejects_bad_trees():
             newick.flatten(bad)
 
 
+def _same_flat(a, b):
+    return (a.size == b.size and a.root == b.root and a.n_leaves == b.n_leaves
+            and np.array_equal(a.parent, b.parent) and np.array_equal(a.left, b.left)
+            and np.array_equal(a.right, b.right)
+            and np.array_equal(a.distance.view(np.uint32), b.distance.view(np.uint32))
+            and np.array_equal(a.support.view(np.uint32), b.support.view(np.uint32))
+            and list(a.leaves.items()) == list(b.leaves.items())
+            and np.array_equal(a.internal_nodes, b.internal_nodes))
+
+
+def test_native_loader_equals_python_restatement(golden_trees):
+    """csrc/st_newick.cu (what the product runs) against newick.flatten_py (the same
+    rules in Python), field for field and bit for bit."""
+    texts = [_read_tree_input(tree_source(name, rec)) for name, rec in golden_trees.items()]
+    texts += [read_tree_text("ml.tree.gz"), read_tree_text("nj.tree.gz")]
+    texts += [
+        "A;", "(A,B);", "('':1,B:2);", "(A:1,B:2,C:3,D:4,E:5,F:6,G:7)0.5:3;",
+        "((A:1,B:2)90:1,(C:3,D:4)'x':2)root;", "(A:inf,B:-0.0,(C:1e400,D:NaN):1e-400);",
+        " ( 'x y' : 1.5 , ( z:2 , w : 3 ) 0.75 : 4 ) ; trailing (junk", "[c](A[x]:1[y],B:2)[z];",
+        "(A:1,B:2);(C,D);", "((a,b,c,d,e,f,g,h,i,j)1e2:1,(k,l,m)x1:2,n);", "(\u00e9t\u00e9:1,'\u65e5\u672c':2);",
+        "(A:.5,B:5.,(C:+1.e+1,D:-.5E-1):1);",
+    ]
+    for t in texts:
+        assert _same_flat(newick.flatten(t), newick.flatten_py(t)), t[:60]
+    rng = np.random.default_rng(3)
+    for n in (2, 3, 17, 400):
+        ft0 = synth.yule_tree(n, seed=int(rng.integers(1 << 30)), names=True)
+        nw = synth.to_newick(ft0)
+        a = newick.flatten(nw)
+        assert _same_flat(a, newick.flatten_py(nw)) and np.array_equal(a.parent, ft0.parent)
+
+
+def test_native_loader_error_messages():
+    for bad in ["((A,B));", "(A,(B));", "((A,B),(C,D)", "(A,B));", "", "(A,,B);", "(A:x,B:1);", "(A:'1',B:1);",
+                "[only a comment]", "(A,B),C;"]:
+        with pytest.raises(TreeStructureError) as e1:
+            newick.flatten(bad)
+        with pytest.raises(TreeStructureError) as e2:
+            newick.flatten_py(bad)
+        assert str(e1.value)[:25] == str(e2.value)[:25], bad
+
+
 def test_deep_caterpillar_newick_does_not_recurse():
     L = 20000
     ft0 = synth.caterpillar_tree(L, seed=3, names=True)
