@@ -221,6 +221,10 @@ ST_API int st_pearson(int device, const double *x, const double *y, int64_t n, d
 ST_API int st_bench_gather(int device, int64_t bytes, int64_t loads_per_thread, int iters,
                     double *sectors_per_s);
 
+/* ---- measurement helper: rate (pairs/s) at which the host thread pool packs int64
+ * id pairs into int32 pinned staging -- the host stage of st_distances(). */
+ST_API int st_bench_pack(int64_t n_pairs, int iters, double *pairs_per_s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -324,6 +324,7 @@ extern "C" void st_tree_destroy(st_tree *t) {
         if (t->d_stage_out[i]) cudaFree(t->d_stage_out[i]);
         if (t->d_stage_out2[i]) cudaFree(t->d_stage_out2[i]);
         if (t->h_stage[i]) cudaFreeHost(t->h_stage[i]);
+        if (t->h_out_stage[i]) cudaFreeHost(t->h_out_stage[i]);
         if (t->ev[i]) cudaEventDestroy(t->ev[i]);
         if (t->streams[i]) cudaStreamDestroy(t->streams[i]);
     }

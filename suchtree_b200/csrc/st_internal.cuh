@@ -121,7 +121,8 @@ struct st_tree {
     mutable void *d_stage_in[3] = {nullptr, nullptr, nullptr};
     mutable void *d_stage_out[3] = {nullptr, nullptr, nullptr};
     mutable void *d_stage_out2[3] = {nullptr, nullptr, nullptr};
-    mutable void *h_stage[3] = {nullptr, nullptr, nullptr};
+    mutable void *h_stage[3] = {nullptr, nullptr, nullptr};      // pinned, packed input ids
+    mutable void *h_out_stage[3] = {nullptr, nullptr, nullptr};  // pinned results (pageable user buffers)
     mutable int64_t stage_pairs = 0;
     mutable cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
 };

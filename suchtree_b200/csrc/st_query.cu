@@ -13,7 +13,15 @@
 #include <algorithm>
 #include <cmath>
 
+#include <chrono>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+#include <cstring>
+#include <vector>
+
 #include "st_device.cuh"
+#include "st_hostpool.cuh"
 
 static const int QT = 512;  // threads per CTA
 
@@ -272,13 +280,27 @@ extern "C" int st_random_leaf_pairs_device(const st_tree *t, uint64_t seed, int6
 }
 
 // -------------------------------------------------------------- host API ----
-// Chunked 3-stage pipeline: H2D(chunk c+1) | kernel(chunk c) | D2H(chunk c-1) on
-// three streams.  int64 pairs are copied as they are (the kernel reads int64
-// directly: no narrowing pass on either side).  Pinned user buffers give true
-// overlap; pageable ones still work (the driver stages them).
+// Chunked 3-slot pipeline: pack(chunk c+1) on the host pool | H2D + kernel + D2H of
+// chunk c on one of three streams | copy-out(chunk c-2).  The caller's int64 ids
+// (the drop-in dtype, any strides, pageable or pinned) are packed to int32 into
+// pinned staging by the host thread pool: half the PCIe bytes (8 instead of 16 per
+// pair), which is what bounds this path.  Results go straight to the caller's
+// buffer when it is pinned, else through pinned staging + a parallel copy.
+// With too few host threads and a pinned contiguous input, the int64 array is
+// copied as it is and the kernel reads int64 (no host pass at all).
 static const int64_t ST_STAGE_PAIRS_MAX = int64_t(1) << 22;
 
-static int ensure_stage(const st_tree *t, int64_t n, bool need_host_pack) {
+static bool is_pinned(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+static int ensure_stage(const st_tree *t, int64_t n, bool need_h_in, bool need_h_out) {
     int64_t want = 4096;
     while (want < n && want < ST_STAGE_PAIRS_MAX) want <<= 1;
     if (want > t->stage_pairs) {
@@ -287,7 +309,8 @@ static int ensure_stage(const st_tree *t, int64_t n, bool need_host_pack) {
             cudaFree(t->d_stage_out[i]);
             cudaFree(t->d_stage_out2[i]);
             if (t->h_stage[i]) cudaFreeHost(t->h_stage[i]);
-            t->d_stage_in[i] = t->d_stage_out[i] = t->d_stage_out2[i] = t->h_stage[i] = nullptr;
+            if (t->h_out_stage[i]) cudaFreeHost(t->h_out_stage[i]);
+            t->d_stage_in[i] = t->d_stage_out[i] = t->d_stage_out2[i] = t->h_stage[i] = t->h_out_stage[i] = nullptr;
         }
         t->stage_pairs = 0;
         for (int i = 0; i < 3; ++i) {
@@ -297,11 +320,92 @@ static int ensure_stage(const st_tree *t, int64_t n, bool need_host_pack) {
         }
         t->stage_pairs = want;
     }
-    if (need_host_pack) {
-        for (int i = 0; i < 3; ++i)
-            if (!t->h_stage[i]) ST_CUDA(cudaMallocHost(&t->h_stage[i], size_t(t->stage_pairs) * 16));
+    for (int i = 0; i < 3; ++i) {
+        if (need_h_in && !t->h_stage[i]) ST_CUDA(cudaMallocHost(&t->h_stage[i], size_t(t->stage_pairs) * 16));
+        if (need_h_out && !t->h_out_stage[i])
+            ST_CUDA(cudaMallocHost(&t->h_out_stage[i], size_t(t->stage_pairs) * 8));
     }
     return ST_OK;
+}
+
+// int64 ids -> int32, OR of everything seen (bit 31 and above set <=> some id is
+// negative or >= 2^31: the rare error path then finds the exact id)
+static uint64_t pack_ids_contig(const int64_t *__restrict__ src, int32_t *__restrict__ dst, int64_t count) {
+    uint64_t acc = 0;
+    int64_t i = 0;
+#if defined(__SSE2__)
+    // 4 ids per step; streaming stores: the staging buffer is read next by the DMA
+    // engine, not by this core, so skip the read-for-ownership of its lines
+    while (i < count && (reinterpret_cast<uintptr_t>(dst + i) & 15)) {
+        const int64_t v = src[i];
+        acc |= uint64_t(v);
+        dst[i++] = int32_t(v);
+    }
+    __m128i vacc = _mm_setzero_si128();
+    for (; i + 8 <= count; i += 8) {
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i));
+        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 2));
+        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 4));
+        const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 6));
+        vacc = _mm_or_si128(vacc, _mm_or_si128(_mm_or_si128(a, b), _mm_or_si128(c, d)));
+        const __m128 lo = _mm_shuffle_ps(_mm_castsi128_ps(a), _mm_castsi128_ps(b), _MM_SHUFFLE(2, 0, 2, 0));
+        const __m128 hi = _mm_shuffle_ps(_mm_castsi128_ps(c), _mm_castsi128_ps(d), _MM_SHUFFLE(2, 0, 2, 0));
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i), _mm_castps_si128(lo));
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 4), _mm_castps_si128(hi));
+    }
+    alignas(16) uint64_t lanes[2];
+    _mm_store_si128(reinterpret_cast<__m128i *>(lanes), vacc);
+    acc |= lanes[0] | lanes[1];
+    _mm_sfence();
+#endif
+    for (; i < count; ++i) {
+        const int64_t v = src[i];
+        acc |= uint64_t(v);
+        dst[i] = int32_t(v);
+    }
+    return acc;
+}
+static uint64_t pack_pairs(const int64_t *src, int64_t s0, int64_t s1, int64_t m, int32_t *dst, int width) {
+    const bool contiguous = (s1 == 1 && s0 == width);
+    const int parts = int(std::min<int64_t>(st_host_threads(), m / 32768 + 1));
+    std::vector<uint64_t> accs(size_t(parts), 0);
+    st_parallel_for(parts, [&](int p, int np) {
+        const int64_t b = m * p / np, e = m * (p + 1) / np;
+        uint64_t acc = 0;
+        if (contiguous) {
+            acc = pack_ids_contig(src + b * width, dst + b * width, (e - b) * width);
+        } else {
+            for (int64_t i = b; i < e; ++i)
+                for (int k = 0; k < width; ++k) {
+                    const int64_t v = src[i * s0 + k * s1];
+                    acc |= uint64_t(v);
+                    dst[i * width + k] = int32_t(v);
+                }
+        }
+        accs[size_t(p)] = acc;
+    });
+    uint64_t acc = 0;
+    for (uint64_t a : accs) acc |= a;
+    return acc;
+}
+static void parallel_copy(void *dst, const void *src, size_t bytes) {
+    const int parts = int(std::min<size_t>(size_t(st_host_threads()), bytes / (size_t(1) << 20) + 1));
+    st_parallel_for(parts, [&](int p, int np) {
+        const size_t b = bytes * size_t(p) / size_t(np), e = bytes * size_t(p + 1) / size_t(np);
+        memcpy(static_cast<char *>(dst) + b, static_cast<const char *>(src) + b, e - b);
+    });
+}
+// the reference's report for an out-of-range array: max id if it is >= size, else min id
+static void report_range(const int64_t *src, int64_t s0, int64_t s1, int64_t n, int width, int64_t n_nodes) {
+    int64_t mx = INT64_MIN, mn = INT64_MAX;
+    for (int64_t i = 0; i < n; ++i)
+        for (int k = 0; k < width; ++k) {
+            const int64_t v = src[i * s0 + k * s1];
+            mx = v > mx ? v : mx;
+            mn = v < mn ? v : mn;
+        }
+    st_set_bad_node(mx >= n_nodes ? mx : mn);
+    st_set_error("node id %lld out of bounds (tree size %lld)", (long long)st_bad_node(), (long long)n_nodes);
 }
 
 static int host_pairs_run(const st_tree *t, const int64_t *pairs, int64_t s0, int64_t s1, int64_t n,
@@ -314,42 +418,116 @@ static int host_pairs_run(const st_tree *t, const int64_t *pairs, int64_t s0, in
     DeviceGuard g(t->device);
     std::lock_guard<std::mutex> lock(t->host_mu);
     const bool contiguous = (s1 == 1 && s0 == 2);
-    int rc = ensure_stage(t, n, !contiguous);
+    const bool out_pinned = is_pinned(out_d ? static_cast<void *>(out_d) : static_cast<void *>(out_m));
+    bool pack = true;
+    if (contiguous && st_host_threads() < 4 && is_pinned(pairs)) pack = false;
+    if (const char *e = getenv("SUCHTREE_B200_HOST_PATH")) {
+        if (e[0] == 'd' && contiguous) pack = false;  // "direct"
+        if (e[0] == 'p') pack = true;                 // "pack"
+    }
+    // hybrid: PCIe wants the ids packed (8 instead of 16 B/pair), host memory bandwidth
+    // wants them left alone (packing costs 24 B/pair of host traffic on top of the DMA's):
+    // pack a fraction of every chunk and ship the rest as int64
+    double pack_fraction = 0.45;
+    if (const char *e = getenv("SUCHTREE_B200_PACK_FRACTION")) pack_fraction = std::min(1.0, std::max(0.0, atof(e)));
+    const bool hybrid = pack && contiguous && pack_fraction < 1.0 && is_pinned(pairs);
+    int rc = ensure_stage(t, n, pack, !out_pinned);
     if (rc != ST_OK) return rc;
     const int64_t C = t->stage_pairs;
+    const size_t out_elem = out_d ? 8 : 4;
+    char *user_out = out_d ? reinterpret_cast<char *>(out_d) : reinterpret_cast<char *>(out_m);
+    int64_t chunk_begin[3] = {0, 0, 0}, chunk_len[3] = {0, 0, 0};
+    auto copy_out = [&](int s) {  // results of the chunk last issued on slot s -> caller's buffer
+        if (!out_pinned && chunk_len[s] > 0)
+            parallel_copy(user_out + size_t(chunk_begin[s]) * out_elem, t->h_out_stage[s],
+                          size_t(chunk_len[s]) * out_elem);
+        chunk_len[s] = 0;
+    };
     int64_t done = 0;
     int c = 0;
     for (; done < n; ++c) {
         const int s = c % 3;
         const int64_t m = std::min(C, n - done);
         cudaStream_t st = t->streams[s];
-        if (c >= 3) ST_CUDA(cudaEventSynchronize(t->ev[s]));  // stage buffers free again
-        const int64_t *src = pairs + done * s0;
-        if (!contiguous) {
-            int64_t *hp = static_cast<int64_t *>(t->h_stage[s]);
-            for (int64_t i = 0; i < m; ++i) {
-                hp[2 * i] = src[i * s0];
-                hp[2 * i + 1] = src[i * s0 + s1];
-            }
-            src = hp;
+        if (c >= 3) {
+            ST_CUDA(cudaEventSynchronize(t->ev[s]));  // slot s: device buffers and staging are free again
+            copy_out(s);
         }
-        ST_CUDA(cudaMemcpyAsync(t->d_stage_in[s], src, size_t(m) * 16, cudaMemcpyHostToDevice, st));
+        const int64_t *src = pairs + done * s0;
         double *dd_out = out_d ? static_cast<double *>(t->d_stage_out[s]) : nullptr;
         int32_t *dm_out = out_m ? static_cast<int32_t *>(t->d_stage_out2[s]) : nullptr;
-        rc = st_launch_pairs(t, t->d_stage_in[s], 64, m, dd_out, dm_out, st);
-        if (rc != ST_OK) return rc;
-        if (out_d)
-            ST_CUDA(cudaMemcpyAsync(out_d + done, dd_out, size_t(m) * 8, cudaMemcpyDeviceToHost, st));
-        if (out_m)
-            ST_CUDA(cudaMemcpyAsync(out_m + done, dm_out, size_t(m) * 4, cudaMemcpyDeviceToHost, st));
+        // first mp pairs: packed to int32 by the host pool; the rest (hybrid mode, pinned
+        // contiguous input): DMA'd as int64 while the pool packs
+        const int64_t mp = pack ? (hybrid ? (int64_t(double(m) * pack_fraction) & ~int64_t(1)) : m) : 0;
+        char *d_in = static_cast<char *>(t->d_stage_in[s]);
+        if (mp < m)
+            ST_CUDA(cudaMemcpyAsync(d_in + size_t(mp) * 8, src + 2 * mp, size_t(m - mp) * 16,
+                                    cudaMemcpyHostToDevice, st));
+        if (mp > 0) {
+            int32_t *hp = static_cast<int32_t *>(t->h_stage[s]);
+            const uint64_t acc = pack_pairs(src, s0, s1, mp, hp, 2);
+            if (acc >> 31) {  // a negative id, or one beyond int32: cannot be a node of any tree
+                for (int k = 0; k < 3; ++k) cudaStreamSynchronize(t->streams[k]);
+                bool dummy = false;
+                st_read_range_status(t, t->streams[0], &dummy);  // clear anything the kernels flagged
+                report_range(pairs, s0, s1, n, 2, t->n_nodes);
+                return ST_ERR_NODE_RANGE;
+            }
+            ST_CUDA(cudaMemcpyAsync(d_in, hp, size_t(mp) * 8, cudaMemcpyHostToDevice, st));
+            rc = st_launch_pairs(t, d_in, 32, mp, dd_out, dm_out, st);
+            if (rc != ST_OK) return rc;
+        }
+        if (mp < m) {
+            rc = st_launch_pairs(t, d_in + size_t(mp) * 8, 64, m - mp, dd_out ? dd_out + mp : nullptr,
+                                 dm_out ? dm_out + mp : nullptr, st);
+            if (rc != ST_OK) return rc;
+        }
+        void *dst = out_pinned ? static_cast<void *>(user_out + size_t(done) * out_elem) : t->h_out_stage[s];
+        const void *dsrc = out_d ? static_cast<const void *>(dd_out) : static_cast<const void *>(dm_out);
+        ST_CUDA(cudaMemcpyAsync(dst, dsrc, size_t(m) * out_elem, cudaMemcpyDeviceToHost, st));
         ST_CUDA(cudaEventRecord(t->ev[s], st));
+        chunk_begin[s] = done;
+        chunk_len[s] = m;
         done += m;
     }
-    for (int s = 0; s < 3 && s < c; ++s) ST_CUDA(cudaStreamSynchronize(t->streams[s]));
+    // drain in issue order
+    for (int k = 0; k < 3 && k < c; ++k) {
+        const int s = (c - std::min(c, 3) + k) % 3;
+        ST_CUDA(cudaStreamSynchronize(t->streams[s]));
+        copy_out(s);
+    }
     bool bad = false;
     rc = st_read_range_status(t, t->streams[0], &bad);
     if (rc != ST_OK) return rc;
     return bad ? ST_ERR_NODE_RANGE : ST_OK;
+}
+
+// measurement helper: rate of the host-side id packing alone (pinned src and dst)
+extern "C" int st_bench_pack(int64_t n_pairs, int iters, double *pairs_per_s) {
+    if (!pairs_per_s || n_pairs < 1 || iters < 1) return ST_ERR_INVALID_ARG;
+    int64_t *src = nullptr;
+    int32_t *dst = nullptr;
+    ST_CUDA(cudaMallocHost(&src, size_t(n_pairs) * 16));
+    if (cudaMallocHost(&dst, size_t(n_pairs) * 8) != cudaSuccess) {
+        cudaFreeHost(src);
+        return ST_ERR_NOMEM;
+    }
+    for (int64_t i = 0; i < 2 * n_pairs; ++i) src[i] = i & 0xffff;
+    uint64_t acc = pack_pairs(src, 2, 1, n_pairs, dst, 2);  // warm (page touch)
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    cudaEventSynchronize(e0);
+    auto t0 = std::chrono::steady_clock::now();
+    for (int it = 0; it < iters; ++it) acc |= pack_pairs(src, 2, 1, n_pairs, dst, 2);
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFreeHost(src);
+    cudaFreeHost(dst);
+    *pairs_per_s = (acc >> 31) ? 0.0 : double(n_pairs) * iters / dt;
+    return ST_OK;
 }
 
 extern "C" int st_distances(const st_tree *t, const int64_t *pairs, int64_t stride0, int64_t stride1,
