@@ -70,6 +70,22 @@ __device__ __forceinline__ int4 st_ld_stream_int4(const void *p) {
                  : "l"(p), "l"(st_policy_evict_first()));
     return r;
 }
+// 256-bit streaming load / stores (sm_100+)
+__device__ __forceinline__ void st_ld_stream_256(const void *p, uint64_t (&w)[4]) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.b64 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3])
+                 : "l"(p), "l"(st_policy_evict_first()));
+}
+__device__ __forceinline__ void st_st_stream_f64x4(double *p, double a, double b, double c, double d) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f64 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p),
+                 "d"(a), "d"(b), "d"(c), "d"(d), "l"(st_policy_evict_first())
+                 : "memory");
+}
+__device__ __forceinline__ void st_st_stream_i32x4(int32_t *p, int32_t a, int32_t b, int32_t c, int32_t d) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.s32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p),
+                 "r"(a), "r"(b), "r"(c), "r"(d), "l"(st_policy_evict_first())
+                 : "memory");
+}
 __device__ __forceinline__ void st_st_stream_f64x2(double *p, double a, double b) {
     asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(p),
                  "d"(a), "d"(b), "l"(st_policy_evict_first())

@@ -23,44 +23,51 @@
 #include "st_device.cuh"
 #include "st_hostpool.cuh"
 
-static const int QT = 512;  // threads per CTA
 
-template <typename IdxT>
-struct PairIO;
-
-template <>
-struct PairIO<int32_t> {
-    // two pairs per 16-byte load
-    static __device__ __forceinline__ void load2(const int32_t *p, int64_t pair_idx, long long &a0,
-                                                 long long &b0, long long &a1, long long &b1) {
-        int4 v = st_ld_stream_int4(p + 2 * pair_idx);
-        a0 = v.x; b0 = v.y; a1 = v.z; b1 = v.w;
-    }
-    static __device__ __forceinline__ void load1(const int32_t *p, int64_t pair_idx, long long &a,
-                                                 long long &b) {
-        a = __ldg(p + 2 * pair_idx);
-        b = __ldg(p + 2 * pair_idx + 1);
-    }
-    static constexpr int kAlign = 16;
+// P pairs per thread per iteration, fetched as raw 64-bit words by 16-byte (P = 2,
+// int32) or 32-byte streaming loads and decoded when used (the prefetched copy of
+// the next iteration stays packed: fewer live registers)
+template <typename IdxT, int P>
+struct RawPairs {
+    static constexpr int W = P * int(sizeof(IdxT)) / 4;  // 64-bit words
+    uint64_t w[W];
 };
-template <>
-struct PairIO<int64_t> {
-    static __device__ __forceinline__ void load2(const int64_t *p, int64_t pair_idx, long long &a0,
-                                                 long long &b0, long long &a1, long long &b1) {
-        int4 v = st_ld_stream_int4(p + 2 * pair_idx);
-        int4 w = st_ld_stream_int4(p + 2 * pair_idx + 2);
-        a0 = (long long)(uint32_t(v.x) | (uint64_t(uint32_t(v.y)) << 32));
-        b0 = (long long)(uint32_t(v.z) | (uint64_t(uint32_t(v.w)) << 32));
-        a1 = (long long)(uint32_t(w.x) | (uint64_t(uint32_t(w.y)) << 32));
-        b1 = (long long)(uint32_t(w.z) | (uint64_t(uint32_t(w.w)) << 32));
+template <typename IdxT, int P>
+__device__ __forceinline__ RawPairs<IdxT, P> st_load_pairs(const IdxT *pairs, int64_t first_pair) {
+    RawPairs<IdxT, P> r;
+    const IdxT *p = pairs + 2 * first_pair;
+    if (P == 1) {
+        if (sizeof(IdxT) == 4) {
+            r.w[0] = uint64_t(uint32_t(__ldg(p))) | (uint64_t(uint32_t(__ldg(p + 1))) << 32);
+        } else {
+            r.w[0] = uint64_t(__ldg(reinterpret_cast<const long long *>(p)));
+            r.w[RawPairs<IdxT, P>::W - 1] = uint64_t(__ldg(reinterpret_cast<const long long *>(p) + 1));
+        }
+    } else if (RawPairs<IdxT, P>::W == 2) {
+        const int4 v = st_ld_stream_int4(p);
+        r.w[0] = uint64_t(uint32_t(v.x)) | (uint64_t(uint32_t(v.y)) << 32);
+        r.w[1] = uint64_t(uint32_t(v.z)) | (uint64_t(uint32_t(v.w)) << 32);
+    } else {
+#pragma unroll
+        for (int h = 0; h < RawPairs<IdxT, P>::W / 4; ++h) {
+            uint64_t q[4];
+            st_ld_stream_256(reinterpret_cast<const char *>(p) + 32 * h, q);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) r.w[4 * h + k] = q[k];
+        }
     }
-    static __device__ __forceinline__ void load1(const int64_t *p, int64_t pair_idx, long long &a,
-                                                 long long &b) {
-        a = __ldg(reinterpret_cast<const long long *>(p) + 2 * pair_idx);
-        b = __ldg(reinterpret_cast<const long long *>(p) + 2 * pair_idx + 1);
+    return r;
+}
+template <typename IdxT, int P>
+__device__ __forceinline__ void st_decode_pair(const RawPairs<IdxT, P> &r, int k, long long &a, long long &b) {
+    if (sizeof(IdxT) == 4) {
+        a = int32_t(uint32_t(r.w[k]));
+        b = int32_t(uint32_t(r.w[k] >> 32));
+    } else {
+        a = (long long)r.w[2 * k];
+        b = (long long)r.w[2 * k + 1];
     }
-    static constexpr int kAlign = 16;
-};
+}
 
 struct PairQ {
     int32_t lo, hi;
@@ -98,8 +105,10 @@ __device__ __forceinline__ void st_pair(const TreeView &tv, const SmemTables &sm
     if (want_m) m = st_mrca_id<M>(tv, sm, k, ft);
 }
 
-template <typename IdxT, bool VEC, int M>
-__global__ void __launch_bounds__(QT, 2)
+// P pairs per thread per iteration: 2P independent record gathers are in flight
+// before anything depends on them (the kernel is latency-bound on those gathers).
+template <typename IdxT, int P, int M, int QT, int MINB>
+__global__ void __launch_bounds__(QT, MINB)
 k_pairs(const TreeView tv, const IdxT *__restrict__ pairs, int64_t n, double *__restrict__ out,
         int32_t *__restrict__ mrca_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -107,53 +116,73 @@ k_pairs(const TreeView tv, const IdxT *__restrict__ pairs, int64_t n, double *__
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
     const bool want_d = out != nullptr, want_m = mrca_out != nullptr;
 
-    if (VEC) {
-        const int64_t n2 = n >> 1;  // pair-of-pairs
-        for (int64_t i = int64_t(blockIdx.x) * QT + threadIdx.x; i < n2; i += int64_t(gridDim.x) * QT) {
-            long long a0, b0, a1, b1;
-            PairIO<IdxT>::load2(pairs, 2 * i, a0, b0, a1, b1);
-            const PairQ q0 = st_make_query(tv, a0, b0), q1 = st_make_query(tv, a1, b1);
-            // four independent gathers in flight before anything depends on them
-            const RecRaw l0 = st_ld_rec<M>(tv, q0.lo), h0 = st_ld_rec<M>(tv, q0.hi);
-            const RecRaw l1 = st_ld_rec<M>(tv, q1.lo), h1 = st_ld_rec<M>(tv, q1.hi);
-            double d0 = 0.0, d1 = 0.0;
-            int32_t m0 = 0, m1 = 0;
-            st_pair<M>(tv, sm, q0, l0, h0, want_d, want_m, d0, m0);
-            st_pair<M>(tv, sm, q1, l1, h1, want_d, want_m, d1, m1);
-            if (want_d) st_st_stream_f64x2(out + 2 * i, q0.bad ? nan : d0, q1.bad ? nan : d1);
-            if (want_m) st_st_stream_i32x2(mrca_out + 2 * i, q0.bad ? -1 : m0, q1.bad ? -1 : m1);
-        }
-        if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int64_t groups = n / P;
+    const int64_t stride = int64_t(gridDim.x) * QT;
+    int64_t i = int64_t(blockIdx.x) * QT + threadIdx.x;
+    // (prefetching the next iteration's ids, and 4 pairs per thread, were both measured
+    //  and are no faster: profiles/r01_summary.md)
+    for (; i < groups; i += stride) {
+        const RawPairs<IdxT, P> cur = st_load_pairs<IdxT, P>(pairs, P * i);
+        PairQ q[P];
+        RecRaw l[P], h[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
             long long a, b;
-            PairIO<IdxT>::load1(pairs, n - 1, a, b);
-            const PairQ q = st_make_query(tv, a, b);
-            const RecRaw l = st_ld_rec<M>(tv, q.lo), h = st_ld_rec<M>(tv, q.hi);
-            double d = 0.0;
-            int32_t m = 0;
-            st_pair<M>(tv, sm, q, l, h, want_d, want_m, d, m);
-            if (want_d) out[n - 1] = q.bad ? nan : d;
-            if (want_m) mrca_out[n - 1] = q.bad ? -1 : m;
+            st_decode_pair<IdxT, P>(cur, k, a, b);
+            q[k] = st_make_query(tv, a, b);
         }
-    } else {
-        for (int64_t i = int64_t(blockIdx.x) * QT + threadIdx.x; i < n; i += int64_t(gridDim.x) * QT) {
-            long long a, b;
-            PairIO<IdxT>::load1(pairs, i, a, b);
-            const PairQ q = st_make_query(tv, a, b);
-            const RecRaw l = st_ld_rec<M>(tv, q.lo), h = st_ld_rec<M>(tv, q.hi);
-            double d = 0.0;
-            int32_t m = 0;
-            st_pair<M>(tv, sm, q, l, h, want_d, want_m, d, m);
-            if (want_d) st_st_stream_f64(out + i, q.bad ? nan : d);
-            if (want_m) st_st_stream_i32(mrca_out + i, q.bad ? -1 : m);
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+            l[k] = st_ld_rec<M>(tv, q[k].lo);
+            h[k] = st_ld_rec<M>(tv, q[k].hi);
         }
+        double d[P];
+        int32_t m[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+            d[k] = 0.0;
+            m[k] = 0;
+            st_pair<M>(tv, sm, q[k], l[k], h[k], want_d, want_m, d[k], m[k]);
+            if (q[k].bad) {
+                d[k] = nan;
+                m[k] = -1;
+            }
+        }
+        if (want_d) {
+            if (P == 4) st_st_stream_f64x4(out + P * i, d[0], d[1], d[2], d[3]);
+            else if (P == 2) st_st_stream_f64x2(out + P * i, d[0], d[1]);
+            else st_st_stream_f64(out + i, d[0]);
+        }
+        if (want_m) {
+            if (P == 4) st_st_stream_i32x4(mrca_out + P * i, m[0], m[1], m[2], m[3]);
+            else if (P == 2) st_st_stream_i32x2(mrca_out + P * i, m[0], m[1]);
+            else st_st_stream_i32(mrca_out + i, m[0]);
+        }
+    }
+    // the n % P pairs left over: one thread each
+    const int64_t t = int64_t(blockIdx.x) * QT + threadIdx.x;
+    if (P > 1 && t < n - groups * P) {
+        const int64_t i = groups * P + t;
+        long long a, b;
+        st_decode_pair<IdxT, 1>(st_load_pairs<IdxT, 1>(pairs, i), 0, a, b);
+        const PairQ q = st_make_query(tv, a, b);
+        const RecRaw l = st_ld_rec<M>(tv, q.lo), h = st_ld_rec<M>(tv, q.hi);
+        double d = 0.0;
+        int32_t m = 0;
+        st_pair<M>(tv, sm, q, l, h, want_d, want_m, d, m);
+        if (want_d) out[i] = q.bad ? nan : d;
+        if (want_m) mrca_out[i] = q.bad ? -1 : m;
     }
 }
 
 // ------------------------------------------------------------------ launch --
-template <typename IdxT, bool VEC, int M>
+template <typename IdxT, int P, int M>
 static int launch_variant_m(const st_tree *t, const void *d_pairs, int64_t n, double *d_out,
-                          int32_t *d_mrca, cudaStream_t stream) {
-    auto kern = k_pairs<IdxT, VEC, M>;
+                            int32_t *d_mrca, cudaStream_t stream) {
+    // 2 pairs/thread: 2 x 512 threads x 64 registers; 4 pairs/thread needs ~80 registers:
+    // 3 x 256 threads (8 gathers in flight per thread)
+    constexpr int QT = P == 4 ? 256 : 512, MINB = P == 4 ? 3 : 2;
+    auto kern = k_pairs<IdxT, P, M, QT, MINB>;
     static thread_local int configured_smem[64] = {0};  // per device, per thread: cheap re-check
     const int smem = t->query_smem_bytes;
     if (smem > 48 * 1024 && configured_smem[t->device & 63] < smem) {
@@ -163,7 +192,7 @@ static int launch_variant_m(const st_tree *t, const void *d_pairs, int64_t n, do
     int per_sm = 0;
     ST_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, QT, smem));
     if (per_sm < 1) per_sm = 1;
-    const int64_t items = VEC ? std::max<int64_t>(n >> 1, 1) : n;
+    const int64_t items = std::max<int64_t>(n / P, 1);
     int64_t want = (items + QT - 1) / QT;
     int grid = int(std::min<int64_t>(want, int64_t(t->sm_count) * per_sm));
     if (grid < 1) grid = 1;
@@ -172,27 +201,43 @@ static int launch_variant_m(const st_tree *t, const void *d_pairs, int64_t n, do
     return ST_OK;
 }
 
-template <typename IdxT, bool VEC>
+template <typename IdxT, int P>
 static int launch_variant(const st_tree *t, const void *d_pairs, int64_t n, double *d_out,
                           int32_t *d_mrca, cudaStream_t stream) {
-    return t->compact ? launch_variant_m<IdxT, VEC, 1>(t, d_pairs, n, d_out, d_mrca, stream)
-                      : launch_variant_m<IdxT, VEC, 0>(t, d_pairs, n, d_out, d_mrca, stream);
+    return t->compact ? launch_variant_m<IdxT, P, 1>(t, d_pairs, n, d_out, d_mrca, stream)
+                      : launch_variant_m<IdxT, P, 0>(t, d_pairs, n, d_out, d_mrca, stream);
+}
+
+static int st_pairs_per_thread() {  // SUCHTREE_B200_PPT = 1 | 2 | 4 (experiments)
+    static const int v = [] {
+        const char *e = getenv("SUCHTREE_B200_PPT");
+        const int x = e ? atoi(e) : 2;
+        return (x == 1 || x == 2 || x == 4) ? x : 2;
+    }();
+    return v;
 }
 
 int st_launch_pairs(const st_tree *t, const void *d_pairs, int idx_bits, int64_t n, double *d_out,
                     int32_t *d_mrca, cudaStream_t stream) {
     if (n == 0) return ST_OK;
-    const bool aligned = (reinterpret_cast<uintptr_t>(d_pairs) % 16 == 0) &&
-                         (!d_out || reinterpret_cast<uintptr_t>(d_out) % 16 == 0) &&
-                         (!d_mrca || reinterpret_cast<uintptr_t>(d_mrca) % 8 == 0);
-    if (idx_bits == 32)
-        return aligned ? launch_variant<int32_t, true>(t, d_pairs, n, d_out, d_mrca, stream)
-                       : launch_variant<int32_t, false>(t, d_pairs, n, d_out, d_mrca, stream);
-    if (idx_bits == 64)
-        return aligned ? launch_variant<int64_t, true>(t, d_pairs, n, d_out, d_mrca, stream)
-                       : launch_variant<int64_t, false>(t, d_pairs, n, d_out, d_mrca, stream);
-    st_set_error("idx_bits must be 32 or 64 (got %d)", idx_bits);
-    return ST_ERR_INVALID_ARG;
+    if (idx_bits != 32 && idx_bits != 64) {
+        st_set_error("idx_bits must be 32 or 64 (got %d)", idx_bits);
+        return ST_ERR_INVALID_ARG;
+    }
+    auto aligned = [&](uintptr_t in_al, uintptr_t d_al, uintptr_t m_al) {
+        return (reinterpret_cast<uintptr_t>(d_pairs) % in_al == 0) &&
+               (!d_out || reinterpret_cast<uintptr_t>(d_out) % d_al == 0) &&
+               (!d_mrca || reinterpret_cast<uintptr_t>(d_mrca) % m_al == 0);
+    };
+    const int ppt = st_pairs_per_thread();
+    if (idx_bits == 32) {
+        if (ppt >= 4 && aligned(32, 32, 16)) return launch_variant<int32_t, 4>(t, d_pairs, n, d_out, d_mrca, stream);
+        if (ppt >= 2 && aligned(16, 16, 8)) return launch_variant<int32_t, 2>(t, d_pairs, n, d_out, d_mrca, stream);
+        return launch_variant<int32_t, 1>(t, d_pairs, n, d_out, d_mrca, stream);
+    }
+    if (ppt >= 4 && aligned(32, 32, 16)) return launch_variant<int64_t, 4>(t, d_pairs, n, d_out, d_mrca, stream);
+    if (ppt >= 2 && aligned(32, 16, 8)) return launch_variant<int64_t, 2>(t, d_pairs, n, d_out, d_mrca, stream);
+    return launch_variant<int64_t, 1>(t, d_pairs, n, d_out, d_mrca, stream);
 }
 
 int st_read_range_status(const st_tree *t, cudaStream_t stream, bool *bad) {
@@ -458,7 +503,7 @@ static int host_pairs_run(const st_tree *t, const int64_t *pairs, int64_t s0, in
         int32_t *dm_out = out_m ? static_cast<int32_t *>(t->d_stage_out2[s]) : nullptr;
         // first mp pairs: packed to int32 by the host pool; the rest (hybrid mode, pinned
         // contiguous input): DMA'd as int64 while the pool packs
-        const int64_t mp = pack ? (hybrid ? (int64_t(double(m) * pack_fraction) & ~int64_t(1)) : m) : 0;
+        const int64_t mp = pack ? (hybrid ? (int64_t(double(m) * pack_fraction) & ~int64_t(3)) : m) : 0;
         char *d_in = static_cast<char *>(t->d_stage_in[s]);
         if (mp < m)
             ST_CUDA(cudaMemcpyAsync(d_in + size_t(mp) * 8, src + 2 * mp, size_t(m - mp) * 16,

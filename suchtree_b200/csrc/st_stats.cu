@@ -311,6 +311,80 @@ k_gather_g4(const __grid_constant__ CUtensorMap tmap, const ulonglong4 *__restri
     if (acc == 0x123456789abcdefull) *sink = acc;
 }
 
+// Experiment: warp-specialised mix.  Warps [0, TMA_WARPS) of every 16-warp CTA fetch
+// sectors with gather4 (per-warp mbarrier, two stages, no CTA-wide sync); the other
+// warps run the plain LSU gather loop.  Are the two paths into L2 additive?
+// Selected with SUCHTREE_B200_GATHER_MODE=ws<k> (k = TMA warps per CTA, 0..16).
+template <int TMA_WARPS>
+__global__ void __launch_bounds__(512)
+k_gather_ws(const __grid_constant__ CUtensorMap tmap, const ulonglong4 *__restrict__ buf,
+            uint64_t n_sectors, int64_t rounds, uint64_t seed, unsigned long long *__restrict__ sink) {
+    constexpr int TW = TMA_WARPS > 0 ? TMA_WARPS : 1;
+    __shared__ __align__(128) ulonglong4 slots[TW][2][32 * 4];  // 8 KB per TMA warp
+    __shared__ __align__(8) uint64_t bar[TW][2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    uint64_t acc = 0;
+    if (warp < TMA_WARPS) {
+        if (lane == 0) {
+            for (int s = 0; s < 2; ++s)
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&bar[warp][s])), "r"(1));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        auto issue = [&](int64_t r) {
+            const int s = int(r & 1);
+            const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar[warp][s]);
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(32 * 4 * 32) : "memory");
+            __syncwarp();
+            Philox4 p = st_philox4x32_10(tid * uint64_t(rounds) + uint64_t(r), seed);
+            int32_t r0 = int32_t((uint64_t(p.x) * n_sectors) >> 32), r1 = int32_t((uint64_t(p.y) * n_sectors) >> 32);
+            int32_t r2 = int32_t((uint64_t(p.z) * n_sectors) >> 32), r3 = int32_t((uint64_t(p.w) * n_sectors) >> 32);
+            uint32_t dst = (uint32_t)__cvta_generic_to_shared(&slots[warp][s][lane * 4]);
+            asm volatile(
+                "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                ::"r"(dst), "l"(&tmap), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar_a)
+                : "memory");
+        };
+        issue(0);
+        for (int64_t r = 0; r < rounds; ++r) {
+            if (r + 1 < rounds) issue(r + 1);
+            const int s = int(r & 1);
+            const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar[warp][s]);
+            const uint32_t phase = uint32_t(r >> 1) & 1;
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile(
+                    "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                    : "=r"(done) : "r"(bar_a), "r"(phase) : "memory");
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                ulonglong4 v = slots[warp][s][lane * 4 + k];
+                acc ^= v.x ^ v.y ^ v.z ^ v.w;
+            }
+            __syncwarp();  // stage s is rewritten by issue(r + 2)
+        }
+    } else {
+        for (int64_t r = 0; r < rounds; ++r) {
+            Philox4 p = st_philox4x32_10(tid * uint64_t(rounds) + uint64_t(r), seed);
+            const uint32_t w[4] = {p.x, p.y, p.z, p.w};
+            uint64_t a[4], b[4], c[4], d[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint64_t idx = (uint64_t(w[k]) * n_sectors) >> 32;
+                asm volatile("ld.global.nc.L2::evict_last.v4.b64 {%0,%1,%2,%3}, [%4];"
+                             : "=l"(a[k]), "=l"(b[k]), "=l"(c[k]), "=l"(d[k])
+                             : "l"(buf + idx));
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc ^= a[k] ^ b[k] ^ c[k] ^ d[k];
+        }
+    }
+    if (acc == 0x123456789abcdefull) *sink = acc;
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -367,7 +441,8 @@ extern "C" int st_bench_gather(int device, int64_t bytes, int64_t loads_per_thre
     const char *mode = getenv("SUCHTREE_B200_GATHER_MODE");
     const bool bulk = mode && mode[0] == 'b';
     const bool use_tex = mode && mode[0] == 't', mix = mode && mode[0] == 'm';
-    const bool g4 = mode && mode[0] == 'g';
+    const bool g4 = mode && (mode[0] == 'g' || mode[0] == 'w');
+    const int ws = (mode && mode[0] == 'w') ? atoi(mode + 2) : -1;
     const int g4mix = (g4 && mode[2] == 'm') ? (mode[5] ? mode[5] - '0' : 1) : 0;
     CUtensorMap tmap;
     if (g4) {
@@ -390,7 +465,18 @@ extern "C" int st_bench_gather(int device, int64_t bytes, int64_t loads_per_thre
             k_gather_tex<0><<<grid, tpb>>>(tex, static_cast<const ulonglong4 *>(buf), n_sectors, loads_per_thread, seed, sink);
         else if (mix)
             k_gather_tex<1><<<grid, tpb>>>(tex, static_cast<const ulonglong4 *>(buf), n_sectors, loads_per_thread, seed, sink);
-        else if (g4) {
+        else if (ws >= 0) {
+            const int64_t rounds = loads_per_thread / 4;
+            const ulonglong4 *b = static_cast<const ulonglong4 *>(buf);
+            switch (ws) {  // 3 CTAs of 512 threads per SM at most (shared memory of the TMA warps)
+                case 0: k_gather_ws<0><<<grid, tpb>>>(tmap, b, n_sectors, rounds, seed, sink); break;
+                case 2: k_gather_ws<2><<<grid, tpb>>>(tmap, b, n_sectors, rounds, seed, sink); break;
+                case 4: k_gather_ws<4><<<grid, tpb>>>(tmap, b, n_sectors, rounds, seed, sink); break;
+                case 1: k_gather_ws<1><<<grid, tpb>>>(tmap, b, n_sectors, rounds, seed, sink); break;
+                case 3: k_gather_ws<3><<<grid, tpb>>>(tmap, b, n_sectors, rounds, seed, sink); break;
+                default: k_gather_ws<5><<<grid, tpb>>>(tmap, b, n_sectors, rounds, seed, sink); break;
+            }
+        } else if (g4) {
             const int64_t rounds = loads_per_thread / 4;
             if (g4mix == 0) k_gather_g4<0><<<grid * 4, tpb / 4>>>(tmap, static_cast<const ulonglong4 *>(buf), n_sectors, rounds, seed, sink);
             else if (g4mix == 1) k_gather_g4<1><<<grid * 4, tpb / 4>>>(tmap, static_cast<const ulonglong4 *>(buf), n_sectors, rounds, seed, sink);
@@ -422,6 +508,6 @@ extern "C" int st_bench_gather(int device, int64_t bytes, int64_t loads_per_thre
         st_set_error("st_bench_gather: %s", cudaGetErrorString(e));
         return ST_ERR_CUDA;
     }
-    *sectors_per_s = double(grid) * tpb * double(loads_per_thread) * (1 + g4mix) / (double(best_ms) * 1e-3);
+    *sectors_per_s = double(grid) * tpb * double(loads_per_thread) * (1 + (ws >= 0 ? 0 : g4mix)) / (double(best_ms) * 1e-3);
     return ST_OK;
 }
