@@ -65,6 +65,7 @@ class SuchTree:
         self._leaves = ft.leaves
         self._leaf_nodes = None
         self._RED = {}
+        self._rd = None
         if device is None:
             device = int(os.environ.get("LOCAL_RANK", "0"))
         self._handle = C.c_void_p()
@@ -289,6 +290,118 @@ class SuchTree:
     def get_descendants(self, node):
         lo, hi = self._clade_interval(self._validate_node(node))
         return np.arange(lo, hi + 1, dtype=np.int64)
+
+    def traverse_preorder(self, from_node=None):
+        """Node ids in preorder (root, left, right); MuchTree.pyx:1502-1536."""
+        start = self._root if from_node is None else self._validate_node(from_node)
+        left, right = self._ft.left, self._ft.right
+        stack = [start]
+        while stack:
+            cur = stack.pop()
+            r, l = int(right[cur]), int(left[cur])
+            if r != -1:
+                stack.append(r)
+            if l != -1:
+                stack.append(l)
+            yield cur
+
+    def pre_order(self):
+        _deprecation_warning("pre_order()", "traverse_preorder()")
+        return self.traverse_preorder()
+
+    # ====== thin callers of the device index (SURVEY.md §8f N4) ======
+    def _root_distances(self):
+        """fp64 root distance of every node, as built on the device (hi + lo of the
+        double-double); fetched once."""
+        if self._rd is None:
+            _, hi, lo = self.export_index()
+            self._rd = hi + lo
+        return self._rd
+
+    def distance_to_root(self, node):
+        """Distance from a node to the root; MuchTree.pyx:813-850.  The reference walks
+        to the root adding fp32 edges; here it is one lookup in the device-built root
+        distances (fp64 sum of the same fp32-quantised edges)."""
+        return float(self._root_distances()[self._validate_node(node)])
+
+    def get_distance_to_root(self, node):
+        _deprecation_warning("get_distance_to_root()", "distance_to_root()")
+        return self.distance_to_root(node)
+
+    @property
+    def relative_evolutionary_divergence(self):
+        """RED of every node (Parks et al. 2018), dict node id -> RED in the reference's
+        preorder insertion order; MuchTree.pyx:303-330.  a = edge to the parent, b = mean
+        distance from the node to its leaf descendants.  The reference calls distance()
+        once per (node, leaf) pair -- O(N x leaves); here b comes from one bottom-up
+        pass, S[v] = S[l] + n[l] e[l] + S[r] + n[r] e[r] (all terms of one sign for
+        ordinary trees: no cancellation, epsilon edges survive), level by level."""
+        if not self._RED:
+            n = self.size
+            parent, left, right = self._ft.parent, self._ft.left, self._ft.right
+            edge = self._ft.distance.astype(np.float64)
+            edge[self._root] = 0.0
+            depth, _, _ = self.export_index()  # device-built node depths
+            levels = np.unique(depth)
+            S = np.zeros(n, dtype=np.float64)
+            cnt = (left == -1).astype(np.float64)
+            for d in levels[::-1]:
+                lvl = np.nonzero((depth == d) & (left != -1))[0]
+                if lvl.size:
+                    l, r = left[lvl], right[lvl]
+                    S[lvl] = (S[l] + cnt[l] * edge[l]) + (S[r] + cnt[r] * edge[r])
+                    cnt[lvl] = cnt[l] + cnt[r]
+            b = S / cnt
+            red = np.zeros(n, dtype=np.float64)
+            for d in levels:
+                if d == 0:
+                    continue
+                lvl = np.nonzero(depth == d)[0]
+                ab = edge[lvl] + b[lvl]
+                if np.any(ab == 0):
+                    bad = int(lvl[np.nonzero(ab == 0)[0][0]])
+                    raise Exception("node {n} : a={a}, b={b}".format(n=bad, a=edge[bad], b=b[bad]))
+                P = red[parent[lvl]]
+                red[lvl] = P + (edge[lvl] / ab) * (1 - P)
+            out = {self._root: 0}
+            for node in list(self.traverse_preorder())[1:]:
+                out[node] = float(red[node])
+            self._RED = out
+        return self._RED
+
+    RED = relative_evolutionary_divergence
+
+    def relationships(self):
+        """DataFrame of all leaf pairs with distance, root distances, MRCA and the two
+        legs of the path; MuchTree.pyx:2158-2179 (pair orientation is random there:
+        sample([a,b],2)).  One bulk distance launch + one bulk MRCA launch."""
+        from itertools import combinations
+        from random import sample
+
+        import pandas as pd
+
+        pairs = [sample([a, b], 2) for a, b in combinations(self.leaves.keys(), 2)]
+        ids = np.array([(self.leaves[a], self.leaves[b]) for a, b in pairs], dtype=np.int64).reshape(-1, 2)
+        rd = self._root_distances()
+        if len(pairs):
+            distances = self.distances_bulk(ids).tolist()
+            mrca = self.common_ancestors_bulk(ids).astype(np.int64)
+        else:
+            distances, mrca = [], np.zeros(0, np.int64)
+        a_to_root = rd[ids[:, 0]]
+        b_to_root = rd[ids[:, 1]]
+        mrca_to_root = rd[mrca]
+        return pd.DataFrame({
+            "a": [p[0] for p in pairs],
+            "b": [p[1] for p in pairs],
+            "distance": distances,
+            "a_to_root": a_to_root.tolist(),
+            "b_to_root": b_to_root.tolist(),
+            "mrca": mrca.tolist(),
+            "mrca_to_root": mrca_to_root.tolist(),
+            "a_to_mrca": (a_to_root - mrca_to_root).tolist(),
+            "b_to_mrca": (b_to_root - mrca_to_root).tolist(),
+        })
 
     # ====== the hot path ======
     def distance(self, a, b):
