@@ -209,6 +209,13 @@ typedef struct st_moments {
 ST_API int st_sample_moments(const st_tree *tree_a, const st_tree *tree_b, const int64_t *linklist,
                       int64_t n_links, uint64_t seed, int64_t first_sample, int64_t n_samples,
                       double x0, double y0, st_moments *out);
+/* ---- exhaustive variant: the same moments over link pairs [first_pair, first_pair +
+ * n_pairs) of linked_distances()'s enumeration (MuchTree.pyx:2919-2925), i.e.
+ * linked_distances() + pearson() (:2900-2934, :62-87) fused, nothing materialised.
+ * Shard the pair range across GPUs and add the sums. */
+ST_API int st_linked_moments(const st_tree *tree_a, const st_tree *tree_b, const int64_t *linklist,
+                      int64_t n_links, int64_t first_pair, int64_t n_pairs, double x0, double y0,
+                      st_moments *out);
 /* Pearson r from (possibly all-reduced) moments: sxy / sqrt(sxx*syy + 1e-20),
  * the reference's formula (MuchTree.pyx:79) on centred sums. */
 ST_API double st_moments_pearson(const st_moments *m);

@@ -460,6 +460,92 @@ extern "C" int st_sample_moments(const st_tree *ta, const st_tree *tb, const int
     return ST_OK;
 }
 
+// ------------------------------------- exhaustive link pairs, fused moments --
+// linked_distances() followed by pearson() without the two distance vectors: the
+// moments of (d_A, d_B) over link pairs k in [first, first + n) of the reference's
+// enumeration (MuchTree.pyx:2919-2925), reduced in registers / shuffles / one partial
+// per CTA.  This is the inner loop of the reference's per-clade correlation scan
+// (docs/examples/SuchLinkedTree_examples.md:299-310).  Shardable by k-range.
+__global__ void __launch_bounds__(MLT)
+k_linked_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ links, int64_t first,
+                 int64_t n, double x0, double y0, double *__restrict__ partials /* [grid][5] */) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SmemTables sa = st_load_tables(ta, smem_raw);
+    const int offs = (st_table_bytes(ta.n_blocks, ta.st_levels, ta.compact) + 15) & ~15;
+    const SmemTables sb = st_load_tables(tb, smem_raw + offs);
+    __shared__ double red[5][MLT / 32];
+
+    Mom5 m{0, 0, 0, 0, 0};
+    for (int64_t q = int64_t(blockIdx.x) * MLT + threadIdx.x; q < n; q += int64_t(gridDim.x) * MLT) {
+        int64_t i, j;
+        tri_unrank(first + q, i, j);
+        const int2 l1 = __ldg(links + j), l2 = __ldg(links + i);
+        const double x = linked_query(ta, sa, l1.y, l2.y) - x0;
+        const double y = linked_query(tb, sb, l1.x, l2.x) - y0;
+        m.sx += x; m.sy += y;
+        m.sxx += x * x; m.syy += y * y; m.sxy += x * y;
+    }
+    double v[5] = {m.sx, m.sy, m.sxx, m.syy, m.sxy};
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        double s = warp_sum(v[k]);
+        if (lane == 0) red[k][wid] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double s = 0;
+        for (int w2 = 0; w2 < MLT / 32; ++w2) s += red[threadIdx.x][w2];
+        partials[size_t(blockIdx.x) * 5 + threadIdx.x] = s;
+    }
+}
+
+extern "C" int st_linked_moments(const st_tree *ta, const st_tree *tb, const int64_t *linklist,
+                                 int64_t L, int64_t first_pair, int64_t n_pairs, double x0, double y0,
+                                 st_moments *out) {
+    int rc = check_pair_of_trees(ta, tb, linklist, L);
+    if (rc != ST_OK) return rc;
+    const int64_t total = L * (L - 1) / 2;
+    if (!out || first_pair < 0 || n_pairs < 0 || first_pair + n_pairs > total) {
+        st_set_error("st_linked_moments: bad arguments (pairs [%lld, %lld) of %lld)", (long long)first_pair,
+                     (long long)(first_pair + n_pairs), (long long)total);
+        return ST_ERR_INVALID_ARG;
+    }
+    out->n = double(n_pairs);
+    out->x0 = x0;
+    out->y0 = y0;
+    out->sx = out->sy = out->sxx = out->syy = out->sxy = 0.0;
+    if (n_pairs == 0) return ST_OK;
+    DeviceGuard g(ta->device);
+    DevLinks dl;
+    rc = upload_links(ta, tb, linklist, L, dl, false, true);
+    if (rc != ST_OK) return rc;
+    const int smem = ((ta->query_smem_bytes + 15) & ~15) + tb->query_smem_bytes;
+    rc = set_smem(k_linked_moments, smem);
+    if (rc != ST_OK) return rc;
+    int per_sm = 0;
+    ST_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linked_moments, MLT, smem));
+    if (per_sm < 1) per_sm = 1;
+    int grid = int(std::min<int64_t>((n_pairs + MLT - 1) / MLT, int64_t(ta->sm_count) * per_sm));
+    cudaStream_t s = ta->streams[0];
+    double *d_part = nullptr;
+    ST_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d_part), size_t(grid + 1) * 5 * 8, s));
+    double *d_out = d_part + size_t(grid) * 5;
+    k_linked_moments<<<grid, MLT, smem, s>>>(ta->view, tb->view, dl.rows, first_pair, n_pairs, x0, y0, d_part);
+    k_reduce_partials<<<1, 160, 0, s>>>(grid, d_part, d_out);
+    double h[5];
+    cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, s);
+    cudaFreeAsync(d_part, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        st_set_error("st_linked_moments: %s", cudaGetErrorString(e));
+        return ST_ERR_CUDA;
+    }
+    out->sx = h[0]; out->sy = h[1]; out->sxx = h[2]; out->syy = h[3]; out->sxy = h[4];
+    return ST_OK;
+}
+
 extern "C" double st_moments_pearson(const st_moments *m) {
     if (!m || m->n <= 0) return 0.0;
     // centred second moments from shifted sums; the shift cancels exactly in exact arithmetic

@@ -265,6 +265,34 @@ class SuchLinkedTrees:
         _lib.check(rc)
         return m
 
+    def linked_moments(self, first_pair=0, n_pairs=None, x0=0.0, y0=0.0):
+        """Moments of (d_A, d_B) over the link pairs [first_pair, first_pair + n_pairs) of
+        linked_distances()'s enumeration, fused on the device (nothing materialised)."""
+        L = self._subset_n_links
+        total = (L * (L - 1)) // 2
+        if n_pairs is None:
+            n_pairs = total - first_pair
+        ll = self._linklist_c()
+        m = _lib.Moments()
+        rc = _lib.lib().st_linked_moments(
+            self._TreeA._handle, self._TreeB._handle, ll.ctypes.data, L, int(first_pair), int(n_pairs),
+            float(x0), float(y0), C.byref(m))
+        _lib.check(rc)
+        return m
+
+    def linked_pearson(self):
+        """pearson(linked_distances()['TreeA'], linked_distances()['TreeB']) in one fused
+        pass -- the inner step of the reference's per-clade correlation scans
+        (subset_b(clade); linked_distances(); pearson())."""
+        L = self._subset_n_links
+        if L < 2:
+            return 0.0
+        # shift by the first pair's distances for conditioning
+        ll = self.linklist
+        x0 = self._TreeA.distance(int(ll[0, 1]), int(ll[1, 1]))
+        y0 = self._TreeB.distance(int(ll[0, 0]), int(ll[1, 0]))
+        return moments_pearson(self.linked_moments(x0=x0, y0=y0))
+
     def sample_pearson(self, n_samples, seed=0):
         """Sampled two-tree Pearson r over n_samples link pairs drawn with replacement."""
         m = self.sample_moments(n_samples, seed=seed)

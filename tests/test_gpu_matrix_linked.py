@@ -156,6 +156,35 @@ def test_linked_distances_match_reference(name):
     assert pearson(r["TreeA"], r["TreeB"]) == pytest.approx(float(z["pearson"]), abs=2e-4)
 
 
+@pytest.mark.parametrize("name", list(LINKED))
+def test_linked_pearson_fused_equals_two_step(name):
+    """linked_pearson() (moments fused on the device, nothing materialised) against
+    pearson(linked_distances()) and the reference's own value; sharded pair ranges
+    (the multi-GPU decomposition) add up to the same moments."""
+    z = np.load(os.path.join(GOLDEN, "linked_%s.npz" % name))
+    SLT, T1, T2 = _slt(name)
+    r = SLT.linked_distances()
+    want = O.pearson_f64(r["TreeA"], r["TreeB"])
+    assert SLT.linked_pearson() == pytest.approx(want, abs=1e-10)
+    assert SLT.linked_pearson() == pytest.approx(float(z["pearson"]), abs=2e-4)
+    total = r["n_pairs"]
+    cut = [0, total // 3, total // 3 + 1, total]
+    parts = [SLT.linked_moments(first_pair=a, n_pairs=b - a) for a, b in zip(cut[:-1], cut[1:])]
+    whole = SLT.linked_moments()
+    for k in ("n", "sx", "sy", "sxx", "syy", "sxy"):
+        assert sum(getattr(p, k) for p in parts) == pytest.approx(getattr(whole, k), rel=1e-12, abs=1e-12)
+    assert whole.sx == pytest.approx(r["TreeA"].sum(), rel=1e-12) and whole.sxy == pytest.approx(
+        (r["TreeA"] * r["TreeB"]).sum(), rel=1e-12)
+    # clade scan step: subset, then the fused correlation
+    node = int(T2.get_parent(list(T2.leaves.values())[0]))
+    if T2.get_parent(node) >= 0:
+        node = int(T2.get_parent(node))
+    SLT.subset_b(node)
+    if SLT.subset_n_links > 2:
+        rs = SLT.linked_distances()
+        assert SLT.linked_pearson() == pytest.approx(O.pearson_f64(rs["TreeA"], rs["TreeB"]), abs=1e-9)
+
+
 def test_published_gopher_louse_pearson(published):
     SLT, _, _ = _slt("gopher_louse")
     r = SLT.linked_distances()
