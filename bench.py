@@ -582,6 +582,48 @@ def run_other_workloads(args, rank, world, local, dev, peak):
         "samples_per_s": world * n4 / sec, "ms_per_call": sec * 1e3, "pearson_r": moments_pearson(m),
         "timing": "host wall clock around the blocking C-ABI call (includes link upload + moment read-back)",
     }
+    # ---- exhaustive link pairs, fused moments (linked_distances + pearson in one pass):
+    #      44,904 links as in the reference's bigtrees example -> 1.008e9 link pairs,
+    #      one eighth of the pair range per GPU
+    L = 44_904
+    ll2 = np.ascontiguousarray(linklist[:L])
+    total = L * (L - 1) // 2
+    pb, pe = shard.pair_range(rank, max(world, 8), total)
+
+    def exhaustive():
+        m = L_.Moments()
+        L_.check(L_.lib().st_linked_moments(TA._handle, TB._handle, ll2.ctypes.data, L, pb, pe - pb, 0.0, 0.0,
+                                            C.byref(m)))
+        return m
+
+    exhaustive()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        m2 = exhaustive()
+    sec = max_over_ranks((time.perf_counter() - t0) / reps)
+    res["linked_exhaustive_moments"] = {
+        "workload": "44,904 links (1.008e9 link pairs): pairs [%d,%d) per GPU, both trees, moments fused" % (pb, pe),
+        "link_pairs_per_s": world * (pe - pb) / sec, "ms_per_call": sec * 1e3,
+        "timing": "host wall clock around the blocking C-ABI call",
+    }
+    del TA, TB
+
+    # ---- N1: quartet topologies, 5e7 random leaf quartets per GPU, device resident
+    T = SuchTree.from_flat(synth.yule_tree(TREE_LEAVES, seed=TREE_SEED), device=local)
+    nq = args.quartets
+    g = torch.Generator(device=dev).manual_seed(21 + rank)
+    quartets = 2 * torch.randint(0, TREE_LEAVES, (nq, 4), generator=g, device=dev, dtype=torch.int64)
+    topo = torch.empty_like(quartets)
+    sec = max_over_ranks(_timed(stream, lambda: T.quartet_topologies_device(quartets.data_ptr(), nq, topo.data_ptr(),
+                                                                            stream=sptr), steps=5))
+    T.check_range(sptr)
+    is_perm = bool(torch.equal(torch.sort(topo, dim=1).values, torch.sort(quartets, dim=1).values))
+    res["n1_quartet_topologies"] = {
+        "workload": "%d random leaf quartets per GPU per launch on the cfg2 tree (int64 x4 in, int64 x4 out)" % nq,
+        "quartets_per_s": world * nq / sec, "ms_per_launch": sec * 1e3,
+        "hbm_frac": 64.0 * nq / sec / 1e9 / peak, "rows_are_permutations": is_perm,
+    }
     return res
 
 def main():
@@ -596,6 +638,7 @@ def main():
     ap.add_argument("--no-other-workloads", action="store_true", help="skip the cfg3/cfg4/cfg5 side measurements")
     ap.add_argument("--cfg3-pairs", type=int, default=1_250_000_000, help="cfg3 pairs per GPU per launch")
     ap.add_argument("--cfg4-samples", type=int, default=125_000_000, help="cfg4 samples per GPU per call")
+    ap.add_argument("--quartets", type=int, default=50_000_000, help="quartets per GPU per launch")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
