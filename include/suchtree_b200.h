@@ -60,8 +60,9 @@ typedef struct st_tree_info {
     int64_t index_bytes;  /* device bytes held by the index */
     int32_t query_smem_bytes;
     int32_t sm_count;
-    int32_t layout;       /* 0 = wide records (32 B/node, double-double root distance),
-                             1 = compact records (16 B/node; every root distance exact in fp64) */
+    int32_t layout;       /* 0 = wide records (32 B/node, double-double root distance) + 64-bit block tables,
+                             1 = compact records (16 B/node; every root distance exact in fp64) + 32-bit tables,
+                             2 = wide records + 32-bit block tables (inexact root distances) */
 } st_tree_info;
 
 /* thread-local text of the last error raised on this thread ("" if none) */

@@ -106,12 +106,18 @@ __device__ __forceinline__ void st_st_stream_i32(int32_t *p, int32_t a) {
                  "l"(st_policy_evict_first())
                  : "memory");
 }
-// Layout mode of the accessors below: 0 = wide records (32 B, double-double rd,
-// 64-bit keys), 1 = compact records (16 B), 2 = decided at run time from tv.compact
-// (kernels off the headline path).
+// Layout mode of the accessors below:
+//   0 = wide records (32 B, double-double rd, 64-bit keys) + wide block tables
+//   1 = compact records (16 B) + compact block tables
+//   3 = wide records + compact block tables (inexact root distances, ordinary depths)
+//   2 = decided at run time from tv.compact / tv.compact_tables (kernels off the headline path)
 template <int M>
-__device__ __forceinline__ bool st_compact(const TreeView &tv) {
+__device__ __forceinline__ bool st_compact(const TreeView &tv) {  // records
     return M == 2 ? tv.compact != 0 : M == 1;
+}
+template <int M>
+__device__ __forceinline__ bool st_ctab(const TreeView &tv) {  // block tables
+    return M == 2 ? tv.compact_tables != 0 : (M == 1 || M == 3);
 }
 
 // one node record = one sector (or half of one), fetched with ONE 256-bit load
@@ -206,7 +212,7 @@ __device__ __forceinline__ uint64_t st_rmq(const TreeView &tv, const SmemTables 
     int32_t span = bhi - blo - 1;
     if (span > 0) {
         int k = 31 - __clz(span);
-        if (st_compact<M>(tv)) {
+        if (st_ctab<M>(tv)) {
             const uint32_t *lvl = sm.stk32 + k * tv.n_blocks;
             const uint32_t mid = min(lvl[blo + 1], lvl[bhi - (1 << k)]);
             // candidates are distinct nodes and the minimum depth is unique: no ties
@@ -233,7 +239,8 @@ __device__ __forceinline__ dd st_mrca_rd(const TreeView &tv, const SmemTables &s
     int32_t id = st_key_id(key);
     if (from_table) {
         if (st_compact<M>(tv)) return dd{sm.brd8[id], 0.0};
-        double2 r = sm.brd[id >> tv.block_shift];
+        // compact tables name the BLOCK, wide ones the node
+        double2 r = sm.brd[st_ctab<M>(tv) ? id : id >> tv.block_shift];
         return dd{r.x, r.y};
     }
     return st_ld_rd<M>(tv, id);
@@ -242,12 +249,17 @@ __device__ __forceinline__ dd st_mrca_rd(const TreeView &tv, const SmemTables &s
 template <int M = 2>
 __device__ __forceinline__ int32_t st_mrca_id(const TreeView &tv, const SmemTables &sm, uint64_t key,
                                               bool from_table) {
-    if (from_table && st_compact<M>(tv)) return sm.bid[st_key_id(key)];
+    if (from_table && st_ctab<M>(tv)) return sm.bid[st_key_id(key)];
     return st_key_id(key);
 }
 
+// compact: 0 = wide tables, 1 = compact tables + compact records, 2 = compact tables + wide records
 __host__ __device__ __forceinline__ int st_table_bytes(int n_blocks, int st_levels, int compact) {
-    return compact ? n_blocks * (4 * st_levels + 12) : n_blocks * (8 * st_levels + 16);
+    return compact == 1 ? n_blocks * (4 * st_levels + 12)
+                        : (compact == 2 ? n_blocks * (4 * st_levels + 20) : n_blocks * (8 * st_levels + 16));
+}
+__host__ __device__ __forceinline__ int st_table_mode(const TreeView &tv) {
+    return tv.compact ? 1 : (tv.compact_tables ? 2 : 0);
 }
 
 // cooperative copy of the block tables into dynamic shared memory (16-byte aligned)
@@ -265,6 +277,16 @@ __device__ __forceinline__ SmemTables st_load_tables(const TreeView &tv, unsigne
         }
         for (int i = threadIdx.x; i < tot; i += blockDim.x) stk32[i] = tv.stk32[i];
         sm.stk32 = stk32; sm.brd8 = brd8; sm.bid = bid;
+    } else if (st_ctab<M>(tv)) {
+        double2 *brd = reinterpret_cast<double2 *>(smem);
+        int32_t *bid = reinterpret_cast<int32_t *>(brd + nb);
+        uint32_t *stk32 = reinterpret_cast<uint32_t *>(bid + nb);
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+            brd[i] = tv.brd[i];
+            bid[i] = tv.bid[i];
+        }
+        for (int i = threadIdx.x; i < tot; i += blockDim.x) stk32[i] = tv.stk32[i];
+        sm.stk32 = stk32; sm.brd = brd; sm.bid = bid;
     } else {
         double2 *brd = reinterpret_cast<double2 *>(smem);
         uint64_t *stk = reinterpret_cast<uint64_t *>(brd + nb);

@@ -28,6 +28,11 @@ struct Pool {
         if (sched_getaffinity(0, sizeof(set), &set) == 0) hw = std::min(hw > 0 ? hw : 1 << 20, CPU_COUNT(&set));
 #endif
         if (hw < 1) hw = 1;
+        // one process per GPU (torchrun): share the cores between the local ranks
+        if (const char *e = getenv("LOCAL_WORLD_SIZE")) {
+            const int lw = atoi(e);
+            if (lw > 1) hw = std::max(1, hw / lw);
+        }
         n_threads = std::min(hw, 16);
         if (const char *e = getenv("SUCHTREE_B200_HOST_THREADS")) {
             int v = atoi(e);

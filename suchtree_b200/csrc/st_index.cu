@@ -532,39 +532,50 @@ extern "C" int st_tree_create_ex(int device, int64_t n_nodes, const int32_t *par
     bool want_compact = !(flags & ST_TREE_WIDE_LAYOUT);
     if (const char *e = getenv("SUCHTREE_B200_LAYOUT")) want_compact = want_compact && e[0] != 'w';
     if (want_compact && (uint64_t(maxd) >> (32 - std::max(bs, ts))) == 0) {
+        // the depths fit: 32-bit block tables in any case ...
+        int64_t cbytes = 0;
+        ST_TRY2(dev_alloc(&t->d_stk32, size_t(t->st_levels) * t->n_blocks, &cbytes));
+        ST_TRY2(dev_alloc(&t->d_brd8, size_t(t->n_blocks), &cbytes));
+        ST_TRY2(dev_alloc(&t->d_bid, size_t(t->n_blocks), &cbytes));
+        const int tot = t->st_levels * t->n_blocks;
+        k_compact_tables<<<(tot + TPB - 1) / TPB, TPB, 0, s>>>(t->n_blocks, t->st_levels, bs, ts, t->d_stk,
+                                                              t->d_brd, t->d_stk32, t->d_brd8, t->d_bid);
+        ST_TRY2_CUDA(cudaGetLastError());
+        t->compact_tables = 1;
+        t->index_bytes += cbytes - int64_t(size_t(t->st_levels) * t->n_blocks * 8);
+        // ... and 16-byte records when every root distance is exact in fp64
         ST_TRY2_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), s));
         k_any_nonzero<<<grid, TPB, 0, s>>>(n, d_rlo[cur], d_flag);
         int inexact = 0;
         ST_TRY2_CUDA(cudaMemcpy(&inexact, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+        if (const char *e = getenv("SUCHTREE_B200_LAYOUT"))
+            if (e[0] == 't') inexact = 1;  // "tables": keep the wide records (experiments)
         if (!inexact) {
-            int64_t cbytes = 0;
-            ST_TRY2(dev_alloc(&t->d_rec16, size_t(n), &cbytes));
-            ST_TRY2(dev_alloc(&t->d_stk32, size_t(t->st_levels) * t->n_blocks, &cbytes));
-            ST_TRY2(dev_alloc(&t->d_brd8, size_t(t->n_blocks), &cbytes));
-            ST_TRY2(dev_alloc(&t->d_bid, size_t(t->n_blocks), &cbytes));
+            int64_t rbytes = 0;
+            ST_TRY2(dev_alloc(&t->d_rec16, size_t(n), &rbytes));
             k_compact_records<<<grid, TPB, 0, s>>>(n, bs, t->d_rec, t->d_rec16);
-            const int tot = t->st_levels * t->n_blocks;
-            k_compact_tables<<<(tot + TPB - 1) / TPB, TPB, 0, s>>>(t->n_blocks, t->st_levels, bs, ts, t->d_stk,
-                                                                  t->d_brd, t->d_stk32, t->d_brd8, t->d_bid);
             ST_TRY2_CUDA(cudaGetLastError());
             ST_TRY2_CUDA(cudaDeviceSynchronize());
-            t->index_bytes += cbytes - int64_t(size_t(n) * sizeof(NodeRec)) -
-                              int64_t(size_t(t->st_levels) * t->n_blocks * 8) - int64_t(size_t(t->n_blocks) * 16);
+            t->index_bytes += rbytes - int64_t(size_t(n) * sizeof(NodeRec)) - int64_t(size_t(t->n_blocks) * 16);
             cudaFree(t->d_rec); t->d_rec = nullptr;
-            cudaFree(t->d_stk); t->d_stk = nullptr;
             cudaFree(t->d_brd); t->d_brd = nullptr;
             t->compact = 1;
+        } else {
+            t->index_bytes -= int64_t(size_t(t->n_blocks) * 8);  // brd8 is not used with wide records
         }
+        ST_TRY2_CUDA(cudaDeviceSynchronize());
+        cudaFree(t->d_stk); t->d_stk = nullptr;
     }
     ST_TRY2_CUDA(cudaDeviceSynchronize());
     free_tmp();
 
-    t->query_smem_bytes = st_table_bytes(t->n_blocks, t->st_levels, t->compact);
+    t->query_smem_bytes = st_table_bytes(t->n_blocks, t->st_levels, t->compact ? 1 : (t->compact_tables ? 2 : 0));
     t->view.rec16 = t->d_rec16;
     t->view.stk32 = t->d_stk32;
     t->view.brd8 = t->d_brd8;
     t->view.bid = t->d_bid;
     t->view.compact = t->compact;
+    t->view.compact_tables = t->compact_tables;
     t->view.table_shift = ts;
     t->view.rec = t->d_rec;
     t->view.depth = t->d_depth;
@@ -600,7 +611,7 @@ extern "C" int st_tree_get_info(const st_tree *t, st_tree_info *info) {
     info->index_bytes = t->index_bytes;
     info->query_smem_bytes = t->query_smem_bytes;
     info->sm_count = t->sm_count;
-    info->layout = t->compact;
+    info->layout = t->compact ? 1 : (t->compact_tables ? 2 : 0);
     return ST_OK;
 }
 

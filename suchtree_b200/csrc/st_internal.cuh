@@ -87,8 +87,9 @@ struct TreeView {
     int32_t micro_shift;
     int32_t st_levels;  // levels stored, level k covers 2^k blocks, level 0 = identity (stored)
     int32_t m_levels;
-    int32_t compact;      // 1: rec16 / stk32 / brd8 / bid are the live tables
-    int32_t table_shift;  // compact block-table keys: depth << table_shift | block
+    int32_t compact;         // 1: rec16 (16-byte records) is the live node array
+    int32_t compact_tables;  // 1: stk32 / bid (+ brd8, or brd with wide records) are the live block tables
+    int32_t table_shift;     // compact block-table keys: depth << table_shift | block
 };
 
 struct st_tree {
@@ -107,7 +108,7 @@ struct st_tree {
     uint32_t *d_stk32 = nullptr;
     double *d_brd8 = nullptr;
     int32_t *d_bid = nullptr;
-    int compact = 0;
+    int compact = 0, compact_tables = 0;
     uint64_t *d_mst = nullptr;
     RangeStatus *d_status = nullptr;
     int32_t *d_leaf_ids = nullptr;  // lazily unused; leaves are the even ids

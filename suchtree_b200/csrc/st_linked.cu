@@ -366,7 +366,7 @@ k_sample_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // two table sets back to back (second one 16-byte aligned)
     const SmemTables sa = st_load_tables(ta, smem_raw);
-    const int offs = (st_table_bytes(ta.n_blocks, ta.st_levels, ta.compact) + 15) & ~15;
+    const int offs = (st_table_bytes(ta.n_blocks, ta.st_levels, st_table_mode(ta)) + 15) & ~15;
     const SmemTables sb = st_load_tables(tb, smem_raw + offs);
     __shared__ double red[5][MLT / 32];
 
@@ -471,7 +471,7 @@ k_linked_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ 
                  int64_t n, double x0, double y0, double *__restrict__ partials /* [grid][5] */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SmemTables sa = st_load_tables(ta, smem_raw);
-    const int offs = (st_table_bytes(ta.n_blocks, ta.st_levels, ta.compact) + 15) & ~15;
+    const int offs = (st_table_bytes(ta.n_blocks, ta.st_levels, st_table_mode(ta)) + 15) & ~15;
     const SmemTables sb = st_load_tables(tb, smem_raw + offs);
     __shared__ double red[5][MLT / 32];
 

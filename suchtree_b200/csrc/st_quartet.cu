@@ -127,8 +127,9 @@ static int launch_quartets_m(const st_tree *t, const int64_t *d_q, int64_t n, in
 static int launch_quartets(const st_tree *t, const int64_t *d_q, int64_t n, int64_t *d_out,
                            cudaStream_t stream) {
     if (n == 0) return ST_OK;
-    return t->compact ? launch_quartets_m<1>(t, d_q, n, d_out, stream)
-                      : launch_quartets_m<0>(t, d_q, n, d_out, stream);
+    if (t->compact) return launch_quartets_m<1>(t, d_q, n, d_out, stream);
+    if (t->compact_tables) return launch_quartets_m<3>(t, d_q, n, d_out, stream);
+    return launch_quartets_m<0>(t, d_q, n, d_out, stream);
 }
 
 extern "C" int st_quartet_topologies_device(const st_tree *t, const int64_t *d_quartets, int64_t n,

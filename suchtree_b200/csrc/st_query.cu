@@ -204,8 +204,9 @@ static int launch_variant_m(const st_tree *t, const void *d_pairs, int64_t n, do
 template <typename IdxT, int P>
 static int launch_variant(const st_tree *t, const void *d_pairs, int64_t n, double *d_out,
                           int32_t *d_mrca, cudaStream_t stream) {
-    return t->compact ? launch_variant_m<IdxT, P, 1>(t, d_pairs, n, d_out, d_mrca, stream)
-                      : launch_variant_m<IdxT, P, 0>(t, d_pairs, n, d_out, d_mrca, stream);
+    if (t->compact) return launch_variant_m<IdxT, P, 1>(t, d_pairs, n, d_out, d_mrca, stream);
+    if (t->compact_tables) return launch_variant_m<IdxT, P, 3>(t, d_pairs, n, d_out, d_mrca, stream);
+    return launch_variant_m<IdxT, P, 0>(t, d_pairs, n, d_out, d_mrca, stream);
 }
 
 static int st_pairs_per_thread() {  // SUCHTREE_B200_PPT = 1 | 2 | 4 (experiments)

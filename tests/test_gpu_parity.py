@@ -63,8 +63,9 @@ def test_small_trees_against_reference_and_oracle(golden_trees, geom, wide):
         pr = np.stack([np.arange(T.size), np.full(T.size, T.root_node)], axis=1).astype(np.int64)
         rd64, rl1 = ot.distances_f64(pr, with_l1=True)
         _check_distances(hi + lo, rd64, rl1, name + " rd")
-    # the fixtures exercise both layouts: epsilon edges force the wide one
-    assert layouts == ({0} if wide else {0, 1})
+    # the fixtures exercise every layout: epsilon edges keep the wide records (layout 2:
+    # wide records + 32-bit block tables), exact trees get the compact ones (layout 1)
+    assert layouts == ({0} if wide else {1, 2})
 
 
 @pytest.mark.parametrize("name", ["ml", "nj"])
