@@ -34,15 +34,31 @@ __device__ __forceinline__ void tri_unrank(int64_t k, int64_t &i, int64_t &j) {
     j = k - r * (r - 1) / 2;
 }
 
+// advance (i, j) by `step` positions of the enumeration (cheap for step <~ i)
+__device__ __forceinline__ void tri_advance(int64_t &i, int64_t &j, int64_t step) {
+    j += step;
+    while (j >= i) {
+        j -= i;
+        ++i;
+    }
+}
+
 // ids of one tree for link pairs [k0, k0+m): out[k-k0] = dist(col[j], col[i])
 __global__ void __launch_bounds__(LT)
 k_linked(const TreeView tv, const int32_t *__restrict__ col, int64_t k0, int64_t m,
          double *__restrict__ out, int64_t *__restrict__ ids_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SmemTables sm = st_load_tables(tv, smem_raw);
-    for (int64_t q = int64_t(blockIdx.x) * LT + threadIdx.x; q < m; q += int64_t(gridDim.x) * LT) {
-        int64_t i, j;
-        tri_unrank(k0 + q, i, j);
+    // every warp owns a contiguous run of the enumeration: un-rank once per thread, then
+    // step by 32 (lanes stay adjacent: coalesced link loads and result stores)
+    const int64_t n_warps = int64_t(gridDim.x) * (LT / 32);
+    const int64_t per_warp = ((m + n_warps - 1) / n_warps + 31) & ~int64_t(31);
+    const int64_t wbeg = (int64_t(blockIdx.x) * (LT / 32) + (threadIdx.x >> 5)) * per_warp;
+    const int64_t wend = wbeg + per_warp < m ? wbeg + per_warp : m;
+    int64_t q = wbeg + (threadIdx.x & 31);
+    int64_t i = 1, j = 0;
+    if (q < wend) tri_unrank(k0 + q, i, j);
+    for (; q < wend; q += 32, tri_advance(i, j, 32)) {
         int32_t a = __ldg(col + j), b = __ldg(col + i);
         st_st_stream_f64(out + q, linked_query(tv, sm, a, b));
         if (ids_out) {
@@ -476,9 +492,16 @@ k_linked_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ 
     __shared__ double red[5][MLT / 32];
 
     Mom5 m{0, 0, 0, 0, 0};
-    for (int64_t q = int64_t(blockIdx.x) * MLT + threadIdx.x; q < n; q += int64_t(gridDim.x) * MLT) {
-        int64_t i, j;
-        tri_unrank(first + q, i, j);
+    // every warp owns a contiguous run of the enumeration: un-rank once per thread, then
+    // step by 32 (lanes stay adjacent: coalesced link loads)
+    const int64_t n_warps = int64_t(gridDim.x) * (MLT / 32);
+    const int64_t per_warp = ((n + n_warps - 1) / n_warps + 31) & ~int64_t(31);
+    const int64_t wbeg = (int64_t(blockIdx.x) * (MLT / 32) + (threadIdx.x >> 5)) * per_warp;
+    const int64_t wend = wbeg + per_warp < n ? wbeg + per_warp : n;
+    int64_t q = wbeg + (threadIdx.x & 31);
+    int64_t i = 1, j = 0;
+    if (q < wend) tri_unrank(first + q, i, j);
+    for (; q < wend; q += 32, tri_advance(i, j, 32)) {
         const int2 l1 = __ldg(links + j), l2 = __ldg(links + i);
         const double x = linked_query(ta, sa, l1.y, l2.y) - x0;
         const double y = linked_query(tb, sb, l1.x, l2.x) - y0;
