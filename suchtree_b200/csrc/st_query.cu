@@ -181,17 +181,28 @@ static int launch_variant_m(const st_tree *t, const void *d_pairs, int64_t n, do
                             int32_t *d_mrca, cudaStream_t stream) {
     // 2 pairs/thread: 2 x 512 threads x 64 registers; 4 pairs/thread needs ~80 registers:
     // 3 x 256 threads (8 gathers in flight per thread)
-    constexpr int QT = P == 4 ? 256 : 512, MINB = P == 4 ? 3 : 2;
+#ifndef ST_QT_P2
+#define ST_QT_P2 512
+#define ST_MINB_P2 2
+#endif
+    constexpr int QT = P == 4 ? 256 : ST_QT_P2, MINB = P == 4 ? 3 : ST_MINB_P2;
     auto kern = k_pairs<IdxT, P, M, QT, MINB>;
-    static thread_local int configured_smem[64] = {0};  // per device, per thread: cheap re-check
-    const int smem = t->query_smem_bytes;
-    if (smem > 48 * 1024 && configured_smem[t->device & 63] < smem) {
+    // per device, per thread: the attribute and the occupancy query are made once per
+    // shared-memory size (they cost microseconds that single-pair calls would notice)
+    static thread_local int configured_smem[64] = {0};
+    static thread_local int cached_smem[64] = {0}, cached_per_sm[64] = {0};
+    const int smem = t->query_smem_bytes, dv = t->device & 63;
+    if (smem > 48 * 1024 && configured_smem[dv] < smem) {
         ST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured_smem[t->device & 63] = smem;
+        configured_smem[dv] = smem;
     }
-    int per_sm = 0;
-    ST_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, QT, smem));
-    if (per_sm < 1) per_sm = 1;
+    if (cached_per_sm[dv] == 0 || cached_smem[dv] != smem) {
+        int q = 0;
+        ST_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, QT, smem));
+        cached_per_sm[dv] = q < 1 ? 1 : q;
+        cached_smem[dv] = smem;
+    }
+    const int per_sm = cached_per_sm[dv];
     const int64_t items = std::max<int64_t>(n / P, 1);
     int64_t want = (items + QT - 1) / QT;
     int grid = int(std::min<int64_t>(want, int64_t(t->sm_count) * per_sm));
@@ -454,6 +465,40 @@ static void report_range(const int64_t *src, int64_t s0, int64_t s1, int64_t n, 
     st_set_error("node id %lld out of bounds (tree size %lld)", (long long)st_bad_node(), (long long)n_nodes);
 }
 
+// Latency path for small calls (distance(a,b), common_ancestor(a,b), short lists): the ids
+// are checked and packed on the host into pinned staging, ONE kernel reads them and writes
+// the results through the pinned mappings (zero-copy over PCIe), one synchronisation.
+static const int64_t ST_SMALL_CALL = 4096;
+
+static int host_pairs_small(const st_tree *t, const int64_t *pairs, int64_t s0, int64_t s1, int64_t n,
+                            double *out_d, int32_t *out_m) {
+    int rc = ensure_stage(t, n, true, true);
+    if (rc != ST_OK) return rc;
+    int32_t *hp = static_cast<int32_t *>(t->h_stage[0]);
+    int64_t mx = INT64_MIN, mn = INT64_MAX;
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t a = pairs[i * s0], b = pairs[i * s0 + s1];
+        mx = std::max(mx, std::max(a, b));
+        mn = std::min(mn, std::min(a, b));
+        hp[2 * i] = int32_t(a);
+        hp[2 * i + 1] = int32_t(b);
+    }
+    if (mn < 0 || mx >= t->n_nodes) {  // the reference's report (MuchTree.pyx:897-903)
+        st_set_bad_node(mx >= t->n_nodes ? mx : mn);
+        st_set_error("node id %lld out of bounds (tree size %lld)", (long long)st_bad_node(), (long long)t->n_nodes);
+        return ST_ERR_NODE_RANGE;
+    }
+    void *ho = t->h_out_stage[0];
+    cudaStream_t st = t->streams[0];
+    rc = st_launch_pairs(t, hp, 32, n, out_d ? static_cast<double *>(ho) : nullptr,
+                         out_m ? static_cast<int32_t *>(ho) : nullptr, st);
+    if (rc != ST_OK) return rc;
+    ST_CUDA(cudaStreamSynchronize(st));
+    if (out_d) memcpy(out_d, ho, size_t(n) * 8);
+    else memcpy(out_m, ho, size_t(n) * 4);
+    return ST_OK;
+}
+
 static int host_pairs_run(const st_tree *t, const int64_t *pairs, int64_t s0, int64_t s1, int64_t n,
                           double *out_d, int32_t *out_m) {
     if (!t || n < 0 || (n > 0 && (!pairs || (!out_d && !out_m)))) {
@@ -463,6 +508,7 @@ static int host_pairs_run(const st_tree *t, const int64_t *pairs, int64_t s0, in
     if (n == 0) return ST_OK;
     DeviceGuard g(t->device);
     std::lock_guard<std::mutex> lock(t->host_mu);
+    if (n <= ST_SMALL_CALL && !(out_d && out_m)) return host_pairs_small(t, pairs, s0, s1, n, out_d, out_m);
     const bool contiguous = (s1 == 1 && s0 == 2);
     const bool out_pinned = is_pinned(out_d ? static_cast<void *>(out_d) : static_cast<void *>(out_m));
     bool pack = true;
