@@ -166,7 +166,7 @@ struct SmemTables {
     const int32_t *bid;    // compact: [n_blocks]
 };
 __device__ __forceinline__ SmemTables st_global_tables(const TreeView &tv) {
-    return SmemTables{tv.stk, tv.brd, tv.stk32, tv.brd8, tv.bid};
+    return SmemTables{tv.stk, tv.brd, tv.stk32, tv.brd8, tv.bid};  // pointers into the device blob
 }
 
 __device__ __forceinline__ uint64_t st_scan_depth(const int32_t *__restrict__ depth, int32_t s,
@@ -253,49 +253,68 @@ __device__ __forceinline__ int32_t st_mrca_id(const TreeView &tv, const SmemTabl
     return st_key_id(key);
 }
 
-// compact: 0 = wide tables, 1 = compact tables + compact records, 2 = compact tables + wide records
-__host__ __device__ __forceinline__ int st_table_bytes(int n_blocks, int st_levels, int compact) {
-    return compact == 1 ? n_blocks * (4 * st_levels + 12)
-                        : (compact == 2 ? n_blocks * (4 * st_levels + 20) : n_blocks * (8 * st_levels + 16));
+// Layout of the block-table blob (device memory AND shared memory: the blob is staged
+// into shared memory by one bulk copy).  mode: 0 = wide tables, 1 = compact tables +
+// compact records, 2 = compact tables + wide records.  Sections are 16-byte aligned.
+struct TableLayout {
+    int off_brd, off_bid, off_stk, bytes;
+};
+__host__ __device__ __forceinline__ TableLayout st_table_layout(int nb, int levels, int mode) {
+    TableLayout L;
+    L.off_brd = 0;
+    const int brd_bytes = (mode == 1 ? nb * 8 : nb * 16);
+    L.off_bid = (brd_bytes + 15) & ~15;
+    L.off_stk = mode == 0 ? L.off_bid : L.off_bid + ((nb * 4 + 15) & ~15);
+    L.bytes = L.off_stk + ((levels * nb * (mode == 0 ? 8 : 4) + 15) & ~15);
+    return L;
+}
+__host__ __device__ __forceinline__ int st_table_bytes(int n_blocks, int st_levels, int mode) {
+    return st_table_layout(n_blocks, st_levels, mode).bytes;
 }
 __host__ __device__ __forceinline__ int st_table_mode(const TreeView &tv) {
     return tv.compact ? 1 : (tv.compact_tables ? 2 : 0);
 }
-
-// cooperative copy of the block tables into dynamic shared memory (16-byte aligned)
-template <int M = 2>
-__device__ __forceinline__ SmemTables st_load_tables(const TreeView &tv, unsigned char *smem) {
+__device__ __forceinline__ SmemTables st_tables_at(const unsigned char *base, const TreeView &tv, int mode) {
+    const TableLayout L = st_table_layout(tv.n_blocks, tv.st_levels, mode);
     SmemTables sm{nullptr, nullptr, nullptr, nullptr, nullptr};
-    const int nb = tv.n_blocks, tot = tv.st_levels * nb;
-    if (st_compact<M>(tv)) {
-        double *brd8 = reinterpret_cast<double *>(smem);
-        int32_t *bid = reinterpret_cast<int32_t *>(brd8 + nb);
-        uint32_t *stk32 = reinterpret_cast<uint32_t *>(bid + nb);
-        for (int i = threadIdx.x; i < nb; i += blockDim.x) {
-            brd8[i] = tv.brd8[i];
-            bid[i] = tv.bid[i];
-        }
-        for (int i = threadIdx.x; i < tot; i += blockDim.x) stk32[i] = tv.stk32[i];
-        sm.stk32 = stk32; sm.brd8 = brd8; sm.bid = bid;
-    } else if (st_ctab<M>(tv)) {
-        double2 *brd = reinterpret_cast<double2 *>(smem);
-        int32_t *bid = reinterpret_cast<int32_t *>(brd + nb);
-        uint32_t *stk32 = reinterpret_cast<uint32_t *>(bid + nb);
-        for (int i = threadIdx.x; i < nb; i += blockDim.x) {
-            brd[i] = tv.brd[i];
-            bid[i] = tv.bid[i];
-        }
-        for (int i = threadIdx.x; i < tot; i += blockDim.x) stk32[i] = tv.stk32[i];
-        sm.stk32 = stk32; sm.brd = brd; sm.bid = bid;
+    if (mode == 1) sm.brd8 = reinterpret_cast<const double *>(base + L.off_brd);
+    else sm.brd = reinterpret_cast<const double2 *>(base + L.off_brd);
+    if (mode == 0) {
+        sm.stk = reinterpret_cast<const uint64_t *>(base + L.off_stk);
     } else {
-        double2 *brd = reinterpret_cast<double2 *>(smem);
-        uint64_t *stk = reinterpret_cast<uint64_t *>(brd + nb);
-        for (int i = threadIdx.x; i < nb; i += blockDim.x) brd[i] = tv.brd[i];
-        for (int i = threadIdx.x; i < tot; i += blockDim.x) stk[i] = tv.stk[i];
-        sm.stk = stk; sm.brd = brd;
+        sm.bid = reinterpret_cast<const int32_t *>(base + L.off_bid);
+        sm.stk32 = reinterpret_cast<const uint32_t *>(base + L.off_stk);
     }
-    __syncthreads();
     return sm;
+}
+
+// Stage the block tables into dynamic shared memory (16-byte aligned) with ONE TMA bulk
+// copy (cp.async.bulk global -> shared, completion on an mbarrier) issued by thread 0.
+// `bar` is an 8-byte shared-memory word owned by the caller (one per table set).
+template <int M = 2>
+__device__ __forceinline__ SmemTables st_load_tables(const TreeView &tv, unsigned char *smem, uint64_t *bar) {
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(bar);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(tv.tables_bytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(tv.tables), "r"(tv.tables_bytes), "r"(bar_a)
+                     : "memory");
+    }
+    __syncthreads();  // the barrier is initialised before anyone polls it
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+            : "=r"(done)
+            : "r"(bar_a), "r"(0)
+            : "memory");
+    }
+    const int mode = st_compact<M>(tv) ? 1 : (st_ctab<M>(tv) ? 2 : 0);
+    return st_tables_at(smem, tv, mode);
 }
 
 // ------------------------------------------------------------ Philox --------

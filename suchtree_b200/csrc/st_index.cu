@@ -311,12 +311,16 @@ extern "C" void st_tree_destroy(st_tree *t) {
     DeviceGuard g(t->device);
     cudaFree(t->d_rec);
     cudaFree(t->d_rec16);
-    cudaFree(t->d_stk32);
-    cudaFree(t->d_brd8);
-    cudaFree(t->d_bid);
     cudaFree(t->d_depth);
-    cudaFree(t->d_stk);
-    cudaFree(t->d_brd);
+    if (t->d_tables) {
+        cudaFree(t->d_tables);  // d_stk / d_brd / d_stk32 / d_brd8 / d_bid point into it
+    } else {                    // creation failed before the blob was packed
+        cudaFree(t->d_stk32);
+        cudaFree(t->d_brd8);
+        cudaFree(t->d_bid);
+        cudaFree(t->d_stk);
+        cudaFree(t->d_brd);
+    }
     cudaFree(t->d_mst);
     cudaFree(t->d_status);
     for (int i = 0; i < 3; ++i) {
@@ -569,7 +573,39 @@ extern "C" int st_tree_create_ex(int device, int64_t n_nodes, const int32_t *par
     ST_TRY2_CUDA(cudaDeviceSynchronize());
     free_tmp();
 
-    t->query_smem_bytes = st_table_bytes(t->n_blocks, t->st_levels, t->compact ? 1 : (t->compact_tables ? 2 : 0));
+    // ---- the block tables as ONE blob in their shared-memory layout: every query CTA stages
+    //      it with a single TMA bulk copy; the view's table pointers point into it
+    const int tmode = t->compact ? 1 : (t->compact_tables ? 2 : 0);
+    const TableLayout TL = st_table_layout(t->n_blocks, t->st_levels, tmode);
+    {
+        int64_t blob_bytes = 0;
+        ST_TRY(dev_alloc(&t->d_tables, size_t(TL.bytes), &blob_bytes));  // counted below
+        ST_TRY_CUDA(cudaMemset(t->d_tables, 0, size_t(TL.bytes)));
+        const size_t nb = size_t(t->n_blocks), lv = size_t(t->st_levels);
+        if (tmode == 1) ST_TRY_CUDA(cudaMemcpy(t->d_tables + TL.off_brd, t->d_brd8, nb * 8, cudaMemcpyDeviceToDevice));
+        else ST_TRY_CUDA(cudaMemcpy(t->d_tables + TL.off_brd, t->d_brd, nb * 16, cudaMemcpyDeviceToDevice));
+        if (tmode == 0) {
+            ST_TRY_CUDA(cudaMemcpy(t->d_tables + TL.off_stk, t->d_stk, lv * nb * 8, cudaMemcpyDeviceToDevice));
+        } else {
+            ST_TRY_CUDA(cudaMemcpy(t->d_tables + TL.off_bid, t->d_bid, nb * 4, cudaMemcpyDeviceToDevice));
+            ST_TRY_CUDA(cudaMemcpy(t->d_tables + TL.off_stk, t->d_stk32, lv * nb * 4, cudaMemcpyDeviceToDevice));
+        }
+        // the separately built arrays are now dead
+        t->index_bytes += blob_bytes - int64_t(tmode == 0 ? lv * nb * 8 + nb * 16
+                                                          : lv * nb * 4 + nb * 4 + (tmode == 1 ? nb * 8 : nb * 16));
+        cudaFree(t->d_stk); cudaFree(t->d_brd); cudaFree(t->d_stk32); cudaFree(t->d_brd8); cudaFree(t->d_bid);
+        t->d_stk = nullptr; t->d_brd = nullptr; t->d_stk32 = nullptr; t->d_brd8 = nullptr; t->d_bid = nullptr;
+        if (tmode == 1) t->d_brd8 = reinterpret_cast<double *>(t->d_tables + TL.off_brd);
+        else t->d_brd = reinterpret_cast<double2 *>(t->d_tables + TL.off_brd);
+        if (tmode == 0) t->d_stk = reinterpret_cast<uint64_t *>(t->d_tables + TL.off_stk);
+        else {
+            t->d_bid = reinterpret_cast<int32_t *>(t->d_tables + TL.off_bid);
+            t->d_stk32 = reinterpret_cast<uint32_t *>(t->d_tables + TL.off_stk);
+        }
+    }
+    t->query_smem_bytes = TL.bytes;
+    t->view.tables = t->d_tables;
+    t->view.tables_bytes = TL.bytes;
     t->view.rec16 = t->d_rec16;
     t->view.stk32 = t->d_stk32;
     t->view.brd8 = t->d_brd8;

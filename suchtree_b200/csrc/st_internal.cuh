@@ -78,6 +78,8 @@ struct TreeView {
     const uint32_t *stk32;     // [st_levels][n_blocks]
     const double *brd8;        // [n_blocks] root distance of each block's minimum node
     const int32_t *bid;        // [n_blocks] id of each block's minimum node
+    const unsigned char *tables;  // the block tables above as ONE blob in their shared-memory layout
+    int32_t tables_bytes;         // (st_table_layout): staged by one TMA bulk copy per query CTA
     const uint64_t *mst;       // [m_levels][n_micro] micro sparse table (packed keys)
     RangeStatus *status;
     int32_t n_nodes;
@@ -108,6 +110,7 @@ struct st_tree {
     uint32_t *d_stk32 = nullptr;
     double *d_brd8 = nullptr;
     int32_t *d_bid = nullptr;
+    unsigned char *d_tables = nullptr;  // blob the view's table pointers point into
     int compact = 0, compact_tables = 0;
     uint64_t *d_mst = nullptr;
     RangeStatus *d_status = nullptr;

@@ -48,7 +48,8 @@ __global__ void __launch_bounds__(LT)
 k_linked(const TreeView tv, const int32_t *__restrict__ col, int64_t k0, int64_t m,
          double *__restrict__ out, int64_t *__restrict__ ids_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const SmemTables sm = st_load_tables(tv, smem_raw);
+    __shared__ __align__(8) uint64_t tables_bar;
+    const SmemTables sm = st_load_tables(tv, smem_raw, &tables_bar);
     // every warp owns a contiguous run of the enumeration: un-rank once per thread, then
     // step by 32 (lanes stay adjacent: coalesced link loads and result stores)
     const int64_t n_warps = int64_t(gridDim.x) * (LT / 32);
@@ -262,7 +263,8 @@ k_sample_xs(const TreeView tv, const int2 *__restrict__ links, uint64_t n_links,
             uint64_t seed, const uint64_t *__restrict__ jump, int64_t total, int32_t n_per_bucket,
             double *__restrict__ out, double *__restrict__ sums, double *__restrict__ sumsq) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const SmemTables sm = st_load_tables(tv, smem_raw);
+    __shared__ __align__(8) uint64_t tables_bar;
+    const SmemTables sm = st_load_tables(tv, smem_raw, &tables_bar);
     const int64_t runs = (total + XS_RUN - 1) / XS_RUN;
     for (int64_t r = int64_t(blockIdx.x) * LT + threadIdx.x; r < runs; r += int64_t(gridDim.x) * LT) {
         const int64_t q0 = r * XS_RUN;
@@ -381,9 +383,10 @@ k_sample_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ 
                  double *__restrict__ partials /* [grid][5] */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // two table sets back to back (second one 16-byte aligned)
-    const SmemTables sa = st_load_tables(ta, smem_raw);
+    __shared__ __align__(8) uint64_t tables_bar[2];
+    const SmemTables sa = st_load_tables(ta, smem_raw, &tables_bar[0]);
     const int offs = (st_table_bytes(ta.n_blocks, ta.st_levels, st_table_mode(ta)) + 15) & ~15;
-    const SmemTables sb = st_load_tables(tb, smem_raw + offs);
+    const SmemTables sb = st_load_tables(tb, smem_raw + offs, &tables_bar[1]);
     __shared__ double red[5][MLT / 32];
 
     Mom5 m{0, 0, 0, 0, 0};
@@ -486,9 +489,10 @@ __global__ void __launch_bounds__(MLT)
 k_linked_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ links, int64_t first,
                  int64_t n, double x0, double y0, double *__restrict__ partials /* [grid][5] */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const SmemTables sa = st_load_tables(ta, smem_raw);
+    __shared__ __align__(8) uint64_t tables_bar[2];
+    const SmemTables sa = st_load_tables(ta, smem_raw, &tables_bar[0]);
     const int offs = (st_table_bytes(ta.n_blocks, ta.st_levels, st_table_mode(ta)) + 15) & ~15;
-    const SmemTables sb = st_load_tables(tb, smem_raw + offs);
+    const SmemTables sb = st_load_tables(tb, smem_raw + offs, &tables_bar[1]);
     __shared__ double red[5][MLT / 32];
 
     Mom5 m{0, 0, 0, 0, 0};

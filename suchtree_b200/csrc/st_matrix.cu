@@ -334,6 +334,9 @@ k_matrix_ordered(const TreeView tv, const int32_t *__restrict__ ids, const MatTa
                  int64_t row_begin, int64_t row_end, double *__restrict__ out) {
     __shared__ double s_ch[TR], s_cl[TR], s_ph[TR], s_pl[TR];
     __shared__ uint32_t s_dep[TR];
+    __shared__ __align__(32) SideRec s_colside[TC];  // 16 KB
+    __shared__ __align__(16) double2 s_colrd[TC];    //  8 KB
+    __shared__ __align__(8) uint64_t s_bar;
 
     const int64_t r0 = row_begin + int64_t(blockIdx.y) * TR;
     const int64_t c0 = int64_t(blockIdx.x) * TC;
@@ -361,22 +364,51 @@ k_matrix_ordered(const TreeView tv, const int32_t *__restrict__ ids, const MatTa
         s_ph[t] = p.x;       s_pl[t] = p.y;
         nonzero_lo |= (s.comb_lo != 0.0) | (p.y != 0.0);
     }
+    // the tile's column block (side records + root distances: two contiguous runs of the
+    // set-up tables) is staged into shared memory by TMA bulk copies, completion on an mbarrier
+    {
+        const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&s_bar);
+        if (t == 0) {
+            const uint32_t bytes_side = uint32_t(cols) * 32u, bytes_rd = uint32_t(cols) * 16u;
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(1));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes_side + bytes_rd)
+                         : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(s_colside)),
+                         "l"((rows_low ? mt.pcol : mt.scol) + c0), "r"(bytes_side), "r"(bar_a)
+                         : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(s_colrd)),
+                         "l"(mt.rd + c0), "r"(bytes_rd), "r"(bar_a)
+                         : "memory");
+        }
+        __syncthreads();
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                : "=r"(done)
+                : "r"(bar_a), "r"(0)
+                : "memory");
+        }
+    }
     // this thread's two columns
     const int64_t cA = c0 + 2 * t, cB = cA + 1;
     const bool hasA = cA < c1, hasB = cB < c1;
     SideRec a{}, b{};
     dd pa{0.0, 0.0}, pb{0.0, 0.0};
     if (hasA) {
-        const double2 p = __ldg(mt.rd + cA);
+        const double2 p = s_colrd[2 * t];
         pa = dd{p.x, p.y};
-        a = ld_side((rows_low ? mt.pcol : mt.scol) + cA);
+        a = s_colside[2 * t];
         if (!rows_low) mat_apply_mid(a, pa, mid.depth, midrd);
         nonzero_lo |= (a.comb_lo != 0.0) | (pa.lo != 0.0);
     }
     if (hasB) {
-        const double2 p = __ldg(mt.rd + cB);
+        const double2 p = s_colrd[2 * t + 1];
         pb = dd{p.x, p.y};
-        b = ld_side((rows_low ? mt.pcol : mt.scol) + cB);
+        b = s_colside[2 * t + 1];
         if (!rows_low) mat_apply_mid(b, pb, mid.depth, midrd);
         nonzero_lo |= (b.comb_lo != 0.0) | (pb.lo != 0.0);
     }

@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(QQT)
 k_quartets(const TreeView tv, const int64_t *__restrict__ quartets, int64_t n,
            int64_t *__restrict__ out, int aligned) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const SmemTables sm = st_load_tables<M>(tv, smem_raw);
+    __shared__ __align__(8) uint64_t tables_bar;
+    const SmemTables sm = st_load_tables<M>(tv, smem_raw, &tables_bar);
     const long long nn = tv.n_nodes;
     for (int64_t i = int64_t(blockIdx.x) * QQT + threadIdx.x; i < n; i += int64_t(gridDim.x) * QQT) {
         const Quad q = quad_load(quartets + 4 * i, aligned != 0);

@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(QT, MINB)
 k_pairs(const TreeView tv, const IdxT *__restrict__ pairs, int64_t n, double *__restrict__ out,
         int32_t *__restrict__ mrca_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const SmemTables sm = st_load_tables<M>(tv, smem_raw);
+    __shared__ __align__(8) uint64_t tables_bar;
+    const SmemTables sm = st_load_tables<M>(tv, smem_raw, &tables_bar);
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
     const bool want_d = out != nullptr, want_m = mrca_out != nullptr;
 
