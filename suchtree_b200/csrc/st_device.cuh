@@ -291,11 +291,10 @@ __device__ __forceinline__ SmemTables st_tables_at(const unsigned char *base, co
 // Stage the block tables into dynamic shared memory (16-byte aligned) with ONE TMA bulk
 // copy (cp.async.bulk global -> shared, completion on an mbarrier) issued by thread 0.
 // `bar` is an 8-byte shared-memory word owned by the caller (one per table set).
-template <int M = 2>
-__device__ __forceinline__ SmemTables st_load_tables(const TreeView &tv, unsigned char *smem, uint64_t *bar) {
-    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(bar);
-    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem);
+__device__ __forceinline__ void st_tables_issue(const TreeView &tv, unsigned char *smem, uint64_t *bar) {
     if (threadIdx.x == 0) {
+        const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(bar);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem);
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(tv.tables_bytes)
@@ -304,7 +303,12 @@ __device__ __forceinline__ SmemTables st_load_tables(const TreeView &tv, unsigne
                      "l"(tv.tables), "r"(tv.tables_bytes), "r"(bar_a)
                      : "memory");
     }
-    __syncthreads();  // the barrier is initialised before anyone polls it
+}
+// call after a __syncthreads() that follows st_tables_issue (the barrier must be
+// initialised before anyone polls it)
+template <int M = 2>
+__device__ __forceinline__ SmemTables st_tables_wait(const TreeView &tv, unsigned char *smem, uint64_t *bar) {
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(bar);
     uint32_t done = 0;
     while (!done) {
         asm volatile(
@@ -315,6 +319,12 @@ __device__ __forceinline__ SmemTables st_load_tables(const TreeView &tv, unsigne
     }
     const int mode = st_compact<M>(tv) ? 1 : (st_ctab<M>(tv) ? 2 : 0);
     return st_tables_at(smem, tv, mode);
+}
+template <int M = 2>
+__device__ __forceinline__ SmemTables st_load_tables(const TreeView &tv, unsigned char *smem, uint64_t *bar) {
+    st_tables_issue(tv, smem, bar);
+    __syncthreads();
+    return st_tables_wait<M>(tv, smem, bar);
 }
 
 // ------------------------------------------------------------ Philox --------

@@ -15,15 +15,36 @@
 static const int LT = 256;
 
 // one full pair query (fast path tables in shared memory)
+template <int M = 2>
 __device__ __forceinline__ double linked_query(const TreeView &tv, const SmemTables &sm, int32_t a,
                                                int32_t b) {
     int32_t lo = min(a, b), hi = max(a, b);
     if (lo == hi) return 0.0;
-    RecRaw l = st_ld_rec(tv, lo), h = st_ld_rec(tv, hi);
+    RecRaw l = st_ld_rec<M>(tv, lo), h = st_ld_rec<M>(tv, hi);
     bool ft;
-    uint64_t key = st_rmq(tv, sm, lo, hi, l.suf, h.pre, &ft);
-    return st_patristic(dd{l.rd_hi, l.rd_lo}, dd{h.rd_hi, h.rd_lo}, st_mrca_rd(tv, sm, key, ft));
+    uint64_t key = st_rmq<M>(tv, sm, lo, hi, l.suf, h.pre, &ft);
+    return st_patristic(dd{l.rd_hi, l.rd_lo}, dd{h.rd_hi, h.rd_lo}, st_mrca_rd<M>(tv, sm, key, ft));
 }
+
+// layout mode of a tree as a template argument (0 wide, 1 compact, 3 wide records +
+// 32-bit tables): the two-tree kernels are instantiated per pair of modes, so no
+// run-time layout branches or dead table pointers cost registers
+static inline int tree_mode(const st_tree *t) { return t->compact ? 1 : (t->compact_tables ? 3 : 0); }
+#define ST_DISPATCH_MODES(ma, mb, CALL)                              \
+    do {                                                             \
+        const int _k = (ma) * 4 + (mb);                              \
+        switch (_k) {                                                \
+            case 0:  { CALL(0, 0); } break;                          \
+            case 1:  { CALL(0, 1); } break;                          \
+            case 3:  { CALL(0, 3); } break;                          \
+            case 4:  { CALL(1, 0); } break;                          \
+            case 5:  { CALL(1, 1); } break;                          \
+            case 7:  { CALL(1, 3); } break;                          \
+            case 12: { CALL(3, 0); } break;                          \
+            case 13: { CALL(3, 1); } break;                          \
+            default: { CALL(3, 3); } break;                          \
+        }                                                            \
+    } while (0)
 
 // k = i(i-1)/2 + j, 0 <= j < i   (the reference's loop order, MuchTree.pyx:2919-2925)
 __device__ __forceinline__ void tri_unrank(int64_t k, int64_t &i, int64_t &j) {
@@ -377,6 +398,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // both trees' block tables live in shared memory (up to ~2 x 96 KB): one big CTA per SM
 static const int MLT = 1024;
 
+template <int MA, int MB>
 __global__ void __launch_bounds__(MLT)
 k_sample_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ links,
                  uint32_t n_links, uint64_t seed, int64_t first, int64_t n, double x0, double y0,
@@ -384,9 +406,12 @@ k_sample_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // two table sets back to back (second one 16-byte aligned)
     __shared__ __align__(8) uint64_t tables_bar[2];
-    const SmemTables sa = st_load_tables(ta, smem_raw, &tables_bar[0]);
     const int offs = (st_table_bytes(ta.n_blocks, ta.st_levels, st_table_mode(ta)) + 15) & ~15;
-    const SmemTables sb = st_load_tables(tb, smem_raw + offs, &tables_bar[1]);
+    st_tables_issue(ta, smem_raw, &tables_bar[0]);  // both bulk copies in flight together
+    st_tables_issue(tb, smem_raw + offs, &tables_bar[1]);
+    __syncthreads();
+    const SmemTables sa = st_tables_wait<MA>(ta, smem_raw, &tables_bar[0]);
+    const SmemTables sb = st_tables_wait<MB>(tb, smem_raw + offs, &tables_bar[1]);
     __shared__ double red[5][MLT / 32];
 
     Mom5 m{0, 0, 0, 0, 0};
@@ -402,8 +427,8 @@ k_sample_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ 
             if (s < first || s >= first + n) continue;
             int2 l1 = __ldg(links + st_bounded(w[2 * h], n_links));
             int2 l2 = __ldg(links + st_bounded(w[2 * h + 1], n_links));
-            double x = linked_query(ta, sa, l1.y, l2.y) - x0;
-            double y = linked_query(tb, sb, l1.x, l2.x) - y0;
+            double x = linked_query<MA>(ta, sa, l1.y, l2.y) - x0;
+            double y = linked_query<MB>(tb, sb, l1.x, l2.x) - y0;
             m.sx += x; m.sy += y;
             m.sxx += x * x; m.syy += y * y; m.sxy += x * y;
         }
@@ -452,19 +477,19 @@ extern "C" int st_sample_moments(const st_tree *ta, const st_tree *tb, const int
     rc = upload_links(ta, tb, linklist, L, dl, false, true);
     if (rc != ST_OK) return rc;
     const int smem = ((ta->query_smem_bytes + 15) & ~15) + tb->query_smem_bytes;
-    rc = set_smem(k_sample_moments, smem);
-    if (rc != ST_OK) return rc;
-    int per_sm = 0;
-    ST_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sample_moments, MLT, smem));
-    if (per_sm < 1) per_sm = 1;
+    // 1024-thread CTAs with both trees' tables: one CTA per SM
     const int64_t calls = (n_samples + 1) / 2 + 1;
-    int grid = int(std::min<int64_t>((calls + MLT - 1) / MLT, int64_t(ta->sm_count) * per_sm));
+    int grid = int(std::min<int64_t>((calls + MLT - 1) / MLT, int64_t(ta->sm_count)));
     cudaStream_t s = ta->streams[0];
     double *d_part = nullptr;  // [grid][5] partials, then 5 folded sums
     ST_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d_part), size_t(grid + 1) * 5 * 8, s));
     double *d_out = d_part + size_t(grid) * 5;
-    k_sample_moments<<<grid, MLT, smem, s>>>(ta->view, tb->view, dl.rows, uint32_t(L), seed, first_sample,
-                                           n_samples, x0, y0, d_part);
+#define ST_LAUNCH_SAMPLE(MA, MB)                                                                         \
+    if (set_smem(k_sample_moments<MA, MB>, smem) == ST_OK)                                               \
+        k_sample_moments<MA, MB><<<grid, MLT, smem, s>>>(ta->view, tb->view, dl.rows, uint32_t(L), seed, \
+                                                         first_sample, n_samples, x0, y0, d_part)
+    ST_DISPATCH_MODES(tree_mode(ta), tree_mode(tb), ST_LAUNCH_SAMPLE);
+#undef ST_LAUNCH_SAMPLE
     k_reduce_partials<<<1, 160, 0, s>>>(grid, d_part, d_out);
     double h[5];
     cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, s);
@@ -485,14 +510,18 @@ extern "C" int st_sample_moments(const st_tree *ta, const st_tree *tb, const int
 // enumeration (MuchTree.pyx:2919-2925), reduced in registers / shuffles / one partial
 // per CTA.  This is the inner loop of the reference's per-clade correlation scan
 // (docs/examples/SuchLinkedTree_examples.md:299-310).  Shardable by k-range.
+template <int MA, int MB>
 __global__ void __launch_bounds__(MLT)
 k_linked_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ links, int64_t first,
                  int64_t n, double x0, double y0, double *__restrict__ partials /* [grid][5] */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t tables_bar[2];
-    const SmemTables sa = st_load_tables(ta, smem_raw, &tables_bar[0]);
     const int offs = (st_table_bytes(ta.n_blocks, ta.st_levels, st_table_mode(ta)) + 15) & ~15;
-    const SmemTables sb = st_load_tables(tb, smem_raw + offs, &tables_bar[1]);
+    st_tables_issue(ta, smem_raw, &tables_bar[0]);  // both bulk copies in flight together
+    st_tables_issue(tb, smem_raw + offs, &tables_bar[1]);
+    __syncthreads();
+    const SmemTables sa = st_tables_wait<MA>(ta, smem_raw, &tables_bar[0]);
+    const SmemTables sb = st_tables_wait<MB>(tb, smem_raw + offs, &tables_bar[1]);
     __shared__ double red[5][MLT / 32];
 
     Mom5 m{0, 0, 0, 0, 0};
@@ -507,8 +536,8 @@ k_linked_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ 
     if (q < wend) tri_unrank(first + q, i, j);
     for (; q < wend; q += 32, tri_advance(i, j, 32)) {
         const int2 l1 = __ldg(links + j), l2 = __ldg(links + i);
-        const double x = linked_query(ta, sa, l1.y, l2.y) - x0;
-        const double y = linked_query(tb, sb, l1.x, l2.x) - y0;
+        const double x = linked_query<MA>(ta, sa, l1.y, l2.y) - x0;
+        const double y = linked_query<MB>(tb, sb, l1.x, l2.x) - y0;
         m.sx += x; m.sy += y;
         m.sxx += x * x; m.syy += y * y; m.sxy += x * y;
     }
@@ -548,17 +577,17 @@ extern "C" int st_linked_moments(const st_tree *ta, const st_tree *tb, const int
     rc = upload_links(ta, tb, linklist, L, dl, false, true);
     if (rc != ST_OK) return rc;
     const int smem = ((ta->query_smem_bytes + 15) & ~15) + tb->query_smem_bytes;
-    rc = set_smem(k_linked_moments, smem);
-    if (rc != ST_OK) return rc;
-    int per_sm = 0;
-    ST_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linked_moments, MLT, smem));
-    if (per_sm < 1) per_sm = 1;
-    int grid = int(std::min<int64_t>((n_pairs + MLT - 1) / MLT, int64_t(ta->sm_count) * per_sm));
+    int grid = int(std::min<int64_t>((n_pairs + MLT - 1) / MLT, int64_t(ta->sm_count)));
     cudaStream_t s = ta->streams[0];
     double *d_part = nullptr;
     ST_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d_part), size_t(grid + 1) * 5 * 8, s));
     double *d_out = d_part + size_t(grid) * 5;
-    k_linked_moments<<<grid, MLT, smem, s>>>(ta->view, tb->view, dl.rows, first_pair, n_pairs, x0, y0, d_part);
+#define ST_LAUNCH_LINKED(MA, MB)                                                                  \
+    if (set_smem(k_linked_moments<MA, MB>, smem) == ST_OK)                                        \
+        k_linked_moments<MA, MB><<<grid, MLT, smem, s>>>(ta->view, tb->view, dl.rows, first_pair, \
+                                                         n_pairs, x0, y0, d_part)
+    ST_DISPATCH_MODES(tree_mode(ta), tree_mode(tb), ST_LAUNCH_LINKED);
+#undef ST_LAUNCH_LINKED
     k_reduce_partials<<<1, 160, 0, s>>>(grid, d_part, d_out);
     double h[5];
     cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, s);
