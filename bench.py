@@ -609,6 +609,37 @@ def run_other_workloads(args, rank, world, local, dev, peak):
     }
     del TA, TB
 
+    # ---- the drop-in sampler API on the shape of the reference's published example
+    #      (docs/examples/SuchLinkedTree_examples.md:76-149: 14 x 103,446 leaves, 44,904
+    #      links; construction 4 min 57 s, sample_linked_distances 3.5e4 samples/s there)
+    if rank == 0:
+        import pandas as pd
+
+        from suchtree_b200 import SuchLinkedTrees
+
+        fa2 = synth.yule_tree(14, seed=8, names=True)
+        fb2 = synth.yule_tree(103_446, seed=9, names=True)
+        A2, B2 = SuchTree.from_flat(fa2, device=local), SuchTree.from_flat(fb2, device=local)
+        rng2 = np.random.default_rng(10)
+        mat = np.zeros((14, 103_446), dtype=np.int8)
+        cols = rng2.choice(103_446, size=44_904, replace=False)
+        mat[rng2.integers(0, 14, size=44_904), cols] = 1
+        links = pd.DataFrame(mat, index=list(A2.leaves.keys()), columns=list(B2.leaves.keys()))
+        t0 = time.perf_counter()
+        SLT = SuchLinkedTrees(A2, B2, links)
+        build_s = time.perf_counter() - t0
+        SLT.sample_linked_distances(sigma=0.0, buckets=64, n=4096, maxcycles=1)  # warm
+        t0 = time.perf_counter()
+        cycles = 10
+        SLT.sample_linked_distances(sigma=0.0, buckets=64, n=4096, maxcycles=cycles)  # never converges: 10 cycles
+        dt = time.perf_counter() - t0
+        res["sample_linked_distances_api"] = {
+            "workload": "SuchLinkedTrees(14-leaf, 103,446-leaf trees, 44,904 links).sample_linked_distances("
+                        "buckets=64, n=4096), %d cycles, the reference's exact xorshift64* stream" % cycles,
+            "samples_per_s": cycles * 64 * 4096 / dt, "construction_s": build_s, "n_links": int(SLT.n_links),
+        }
+        del SLT, A2, B2
+
     # ---- N1: quartet topologies, 5e7 random leaf quartets per GPU, device resident
     T = SuchTree.from_flat(synth.yule_tree(TREE_LEAVES, seed=TREE_SEED), device=local)
     nq = args.quartets
