@@ -62,7 +62,7 @@ static_assert(sizeof(NodeRec16) == 16, "NodeRec16 must be 16 bytes");
 // range status written by query kernels (pinned-host mapped would also do; it
 // lives in device memory and is read back by st_check_range / host entry points)
 struct RangeStatus {
-    unsigned long long max_bad;  // max id >= n_nodes seen (0 = none; ids are stored +1... see kernels)
+    unsigned long long max_bad;  // max id >= n_nodes seen (0 = none: 0 is always a valid id)
     long long min_bad;           // min id < 0 seen (0 = none)
 };
 
@@ -114,7 +114,6 @@ struct st_tree {
     int compact = 0, compact_tables = 0;
     uint64_t *d_mst = nullptr;
     RangeStatus *d_status = nullptr;
-    int32_t *d_leaf_ids = nullptr;  // lazily unused; leaves are the even ids
     TreeView view{};
     int query_smem_bytes = 0;
 

@@ -338,20 +338,20 @@ extern "C" int st_sample_linked_cycle(const st_tree *ta, const st_tree *tb, cons
     const XsJump &J = xs_table();
     uint64_t *d_jump = nullptr;
     double *d_out = nullptr, *d_stats = nullptr;
-    auto cleanup = [&]() {
-        cudaFree(d_jump);
-        cudaFree(d_out);
-        cudaFree(d_stats);
-    };
-    if (cudaMalloc(&d_jump, sizeof(J.col)) != cudaSuccess ||
-        cudaMalloc(&d_out, size_t(total) * 8 * 2) != cudaSuccess ||
-        cudaMalloc(&d_stats, size_t(buckets) * 8 * 4) != cudaSuccess) {
-        cleanup();
-        st_set_error("st_sample_linked_cycle: cudaMalloc failed");
-        return ST_ERR_NOMEM;
-    }
     std::lock_guard<std::mutex> lock(ta->host_mu);
     cudaStream_t s = ta->streams[0];
+    auto cleanup = [&]() {  // stream-ordered scratch: recycled by the pool, no driver malloc per cycle
+        if (d_jump) cudaFreeAsync(d_jump, s);
+        if (d_out) cudaFreeAsync(d_out, s);
+        if (d_stats) cudaFreeAsync(d_stats, s);
+    };
+    if (cudaMallocAsync(reinterpret_cast<void **>(&d_jump), sizeof(J.col), s) != cudaSuccess ||
+        cudaMallocAsync(reinterpret_cast<void **>(&d_out), size_t(total) * 8 * 2, s) != cudaSuccess ||
+        cudaMallocAsync(reinterpret_cast<void **>(&d_stats), size_t(buckets) * 8 * 4, s) != cudaSuccess) {
+        cleanup();
+        st_set_error("st_sample_linked_cycle: device allocation failed");
+        return ST_ERR_NOMEM;
+    }
     cudaMemcpyAsync(d_jump, J.col, sizeof(J.col), cudaMemcpyHostToDevice, s);
     cudaMemsetAsync(d_stats, 0, size_t(buckets) * 8 * 4, s);
     const int64_t runs = (total + XS_RUN - 1) / XS_RUN;
@@ -366,9 +366,9 @@ extern "C" int st_sample_linked_cycle(const st_tree *ta, const st_tree *tb, cons
     cudaMemcpyAsync(out_a, d_out, size_t(total) * 8, cudaMemcpyDeviceToHost, s);
     cudaMemcpyAsync(out_b, d_out + total, size_t(total) * 8, cudaMemcpyDeviceToHost, s);
     cudaMemcpyAsync(stats.data(), d_stats, stats.size() * 8, cudaMemcpyDeviceToHost, s);
+    cleanup();
     cudaError_t e = cudaStreamSynchronize(s);
     if (e == cudaSuccess) e = cudaGetLastError();
-    cleanup();
     if (e != cudaSuccess) {
         st_set_error("st_sample_linked_cycle: %s", cudaGetErrorString(e));
         return ST_ERR_CUDA;
