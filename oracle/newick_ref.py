@@ -40,7 +40,10 @@ _TOKEN = re.compile(
       | \[[^\]]*\]               # comment
       | '(?:[^']|'')*'           # quoted label
       | [(),:;]                  # punctuation
-      | [^\s()\[\]',:;]+         # bare label / number
+      | [^\s()\[\]',:;][^\s()\[\],:;]*   # bare label / number; a quote INSIDE a bare label is an
+                                 # ordinary character (data/plant-pollinators/rabr/plant.tree has
+                                 # the leaf Cuphea_o'donellii, and rabr_links.csv, made with real
+                                 # dendropy, calls it exactly that)
     """,
     re.X,
 )

@@ -7,7 +7,8 @@
 // loaded at all (recursive iterators).  This parser is iterative, O(n), and keeps
 // the rules that DEFINE node ids bit-exact:
 //   * tokens: [comments] dropped, 'quoted labels' ('' = quote), ( ) , : ; and bare
-//     labels (anything without whitespace or ()[]',:;); underscores preserved (:141)
+//     labels (anything without whitespace or ()[],:; that does not START with a quote);
+//     underscores preserved (:141)
 //   * polytomies: dendropy's deterministic resolve_polytomies() (:157) -- nodes with
 //     more than two children collected in post-order, then the first two children
 //     are repeatedly re-attached under a new zero-length node appended LAST
@@ -181,8 +182,11 @@ extern "C" int st_newick_parse(const char *text, int64_t len, st_newick **out) {
             }
             continue;
         } else {
+            // bare label: a quote after the first character is an ordinary character
             int64_t j = i;
-            while (j < len && !is_space((unsigned char)text[j]) && !is_punct((unsigned char)text[j])) ++j;
+            while (j < len && !is_space((unsigned char)text[j]) &&
+                   (!is_punct((unsigned char)text[j]) || (text[j] == '\'' && j > i)))
+                ++j;
             tok.assign(text + i, size_t(j - i));
             i = j;
         }

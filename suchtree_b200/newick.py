@@ -6,7 +6,8 @@ rules that DEFINE node ids are reproduced exactly, because every id a user holds
 must stay bit-identical:
 
   * leaf labels are taxa, internal labels are support values; `[...]` comments
-    are dropped; 'quoted labels' keep their text ('' = escaped quote);
+    are dropped; 'quoted labels' keep their text ('' = escaped quote); a quote
+    inside a bare label is an ordinary character;
     underscores are preserved (preserve_underscores=True, :141);
   * polytomies are resolved as dendropy's deterministic resolve_polytomies()
     does (:157): nodes with >2 children are collected in post-order, then the
@@ -31,7 +32,9 @@ from .exceptions import TreeStructureError
 
 EPSILON = float(np.finfo(np.float64).eps)
 
-_TOKENS = re.compile(r"\[[^\]]*\]|'(?:[^']|'')*'|[(),:;]|[^\s()\[\]',:;]+")
+# a quote opens a quoted label only at the START of a token; inside a bare label it is an
+# ordinary character (Cuphea_o'donellii in the reference's data/plant-pollinators/rabr)
+_TOKENS = re.compile(r"\[[^\]]*\]|'(?:[^']|'')*'|[(),:;]|[^\s()\[\]',:;][^\s()\[\],:;]*")
 
 
 class FlatTree:

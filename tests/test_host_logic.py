@@ -89,6 +89,7 @@ def test_native_loader_equals_python_restatement(golden_trees):
         " ( 'x y' : 1.5 , ( z:2 , w : 3 ) 0.75 : 4 ) ; trailing (junk", "[c](A[x]:1[y],B:2)[z];",
         "(A:1,B:2);(C,D);", "((a,b,c,d,e,f,g,h,i,j)1e2:1,(k,l,m)x1:2,n);", "(\u00e9t\u00e9:1,'\u65e5\u672c':2);",
         "(A:.5,B:5.,(C:+1.e+1,D:-.5E-1):1);",
+        "(A:1,(Cuphea_o'donellii:1,B''s:2):1,'it''s':3);",
     ]
     for t in texts:
         assert _same_flat(newick.flatten(t), newick.flatten_py(t)), t[:60]
@@ -98,6 +99,18 @@ def test_native_loader_equals_python_restatement(golden_trees):
         nw = synth.to_newick(ft0)
         a = newick.flatten(nw)
         assert _same_flat(a, newick.flatten_py(nw)) and np.array_equal(a.parent, ft0.parent)
+
+
+def test_quote_inside_a_bare_label_is_an_ordinary_character():
+    """data/plant-pollinators/rabr/plant.tree of the reference has the leaf
+    Cuphea_o'donellii, and its link table (made with real dendropy) uses that name: a
+    quote opens a quoted label only at the start of a token."""
+    import tree_build
+
+    nw = "((Ludwigia_nervosa:1,Cuphea_o'donellii:1)1:1,('quoted name':2,x'y'z:1):1);"
+    for ft in (newick.flatten(nw), newick.flatten_py(nw)):
+        assert list(ft.leaves) == ["Ludwigia_nervosa", "Cuphea_o'donellii", "quoted name", "x'y'z"]
+    assert tree_build.build_arrays(nw)["leaves"] == newick.flatten(nw).leaves
 
 
 def test_native_loader_error_messages():
