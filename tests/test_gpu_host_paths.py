@@ -117,3 +117,35 @@ def test_range_errors_on_every_route(tree, n):
         # and the tree still answers
         q = _pairs(ft, 10, 6)
         assert np.all(np.isfinite(T.distances_bulk(q)))
+
+
+def test_concurrent_host_calls_from_threads(tree):
+    """Handles are immutable after creation: host threads may query one tree (and
+    several trees) concurrently; the GIL is released inside the C-ABI calls."""
+    import threading
+
+    T, ot, ft = tree
+    ft2 = synth.balanced_tree(4096, seed=3)
+    T2, ot2 = SuchTree.from_flat(ft2), O.OracleTree(ft2.parent, ft2.distance)
+    jobs = []
+    for k in range(8):
+        tr, orc, f = (T, ot, ft) if k % 2 == 0 else (T2, ot2, ft2)
+        n = [3, 5000, 300000, 70000][k % 4]
+        p = np.random.default_rng(100 + k).integers(0, f.size, size=(n, 2)).astype(np.int64)
+        jobs.append((tr, orc, p))
+    results = [None] * len(jobs)
+
+    def run(i):
+        tr, _, p = jobs[i]
+        for _ in range(3):
+            results[i] = (tr.distances_bulk(p), tr.common_ancestors_bulk(p))
+
+    threads = [threading.Thread(target=run, args=(i,)) for i in range(len(jobs))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=120)
+        assert not th.is_alive()
+    for (tr, orc, p), (d, m) in zip(jobs, results):
+        want_d, want_m = orc.distances_f64_climb(p, with_mrca=True)
+        assert np.array_equal(d, want_d) and np.array_equal(m, want_m)
