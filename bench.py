@@ -183,7 +183,7 @@ def run_reference_arm(args):
 # clocks
 # --------------------------------------------------------------------------- #
 class ClockSampler(threading.Thread):
-    def __init__(self, device_index, period=0.1):
+    def __init__(self, device_index, period=0.004):  # the timed region is tens of milliseconds
         super().__init__(daemon=True)
         self.idx, self.period = device_index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -226,7 +226,8 @@ class ClockSampler(threading.Thread):
         if self.ok:
             self.join(timeout=2)
         med = float(np.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
 
 
 def physical_gpu_index(local):
