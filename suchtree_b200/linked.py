@@ -159,6 +159,40 @@ class SuchLinkedTrees:
     subset_b_root = property(lambda self: self._subset_b_root)
     subset_n_links = property(lambda self: self._subset_n_links)
 
+    # ---- per-column access and the dense matrix (:2774-2837) ------------------
+    def _col_index(self, col):
+        col_id = self._col_names.index(col) if isinstance(col, str) else col
+        if col_id > self._n_cols:
+            raise Exception("col_id out of bounds", col_id)
+        return col_id
+
+    def get_column_leafs(self, col, as_row_ids=False):
+        """TreeA leaf ids (or row indices) linked to one column (a TreeB leaf), in the
+        link matrix's row order; :2774-2792."""
+        col_id = self._col_index(col)
+        links = self._link_a[self._link_cols == col_id]
+        return self._row_map[links] if as_row_ids else links.copy()
+
+    def get_column_links(self, col):
+        """Boolean row mask of one column; :2794-2809."""
+        column = np.zeros(self._n_rows, dtype=bool)
+        column[self._row_map[self._link_a[self._link_cols == self._col_index(col)]]] = True
+        return column
+
+    @property
+    def linkmatrix(self):
+        """Dense boolean (subset_a_size, subset_b_size) link matrix, built on access
+        (:2811-2837; indexed by row id / column id exactly like the reference, including
+        its behaviour under subsetting, which upstream marks FIXME)."""
+        table = np.zeros((self._subset_a_size, self._subset_b_size), dtype=bool)
+        in_a = np.zeros(self._TreeA.size, dtype=bool)
+        in_a[np.asarray(self._subset_a_leafs, dtype=np.int64)] = True
+        in_cols = np.zeros(self._n_cols, dtype=bool)
+        in_cols[np.asarray(self._subset_columns, dtype=np.int64)] = True
+        keep = in_cols[self._link_cols] & in_a[self._link_a]
+        table[self._row_map[self._link_a[keep]], self._link_cols[keep]] = True
+        return table
+
     @property
     def linklist(self):
         return self._np_linklist[: self._subset_n_links, :]

@@ -226,6 +226,39 @@ def test_sample_linked_distances_reproduces_reference_stream(name):
     assert SLT._seed == seed  # the state advanced exactly as the reference's would
 
 
+def test_link_bookkeeping_accessors():
+    """Per-column access, the dense matrix and the link list against the DataFrame they
+    were built from (what SuchTree/tests/test_SuchLinkedTrees.py:129-246 checks), with
+    shuffled rows so that matrix order and tree order differ."""
+    T = SuchTree(os.path.join(DATA, "test.tree"))
+    N = T.num_leaves
+    rng = np.random.default_rng(17)
+    row_names = list(T.leaves.keys())
+    rng.shuffle(row_names)
+    links = pd.DataFrame(rng.integers(0, 3, size=(N, N)), columns=list(T.leaves.keys()), index=row_names)
+    SLT = SuchLinkedTrees(T, T, links)
+    assert SLT.n_rows == SLT.n_cols == N and SLT.n_links == int((links.to_numpy() > 0).sum())
+    assert list(SLT.col_ids) == list(T.leaves.values()) and SLT.row_names == list(T.leaves.keys())
+    mask = links > 0
+    for n, colname in enumerate(links.columns):
+        s = mask[colname]
+        want = {T.leaves[x] for x in s[s].index}
+        assert set(SLT.get_column_leafs(n)) == want == set(SLT.get_column_leafs(colname))
+        rows = {list(SLT.row_ids).index(v) for v in want}
+        assert set(SLT.get_column_leafs(n, as_row_ids=True)) == rows
+        c = SLT.get_column_links(n)
+        assert [bool(s[r]) for r in SLT.row_names] == c.tolist()
+    lm = SLT.linkmatrix
+    for ci, col in enumerate(SLT.col_names):
+        for ri, row in enumerate(SLT.row_names):
+            assert bool(links.at[row, col]) == lm[ri][ci]
+    un = links.unstack()
+    want = {(T.leaves[c], T.leaves[r]) for c, r in un[un > 0].index}
+    assert {(int(b), int(a)) for b, a in SLT.linklist} == want
+    with pytest.raises(Exception):
+        SLT.get_column_leafs(N + 1)
+
+
 def test_sampler_returns_none_at_maxcycles():
     SLT, _, _ = _slt("gopher_louse")
     assert SLT.sample_linked_distances(sigma=1e-9, buckets=4, n=16, maxcycles=2) is None
