@@ -479,7 +479,9 @@ def run_other_workloads(args, rank, world, local, dev, peak):
     import torch
     import torch.distributed as dist
 
-    from suchtree_b200 import SuchTree, shard, synth
+    import ctypes as C
+
+    from suchtree_b200 import SuchTree, _lib, shard, synth
     from suchtree_b200.linked import moments_pearson
 
     stream = torch.cuda.current_stream(dev)
@@ -509,11 +511,17 @@ def run_other_workloads(args, rank, world, local, dev, peak):
         # size-independent properties at full size: symmetric pairs give d(a,a)=0 and the
         # result is finite and bounded by twice the largest root distance
         finite = bool(torch.isfinite(out).all().item())
+        # gather roofline for an index of this size (random sectors over the same footprint)
+        sps = C.c_double(0)
+        gfrac = None
+        if _lib.lib().st_bench_gather(local, int(T.index_info["index_bytes"]), 64, 3, C.byref(sps)) == 0 and sps.value > 0:
+            gfrac = 2.0 * n3 / sec / sps.value
         res["cfg3_" + shape] = {
             "workload": "1M-leaf %s tree (depth %d), %d random leaf pairs per GPU per launch" % (shape, T.depth, n3),
             "pairs_per_s": world * n3 / sec, "ms_per_launch": sec * 1e3, "index_build_s": build_s,
             "index_bytes": int(T.index_info["index_bytes"]),
-            "hbm_frac": 16.0 * n3 / sec / 1e9 / peak, "all_finite": finite,
+            "hbm_frac": 16.0 * n3 / sec / 1e9 / peak, "gather_frac": gfrac,
+            "gather_peak_sectors_per_s": sps.value, "all_finite": finite,
         }
         del T
     del pairs, out
