@@ -6,6 +6,7 @@
 // fixed reduction tree instead of the reference's sequential fp32 accumulators.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 
 #include "st_device.cuh"
@@ -385,6 +386,81 @@ k_gather_ws(const __grid_constant__ CUtensorMap tmap, const ulonglong4 *__restri
     if (acc == 0x123456789abcdefull) *sink = acc;
 }
 
+// Experiment: are the LSU and the TMA gather paths additive?  Every CTA has 16 LSU warps
+// (the plain gather loop, `rounds` rounds of 4 sectors) PLUS `TW` TMA warps that fetch
+// sectors with gather4 for `rounds_tma` rounds (per-warp mbarriers, two stages, dynamic
+// shared memory).  The host reports (LSU sectors + TMA sectors) / kernel time; TW = 0 with
+// the same CTA shape is the baseline.  SUCHTREE_B200_GATHER_MODE=add<TW>_<percent>.
+__global__ void __launch_bounds__(1024)
+k_gather_add(const __grid_constant__ CUtensorMap tmap, const ulonglong4 *__restrict__ buf,
+             uint64_t n_sectors, int64_t rounds, int64_t rounds_tma, int tma_warps, uint64_t seed,
+             unsigned long long *__restrict__ sink) {
+    extern __shared__ __align__(128) unsigned char dyn[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    uint64_t acc = 0;
+    if (warp >= 16) {
+        const int w = warp - 16;
+        ulonglong4 *slots = reinterpret_cast<ulonglong4 *>(dyn) + size_t(w) * 2 * 128;  // [2][128]
+        uint64_t *bar = reinterpret_cast<uint64_t *>(dyn + size_t(tma_warps) * 8192) + 2 * w;
+        if (lane == 0) {
+            for (int s = 0; s < 2; ++s)
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&bar[s])), "r"(1));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        auto issue = [&](int64_t r) {
+            const int s = int(r & 1);
+            const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar[s]);
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(32 * 4 * 32) : "memory");
+            __syncwarp();
+            Philox4 p = st_philox4x32_10(tid * uint64_t(rounds) + uint64_t(r), seed);
+            int32_t r0 = int32_t((uint64_t(p.x) * n_sectors) >> 32), r1 = int32_t((uint64_t(p.y) * n_sectors) >> 32);
+            int32_t r2 = int32_t((uint64_t(p.z) * n_sectors) >> 32), r3 = int32_t((uint64_t(p.w) * n_sectors) >> 32);
+            uint32_t dst = (uint32_t)__cvta_generic_to_shared(&slots[s * 128 + lane * 4]);
+            asm volatile(
+                "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                ::"r"(dst), "l"(&tmap), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar_a)
+                : "memory");
+        };
+        if (rounds_tma > 0) issue(0);
+        for (int64_t r = 0; r < rounds_tma; ++r) {
+            if (r + 1 < rounds_tma) issue(r + 1);
+            const int s = int(r & 1);
+            const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar[s]);
+            const uint32_t phase = uint32_t(r >> 1) & 1;
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile(
+                    "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                    : "=r"(done) : "r"(bar_a), "r"(phase) : "memory");
+            }
+            // one 32-byte read per lane and round: consumers of a real kernel would read their
+            // records from shared memory like this
+            ulonglong4 v = slots[s * 128 + lane * 4];
+            acc ^= v.x ^ v.y ^ v.z ^ v.w;
+            __syncwarp();
+        }
+    } else {
+        for (int64_t r = 0; r < rounds; ++r) {
+            Philox4 p = st_philox4x32_10(tid * uint64_t(rounds) + uint64_t(r), seed);
+            const uint32_t w[4] = {p.x, p.y, p.z, p.w};
+            uint64_t a[4], b[4], c[4], d[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint64_t idx = (uint64_t(w[k]) * n_sectors) >> 32;
+                asm volatile("ld.global.nc.L2::evict_last.v4.b64 {%0,%1,%2,%3}, [%4];"
+                             : "=l"(a[k]), "=l"(b[k]), "=l"(c[k]), "=l"(d[k])
+                             : "l"(buf + idx));
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc ^= a[k] ^ b[k] ^ c[k] ^ d[k];
+        }
+    }
+    if (acc == 0x123456789abcdefull) *sink = acc;
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -441,7 +517,9 @@ extern "C" int st_bench_gather(int device, int64_t bytes, int64_t loads_per_thre
     const char *mode = getenv("SUCHTREE_B200_GATHER_MODE");
     const bool bulk = mode && mode[0] == 'b';
     const bool use_tex = mode && mode[0] == 't', mix = mode && mode[0] == 'm';
-    const bool g4 = mode && (mode[0] == 'g' || mode[0] == 'w');
+    const bool g4 = mode && (mode[0] == 'g' || mode[0] == 'w' || mode[0] == 'a');
+    int add_tw = -1, add_pct = 0;
+    if (mode && mode[0] == 'a') sscanf(mode, "add%d_%d", &add_tw, &add_pct);
     const int ws = (mode && mode[0] == 'w') ? atoi(mode + 2) : -1;
     const int g4mix = (g4 && mode[2] == 'm') ? (mode[5] ? mode[5] - '0' : 1) : 0;
     CUtensorMap tmap;
@@ -465,7 +543,13 @@ extern "C" int st_bench_gather(int device, int64_t bytes, int64_t loads_per_thre
             k_gather_tex<0><<<grid, tpb>>>(tex, static_cast<const ulonglong4 *>(buf), n_sectors, loads_per_thread, seed, sink);
         else if (mix)
             k_gather_tex<1><<<grid, tpb>>>(tex, static_cast<const ulonglong4 *>(buf), n_sectors, loads_per_thread, seed, sink);
-        else if (ws >= 0) {
+        else if (add_tw >= 0) {
+            const int64_t rounds = loads_per_thread / 4, rounds_tma = rounds * add_pct / 100;
+            const int threads = 512 + 32 * add_tw, smem = add_tw * 8192 + add_tw * 16 + 16;
+            cudaFuncSetAttribute(k_gather_add, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+            k_gather_add<<<prop.multiProcessorCount * 3, threads, smem>>>(tmap, static_cast<const ulonglong4 *>(buf), n_sectors,
+                                                                       rounds, rounds_tma, add_tw, seed, sink);
+        } else if (ws >= 0) {
             const int64_t rounds = loads_per_thread / 4;
             const ulonglong4 *b = static_cast<const ulonglong4 *>(buf);
             switch (ws) {  // 3 CTAs of 512 threads per SM at most (shared memory of the TMA warps)
@@ -507,6 +591,12 @@ extern "C" int st_bench_gather(int device, int64_t bytes, int64_t loads_per_thre
     if (e != cudaSuccess) {
         st_set_error("st_bench_gather: %s", cudaGetErrorString(e));
         return ST_ERR_CUDA;
+    }
+    if (add_tw >= 0) {
+        const double rounds = double(loads_per_thread / 4), rounds_tma = double((loads_per_thread / 4) * add_pct / 100);
+        const double per_cta = 512.0 * rounds * 4.0 + 32.0 * add_tw * rounds_tma * 4.0;
+        *sectors_per_s = double(prop.multiProcessorCount) * 3.0 * per_cta / (double(best_ms) * 1e-3);
+        return ST_OK;
     }
     *sectors_per_s = double(grid) * tpb * double(loads_per_thread) * (1 + (ws >= 0 ? 0 : g4mix)) / (double(best_ms) * 1e-3);
     return ST_OK;
