@@ -66,6 +66,7 @@ class SuchTree:
         self._leaf_nodes = None
         self._RED = {}
         self._rd = None
+        self._leaf_ids = None
         if device is None:
             device = int(os.environ.get("LOCAL_RANK", "0"))
         self._handle = C.c_void_p()
@@ -162,7 +163,9 @@ class SuchTree:
 
     @property
     def leaf_node_ids(self):
-        return np.array(list(self.leaves.values()))
+        if self._leaf_ids is None:  # the tree is immutable: built once, handed out as copies
+            self._leaf_ids = np.array(list(self.leaves.values()))
+        return self._leaf_ids.copy()
 
     @property
     def leaf_names(self):
@@ -586,17 +589,25 @@ class SuchTree:
             raise ValueError("k must be positive")
         q = self._validate_node(node)
         if from_nodes is None:
+            # all leaves (minus the query if it is one), as arrays: names are looked up
+            # for the k winners only
+            from_ids = np.asarray(self.leaf_node_ids, dtype=np.int64)
             if self.is_leaf(q):
-                from_ids = [nid for nid in self.leaf_node_ids if nid != q]
-            else:
-                from_ids = list(self.leaf_node_ids)
-            from_orig = [self.leaf_nodes[nid] for nid in from_ids]
+                from_ids = from_ids[from_ids != q]
+            from_orig = None
         else:
-            from_ids = [self._validate_node(n) for n in from_nodes]
+            from_ids = np.array([self._validate_node(n) for n in from_nodes], dtype=np.int64)
             from_orig = list(from_nodes)
-        pairs = np.array([(q, nid) for nid in from_ids], dtype=np.int64)
+        if from_ids.shape[0] == 0:
+            return []
+        pairs = np.empty((from_ids.shape[0], 2), dtype=np.int64)
+        pairs[:, 0] = q
+        pairs[:, 1] = from_ids
         d = self.distances_bulk(pairs)
         order = np.argsort(d)
+        if from_orig is None:
+            leaf_nodes = self.leaf_nodes
+            return [(leaf_nodes[int(from_ids[i])], d[i]) for i in order[:k]]
         return [(from_orig[i], d[i]) for i in order[:k]]
 
     def pairwise_distances(self, nodes=None):
