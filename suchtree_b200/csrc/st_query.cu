@@ -5,28 +5,28 @@
 // for every ancestor of b (O(depth^2) pointer chasing per pair), the MRCA is the
 // argmin of depth over the id interval [min(a,b), max(a,b)] (ids are in-order
 // ranks), answered in O(1) from
-//     rec[lo].suf, rec[hi].pre            one 32-B sector each (they also carry rd)
-//     two block-table entries             shared memory
-// and the distance is rd[a] + rd[b] - 2 rd[mrca] in double-double
-//     rec[mrca].rd                        one more sector.
-// => 3 random L2 sectors + 16 B (int32x2 in, fp64 out) of streamed HBM per pair.
+//     rec[lo].suf, rec[hi].pre            one record each: 16 or 32 bytes, <= one sector,
+//                                         and they also carry rd[lo], rd[hi]
+//     two block-table entries             shared memory (staged by one TMA bulk copy)
+// and the distance is rd[a] + rd[b] - 2 rd[mrca] in double-double, with rd[mrca] from
+// the shared-memory table of block minima (a third gather only when the MRCA is not a
+// block minimum: ~3 % of far-apart pairs).
+// => 2 random L2 sectors + 16 B (int32x2 in, fp64 out) of streamed HBM per pair.
+// The same file holds the host-buffer pipeline of the drop-in entry points.
 #include <algorithm>
-#include <cmath>
-
 #include <chrono>
+#include <cmath>
+#include <cstring>
+#include <vector>
 #if defined(__SSE2__)
 #include <emmintrin.h>
 #endif
-#include <cstring>
-#include <vector>
 
 #include "st_device.cuh"
 #include "st_hostpool.cuh"
 
-
 // P pairs per thread per iteration, fetched as raw 64-bit words by 16-byte (P = 2,
-// int32) or 32-byte streaming loads and decoded when used (the prefetched copy of
-// the next iteration stays packed: fewer live registers)
+// int32) or 32-byte streaming loads and decoded when used
 template <typename IdxT, int P>
 struct RawPairs {
     static constexpr int W = P * int(sizeof(IdxT)) / 4;  // 64-bit words
