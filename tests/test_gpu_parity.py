@@ -271,3 +271,39 @@ def test_mrca_properties():
         assert a in T.get_descendants(m) and b in T.get_descendants(m)
     for a, b in combinations(T.leaves.keys(), 2):
         assert T.common_ancestor(a, b) == T.common_ancestor(T.leaves[a], T.leaves[b])
+
+
+def test_more_than_2_pow_32_pairs_in_one_launch():
+    """64-bit indexing: the reference's `unsigned int` loop counters
+    (MuchTree.pyx:923-930) wrap above 2^32 pairs per call.  One launch over 2^32 + 2^20
+    device-resident pairs; the results beyond the 32-bit boundary must equal a separate
+    small launch over the same pairs."""
+    import torch
+
+    free, _ = torch.cuda.mem_get_info()
+    n = (1 << 32) + (1 << 20)
+    if free < 17 * n + (4 << 30):
+        pytest.skip("needs ~75 GB of free device memory")
+    ft = synth.yule_tree(100000, seed=1)
+    T = SuchTree.from_flat(ft)
+    dev = torch.device("cuda", T.device)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    pairs = torch.empty((n, 2), dtype=torch.int32, device=dev)
+    out = torch.empty(n, dtype=torch.float64, device=dev)
+    T.random_leaf_pairs_device(5, 0, n, pairs.data_ptr(), stream=stream)
+    T.distances_device(pairs.data_ptr(), n, out.data_ptr(), stream=stream)
+    T.check_range(stream)
+    for lo in (0, (1 << 31) - 512, (1 << 32) - 512, n - 4096):
+        m = min(4096, n - lo)
+        ref = torch.empty(m, dtype=torch.float64, device=dev)
+        T.distances_device(pairs[lo:lo + m].data_ptr(), m, ref.data_ptr(), stream=stream)
+        torch.cuda.synchronize()
+        assert torch.equal(out[lo:lo + m], ref), lo
+        # and the generator itself did not wrap: same pairs as a shard started at `lo`
+        chk = torch.empty((m, 2), dtype=torch.int32, device=dev)
+        T.random_leaf_pairs_device(5, lo, m, chk.data_ptr(), stream=stream)
+        torch.cuda.synchronize()
+        assert torch.equal(pairs[lo:lo + m], chk), lo
+    assert bool(torch.isfinite(out[-(1 << 20):]).all())
+    del pairs, out
+    torch.cuda.empty_cache()
