@@ -41,6 +41,17 @@ WORKLOAD = ("cfg2: simulated 100k-leaf random binary (Yule, seed 1) tree, 1e8 ra
             "pairs per GPU per step via distances()")
 
 
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -168,7 +179,7 @@ def run_reference_arm(args):
         "config": {"workload": WORKLOAD, "tree_leaves": TREE_LEAVES, "pairs_per_step": per_step,
                    "note": "bounded sample of the 1e8-pair step; pool start-up outside the rate"},
         "cpu_baseline": {
-            "value": value, "unit": UNIT, "cores": cores, "kind": ref.kind,
+            "value": value, "unit": UNIT, "cores": cores, "kind": ref.kind, "cpu_model": cpu_model(),
             "sample": "%d pairs/step x %d steps of the cfg2 pair stream, fork Pool(%d) over "
                       "contiguous blocks; single core: %.3g pairs/s" % (per_step, args.steps, cores, rate1),
         },
@@ -291,7 +302,7 @@ def run_ours(args):
         rate_all, _ = ref.run(sample, cores) if cores > 1 else (rate1, None)
         cpu_baseline = {
             "value": rate_all, "unit": UNIT, "cores": cores, "kind": ref.kind,
-            "single_core_value": rate1,
+            "single_core_value": rate1, "cpu_model": cpu_model(), "os_cpu_count": os.cpu_count(),
             "sample": "first %d pairs of the step's Philox stream through the reference's "
                       "distances_bulk; 1 core, then fork Pool(%d)" % (n_s, cores),
         }
@@ -494,6 +505,42 @@ def run_other_workloads(args, rank, world, local, dev, peak):
         return float(t.item())
 
     res = {}
+    # ---- cfg1: the reference's own CPU-runnable case -- gopher tree (29 nodes), 1e6 random
+    #      leaf pairs: GPU (device-resident and through the drop-in host call) beside the
+    #      unmodified reference on one host core, results compared
+    if rank == 0:
+        G = SuchTree(os.path.join(REPO, "tests", "golden", "data", "test.tree"), device=local)
+        p1 = (np.random.default_rng(0).integers(0, 15, size=(1_000_000, 2)) * 2).astype(np.int64)
+        d_p1 = torch.from_numpy(p1).to(dev)
+        d_o1 = torch.empty(p1.shape[0], dtype=torch.float64, device=dev)
+        sec = _timed(stream, lambda: G.distances_device(d_p1.data_ptr(), p1.shape[0], d_o1.data_ptr(), idx_bits=64,
+                                                        stream=sptr), steps=20)
+        G.distances_bulk(p1)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            got = G.distances_bulk(p1)
+        host_s = (time.perf_counter() - t0) / 5
+        entry = {"workload": "cfg1: data/gopher-louse gopher tree (29 nodes), 1e6 random leaf-id pairs (int64)",
+                 "pairs_per_s_device_resident": p1.shape[0] / sec, "pairs_per_s_host_call": p1.shape[0] / host_s,
+                 "matches_device_path": bool(np.array_equal(got, d_o1.cpu().numpy()))}
+        try:
+            sys.path.insert(0, os.path.join(REPO, "oracle"))
+            import ref_loader
+
+            mod = ref_loader.load_reference(build_if_missing=False) if world == 1 else None
+            if mod is not None:
+                R = mod.SuchTree(os.path.join(REPO, "tests", "golden", "data", "test.tree"))
+                R.distances_bulk(p1[:1000])
+                t0 = time.perf_counter()
+                want = R.distances_bulk(p1)
+                entry["reference_pairs_per_s_one_core"] = p1.shape[0] / (time.perf_counter() - t0)
+                # fp32 accumulation in the reference (MuchTree.pyx:924): depth-scaled tolerance
+                entry["parity_vs_reference"] = bool(np.all(np.abs(got - want) <= 2e-7 * R.depth * np.maximum(got, 1e-30)))
+        except Exception as e:  # diagnostics only
+            entry["reference_error"] = repr(e)[:80]
+        res["cfg1_gopher"] = entry
+        del G
+
     # ---- cfg3: deep-path worst case + balanced, 1M leaves
     n3 = args.cfg3_pairs
     pairs = torch.empty((n3, 2), dtype=torch.int32, device=dev)
