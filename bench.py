@@ -317,8 +317,9 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
 
-        # rank 0 prints exactly one line on stdout: keep NCCL's version banner off it
-        os.environ["NCCL_DEBUG"] = os.environ.get("SUCHTREE_B200_NCCL_DEBUG", "WARN")
+        # rank 0 prints exactly one line on stdout: NCCL's own output (version banner,
+        # NCCL_DEBUG lines) goes to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     from suchtree_b200 import SuchTree, _lib
 
