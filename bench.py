@@ -317,10 +317,18 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
 
-        # rank 0 prints exactly one line on stdout: NCCL's own output (version banner,
-        # NCCL_DEBUG lines) goes to stderr instead
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly one JSON line: whatever NCCL prints while the communicator
+        # comes up (its version banner) goes to stderr -- fd 1 points at fd 2 meanwhile
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     from suchtree_b200 import SuchTree, _lib
 
     T = SuchTree.from_flat(ft, device=local)
