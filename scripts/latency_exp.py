@@ -9,11 +9,11 @@ for name, tree in (("100k-leaf", T), ("gopher", G)):
     ids = list(tree.leaves.values())
     a, b = ids[1], ids[-2]
     tree.distance(a, b)
-    for n in (1, 16, 256, 4096, 65536):
+    for n in (1, 256, 4096, 16384, 65536, 262144, 300000):
         pairs = np.array([[a, b]] * n, dtype=np.int64)
         tree.distances_bulk(pairs)
         t0 = time.perf_counter()
-        reps = 300
+        reps = 100
         for _ in range(reps):
             tree.distances_bulk(pairs)
         dt = (time.perf_counter() - t0) / reps

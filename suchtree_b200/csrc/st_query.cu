@@ -466,27 +466,35 @@ static void report_range(const int64_t *src, int64_t s0, int64_t s1, int64_t n, 
     st_set_error("node id %lld out of bounds (tree size %lld)", (long long)st_bad_node(), (long long)n_nodes);
 }
 
-// Latency path for small calls (distance(a,b), common_ancestor(a,b), short lists): the ids
-// are checked and packed on the host into pinned staging, ONE kernel reads them and writes
-// the results through the pinned mappings (zero-copy over PCIe), one synchronisation.
-static const int64_t ST_SMALL_CALL = 4096;
+// Latency path for small and medium calls (distance(a,b), common_ancestor(a,b), lists up to
+// 2^18 pairs): the ids are packed on the host into pinned staging, ONE kernel reads them and
+// writes the results through the pinned mappings (zero-copy over PCIe), one synchronisation.
+static const int64_t ST_SMALL_CALL = 4096;      // host-side range check, scalar pack
+static const int64_t ST_MEDIUM_CALL = 262144;   // pool pack, device-side range check
 
 static int host_pairs_small(const st_tree *t, const int64_t *pairs, int64_t s0, int64_t s1, int64_t n,
                             double *out_d, int32_t *out_m) {
     int rc = ensure_stage(t, n, true, true);
     if (rc != ST_OK) return rc;
     int32_t *hp = static_cast<int32_t *>(t->h_stage[0]);
-    int64_t mx = INT64_MIN, mn = INT64_MAX;
-    for (int64_t i = 0; i < n; ++i) {
-        const int64_t a = pairs[i * s0], b = pairs[i * s0 + s1];
-        mx = std::max(mx, std::max(a, b));
-        mn = std::min(mn, std::min(a, b));
-        hp[2 * i] = int32_t(a);
-        hp[2 * i + 1] = int32_t(b);
-    }
-    if (mn < 0 || mx >= t->n_nodes) {  // the reference's report (MuchTree.pyx:897-903)
-        st_set_bad_node(mx >= t->n_nodes ? mx : mn);
-        st_set_error("node id %lld out of bounds (tree size %lld)", (long long)st_bad_node(), (long long)t->n_nodes);
+    const bool tiny = n <= ST_SMALL_CALL;
+    if (tiny) {
+        int64_t mx = INT64_MIN, mn = INT64_MAX;
+        for (int64_t i = 0; i < n; ++i) {
+            const int64_t a = pairs[i * s0], b = pairs[i * s0 + s1];
+            mx = std::max(mx, std::max(a, b));
+            mn = std::min(mn, std::min(a, b));
+            hp[2 * i] = int32_t(a);
+            hp[2 * i + 1] = int32_t(b);
+        }
+        if (mn < 0 || mx >= t->n_nodes) {  // the reference's report (MuchTree.pyx:897-903)
+            st_set_bad_node(mx >= t->n_nodes ? mx : mn);
+            st_set_error("node id %lld out of bounds (tree size %lld)", (long long)st_bad_node(),
+                         (long long)t->n_nodes);
+            return ST_ERR_NODE_RANGE;
+        }
+    } else if (pack_pairs(pairs, s0, s1, n, hp, 2) >> 31) {  // negative or beyond int32
+        report_range(pairs, s0, s1, n, 2, t->n_nodes);
         return ST_ERR_NODE_RANGE;
     }
     void *ho = t->h_out_stage[0];
@@ -494,9 +502,25 @@ static int host_pairs_small(const st_tree *t, const int64_t *pairs, int64_t s0, 
     rc = st_launch_pairs(t, hp, 32, n, out_d ? static_cast<double *>(ho) : nullptr,
                          out_m ? static_cast<int32_t *>(ho) : nullptr, st);
     if (rc != ST_OK) return rc;
-    ST_CUDA(cudaStreamSynchronize(st));
-    if (out_d) memcpy(out_d, ho, size_t(n) * 8);
-    else memcpy(out_m, ho, size_t(n) * 4);
+    if (tiny) {
+        ST_CUDA(cudaStreamSynchronize(st));
+    } else {
+        // ids in [n_nodes, 2^31) are caught by the kernel: its status word rides the same
+        // stream (a copy to pageable memory returns when it has completed: one wait in all)
+        RangeStatus h{};
+        ST_CUDA(cudaMemcpyAsync(&h, t->d_status, sizeof(h), cudaMemcpyDeviceToHost, st));
+        ST_CUDA(cudaStreamSynchronize(st));
+        if (h.max_bad != 0 || h.min_bad != 0) {
+            ST_CUDA(cudaMemsetAsync(t->d_status, 0, sizeof(RangeStatus), st));
+            ST_CUDA(cudaStreamSynchronize(st));
+            report_range(pairs, s0, s1, n, 2, t->n_nodes);
+            return ST_ERR_NODE_RANGE;
+        }
+    }
+    const size_t bytes = size_t(n) * (out_d ? 8 : 4);
+    void *dst = out_d ? static_cast<void *>(out_d) : static_cast<void *>(out_m);
+    if (tiny) memcpy(dst, ho, bytes);
+    else parallel_copy(dst, ho, bytes);
     return ST_OK;
 }
 
@@ -509,7 +533,7 @@ static int host_pairs_run(const st_tree *t, const int64_t *pairs, int64_t s0, in
     if (n == 0) return ST_OK;
     DeviceGuard g(t->device);
     std::lock_guard<std::mutex> lock(t->host_mu);
-    if (n <= ST_SMALL_CALL && !(out_d && out_m)) return host_pairs_small(t, pairs, s0, s1, n, out_d, out_m);
+    if (n <= ST_MEDIUM_CALL && !(out_d && out_m)) return host_pairs_small(t, pairs, s0, s1, n, out_d, out_m);
     const bool contiguous = (s1 == 1 && s0 == 2);
     const bool out_pinned = is_pinned(out_d ? static_cast<void *>(out_d) : static_cast<void *>(out_m));
     bool pack = true;
