@@ -280,6 +280,7 @@ def test_more_than_2_pow_32_pairs_in_one_launch():
     small launch over the same pairs."""
     import torch
 
+    torch.cuda.empty_cache()
     free, _ = torch.cuda.mem_get_info()
     n = (1 << 32) + (1 << 20)
     if free < 17 * n + (4 << 30):
