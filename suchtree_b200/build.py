@@ -13,7 +13,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsuchtree_b200.so")
+# the C header: <repo>/include in a checkout, <package>/include when pip-installed
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+if not os.path.exists(os.path.join(INCLUDE, "suchtree_b200.h")):
+    INCLUDE = os.path.join(HERE, "include")
 OBJ = os.path.join(HERE, "_obj")
 
 NVCC_FLAGS = [

@@ -9,7 +9,7 @@
 #include <string>
 #include <vector>
 
-#include "../../include/suchtree_b200.h"
+#include "suchtree_b200.h"  // include/ of the repository, or suchtree_b200/include/ when installed
 
 // ---------------------------------------------------------------- errors ----
 void st_set_error(const char *fmt, ...);
