@@ -143,8 +143,8 @@ __device__ __forceinline__ SideRec ld_side(const SideRec *p) {
     s.comb_hi = __longlong_as_double((long long)x);
     s.comb_lo = __longlong_as_double((long long)y);
     s.depth = uint32_t(z);
-    (void)w;
-    s.pad0 = 0; s.pad1 = 0;
+    s.pad0 = 0;
+    s.pad1 = w;  // padding word of the record (keeps the fourth lane of the load "used")
     return s;
 }
 
