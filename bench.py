@@ -720,6 +720,37 @@ def run_other_workloads(args, rank, world, local, dev, peak):
         "quartets_per_s": world * nq / sec, "ms_per_launch": sec * 1e3,
         "hbm_frac": 64.0 * nq / sec / 1e9 / peak, "rows_are_permutations": is_perm,
     }
+    del T, quartets, topo
+
+    # ---- the reference's per-clade scan (docs/examples/SuchLinkedTree_examples.md:286-310:
+    #      for every internal node of TreeB { subset_b; linked_distances; pearson }, keeping
+    #      clades with 10..2500 links; 6 h 39 min there) as one launch sequence.  Rank 0 only,
+    #      no collective; on its own try so that a failure costs this entry alone.
+    if rank == 0:
+        try:
+            from suchtree_b200 import SuchLinkedTrees
+
+            fa3, fb3 = synth.yule_tree(TREE_LEAVES, seed=4, names=True), synth.yule_tree(TREE_LEAVES, seed=5, names=True)
+            A3, B3 = SuchTree.from_flat(fa3, device=local), SuchTree.from_flat(fb3, device=local)
+            SLT3 = SuchLinkedTrees.from_linklist(A3, B3, linklist)
+            SLT3.clade_pearson(min_links=10, max_links=2500)  # warm: clade intervals, scratch pool
+            t0 = time.perf_counter()
+            reps3 = 3
+            for _ in range(reps3):
+                scan = SLT3.clade_pearson(min_links=10, max_links=2500)
+            dt = (time.perf_counter() - t0) / reps3
+            done = np.isfinite(scan["r"])
+            res["clade_scan"] = {
+                "workload": "clade_pearson(min_links=10, max_links=2500) over all %d internal nodes of TreeB: two "
+                            "100k-leaf Yule trees, 100k random links (cfg4's), one GPU" % int(scan["node_ids"].shape[0]),
+                "clades_computed": int(done.sum()), "link_pairs": int(scan["n_pairs"].sum()),
+                "link_pairs_per_s": float(scan["n_pairs"].sum()) / dt, "s_per_scan": dt,
+                "timing": "host wall clock around the Python call (link sort + work-item plan on the host, "
+                          "3 kernels, moments read back)",
+            }
+            del SLT3, A3, B3
+        except Exception as e:  # diagnostics only
+            res["clade_scan"] = {"error": repr(e)[:200]}
     return res
 
 def main():

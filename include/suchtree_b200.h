@@ -217,6 +217,24 @@ ST_API int st_sample_moments(const st_tree *tree_a, const st_tree *tree_b, const
 ST_API int st_linked_moments(const st_tree *tree_a, const st_tree *tree_b, const int64_t *linklist,
                       int64_t n_links, int64_t first_pair, int64_t n_pairs, double x0, double y0,
                       st_moments *out);
+/* ---- per-clade scan: the host loop of the reference's co-phylogeny examples
+ *      (docs/examples/SuchLinkedTree_examples.md:286-310) -- for every internal node of one
+ *      tree { subset_b(node) (MuchTree.pyx:2876-2886, which re-runs _build_linklist,
+ *      :2845-2874); linked_distances() (:2900-2934); pearson() (:62-87) } -- as ONE launch
+ *      sequence; nothing is materialised.
+ * side = 0: clades of TreeB (selects on linklist[:,0]); side = 1: clades of TreeA
+ * (linklist[:,1]).  A clade is the inclusive interval [clade_lo[c], clade_hi[c]] of in-order
+ * node ids (the leaves SuchTree.get_leaves(node) returns, :427-463, are exactly the even ids
+ * in the interval spanned by the node's subtree); HOST int64 [n_clades].  For clade c the
+ * links whose id on `side` lies in the interval are the subset subset_b(node) would select
+ * out of `linklist`; n_links_out[c] (may be NULL) = their number (subset_n_links).  When
+ * max(min_links, 2) <= n <= max_links (max_links < 0: no upper bound), out[c] receives the
+ * moments over the n(n-1)/2 link pairs of the subset with x0, y0 = the distances of its first
+ * pair; otherwise out[c].n = 0 and the clade costs nothing.  HOST st_moments [n_clades]. */
+ST_API int st_clade_moments(const st_tree *tree_a, const st_tree *tree_b, const int64_t *linklist,
+                     int64_t n_links, int side, const int64_t *clade_lo, const int64_t *clade_hi,
+                     int64_t n_clades, int64_t min_links, int64_t max_links, st_moments *out,
+                     int64_t *n_links_out);
 /* Pearson r from (possibly all-reduced) moments: sxy / sqrt(sxx*syy + 1e-20),
  * the reference's formula (MuchTree.pyx:79) on centred sums. */
 ST_API double st_moments_pearson(const st_moments *m);

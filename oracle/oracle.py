@@ -200,3 +200,43 @@ def sample_bucket(seed, linklist, n):
     qb = np.empty((n, 2), np.int64)
     lib().oracle_sample_bucket(C.byref(s), ll, ll.shape[0], n, qa, qb)
     return qa, qb, int(s.value)
+
+
+# ---- per-clade scan: the reference's own loop, restated -------------------------
+def get_leaves(left, right, node):
+    """SuchTree.get_leaves (MuchTree.pyx:427-463): breadth-first queue from `node`."""
+    to_visit = [int(node)]
+    out = []
+    for cur in to_visit:
+        if left[cur] == -1:
+            out.append(cur)
+        else:
+            to_visit.append(int(left[cur]))
+            to_visit.append(int(right[cur]))
+    return np.array(out, dtype=np.int64)
+
+
+def subset_linklist(linklist, leafs, column):
+    """What subset_b(node) / subset_a(node) + _build_linklist (MuchTree.pyx:2845-2898)
+    leave of a link list: the rows whose id in `column` (0 = TreeB, 1 = TreeA) is one of
+    `leafs`, relative order kept (the link list is built column by column either way)."""
+    ll = np.ascontiguousarray(linklist, np.int64)
+    return np.ascontiguousarray(ll[np.isin(ll[:, column], np.asarray(leafs, np.int64))])
+
+
+def clade_scan(tree_a, tree_b, left, right, linklist, nodes, side):
+    """for node in nodes: subset_b(node) [side 'b'] or subset_a(node) [side 'a'];
+    linked_distances(); pearson() -- docs/examples/SuchLinkedTree_examples.md:286-310 --
+    with O2 distances (fp64 path sums) and the fp64 pearson.  left/right: child arrays of
+    the scanned tree.  Returns (n_links, r) per node; r = nan when there is no link pair."""
+    column = 0 if side == "b" else 1
+    n_links = np.zeros(len(nodes), np.int64)
+    r = np.full(len(nodes), np.nan)
+    for k, node in enumerate(nodes):
+        sub = subset_linklist(linklist, get_leaves(left, right, node), column)
+        n_links[k] = sub.shape[0]
+        if sub.shape[0] < 2:
+            continue
+        ids_a, ids_b = linked_pairs(sub)  # :2918-2925
+        r[k] = pearson_f64(tree_a.distances_f64(ids_a), tree_b.distances_f64(ids_b))
+    return n_links, r

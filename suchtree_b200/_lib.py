@@ -77,6 +77,7 @@ SIGNATURES = {
         _int, [_vp, _vp, _vp, _i64, _u64, _i64, _i64, C.c_double, C.c_double, C.POINTER(Moments)]),
     "st_linked_moments": (
         _int, [_vp, _vp, _vp, _i64, _i64, _i64, C.c_double, C.c_double, C.POINTER(Moments)]),
+    "st_clade_moments": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "st_moments_pearson": (C.c_double, [C.POINTER(Moments)]),
     "st_pearson": (_int, [_int, _vp, _vp, _i64, C.POINTER(C.c_double)]),
     "st_bench_pack": (_int, [_i64, _int, C.POINTER(C.c_double)]),

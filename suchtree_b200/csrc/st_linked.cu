@@ -484,12 +484,18 @@ extern "C" int st_sample_moments(const st_tree *ta, const st_tree *tb, const int
     double *d_part = nullptr;  // [grid][5] partials, then 5 folded sums
     ST_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d_part), size_t(grid + 1) * 5 * 8, s));
     double *d_out = d_part + size_t(grid) * 5;
+    int rc_launch = ST_OK;
 #define ST_LAUNCH_SAMPLE(MA, MB)                                                                         \
-    if (set_smem(k_sample_moments<MA, MB>, smem) == ST_OK)                                               \
+    rc_launch = set_smem(k_sample_moments<MA, MB>, smem);                                                \
+    if (rc_launch == ST_OK)                                                                              \
         k_sample_moments<MA, MB><<<grid, MLT, smem, s>>>(ta->view, tb->view, dl.rows, uint32_t(L), seed, \
                                                          first_sample, n_samples, x0, y0, d_part)
     ST_DISPATCH_MODES(tree_mode(ta), tree_mode(tb), ST_LAUNCH_SAMPLE);
 #undef ST_LAUNCH_SAMPLE
+    if (rc_launch != ST_OK) {  // the kernel was not launched: no result to report
+        cudaFreeAsync(d_part, s);
+        return rc_launch;
+    }
     k_reduce_partials<<<1, 160, 0, s>>>(grid, d_part, d_out);
     double h[5];
     cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, s);
@@ -582,12 +588,18 @@ extern "C" int st_linked_moments(const st_tree *ta, const st_tree *tb, const int
     double *d_part = nullptr;
     ST_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d_part), size_t(grid + 1) * 5 * 8, s));
     double *d_out = d_part + size_t(grid) * 5;
+    int rc_launch = ST_OK;
 #define ST_LAUNCH_LINKED(MA, MB)                                                                  \
-    if (set_smem(k_linked_moments<MA, MB>, smem) == ST_OK)                                        \
+    rc_launch = set_smem(k_linked_moments<MA, MB>, smem);                                         \
+    if (rc_launch == ST_OK)                                                                       \
         k_linked_moments<MA, MB><<<grid, MLT, smem, s>>>(ta->view, tb->view, dl.rows, first_pair, \
                                                          n_pairs, x0, y0, d_part)
     ST_DISPATCH_MODES(tree_mode(ta), tree_mode(tb), ST_LAUNCH_LINKED);
 #undef ST_LAUNCH_LINKED
+    if (rc_launch != ST_OK) {  // the kernel was not launched: no result to report
+        cudaFreeAsync(d_part, s);
+        return rc_launch;
+    }
     k_reduce_partials<<<1, 160, 0, s>>>(grid, d_part, d_out);
     double h[5];
     cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, s);
@@ -599,6 +611,261 @@ extern "C" int st_linked_moments(const st_tree *ta, const st_tree *tb, const int
         return ST_ERR_CUDA;
     }
     out->sx = h[0]; out->sy = h[1]; out->sxx = h[2]; out->syy = h[3]; out->sxy = h[4];
+    return ST_OK;
+}
+
+// ----------------------------------------------- per-clade scan, one launch --
+// The reference's co-phylogeny scan (docs/examples/SuchLinkedTree_examples.md:286-310) is a
+// host loop over the internal nodes of one tree: subset_b(node) (MuchTree.pyx:2876-2886, which
+// re-runs _build_linklist, :2845-2874), linked_distances() (:2900-2934), pearson().  A clade
+// is a contiguous interval of in-order ids (SuchTree.get_leaves, :427-463), so with the links
+// sorted by the id on the scanned side every subset is a contiguous RUN of links, and the whole
+// scan is one flat list of work items (clade, pair range) over the same fused-moment inner loop
+// as k_linked_moments.  One warp per item, items handed out by an atomic counter (any
+// assignment gives the same result: each item owns its partial, folded per clade in item order).
+struct CladeItem {
+    int64_t first;  // first pair of the item in the clade's own (i, j<i) enumeration
+    int32_t clade;  // slot among the eligible clades
+    int32_t len;    // pairs in the item
+};
+static_assert(sizeof(CladeItem) == 16, "CladeItem is one 16-byte load");
+
+// x0, y0 of every clade: the distances of its first link pair (conditioning shift, as in
+// SuchLinkedTrees.linked_pearson)
+__global__ void k_clade_shift(const TreeView ta, const TreeView tb, const int2 *__restrict__ links,
+                              const int64_t *__restrict__ run_begin, int32_t n_clades,
+                              double2 *__restrict__ shift) {
+    const int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_clades) return;
+    const int2 l1 = __ldg(links + run_begin[c]), l2 = __ldg(links + run_begin[c] + 1);
+    shift[c] = make_double2(linked_query<2>(ta, st_global_tables(ta), l1.y, l2.y),
+                            linked_query<2>(tb, st_global_tables(tb), l1.x, l2.x));
+}
+
+template <int MA, int MB>
+__global__ void __launch_bounds__(MLT)
+k_clade_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ links,
+                const int64_t *__restrict__ run_begin, const double2 *__restrict__ shift,
+                const CladeItem *__restrict__ items, int32_t n_items, int32_t *__restrict__ next_item,
+                double *__restrict__ partials /* [n_items][5] */) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t tables_bar[2];
+    const int offs = (st_table_bytes(ta.n_blocks, ta.st_levels, st_table_mode(ta)) + 15) & ~15;
+    st_tables_issue(ta, smem_raw, &tables_bar[0]);
+    st_tables_issue(tb, smem_raw + offs, &tables_bar[1]);
+    __syncthreads();
+    const SmemTables sa = st_tables_wait<MA>(ta, smem_raw, &tables_bar[0]);
+    const SmemTables sb = st_tables_wait<MB>(tb, smem_raw + offs, &tables_bar[1]);
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int32_t it = 0;
+        if (lane == 0) it = atomicAdd(next_item, 1);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= n_items) break;
+        const int4 raw = __ldg(reinterpret_cast<const int4 *>(items + it));
+        const int64_t first = (int64_t)((uint64_t(uint32_t(raw.y)) << 32) | uint32_t(raw.x));
+        const int32_t clade = raw.z, len = raw.w;
+        const int2 *__restrict__ run = links + __ldg(run_begin + clade);
+        const double2 sh = __ldg(shift + clade);
+        Mom5 m{0, 0, 0, 0, 0};
+        int32_t i = 1, j = 0;  // link indices inside the run (n_links < 2^31)
+        if (lane < len) {
+            int64_t i64, j64;
+            tri_unrank(first + lane, i64, j64);
+            i = int32_t(i64);
+            j = int32_t(j64);
+        }
+        for (int32_t q = lane; q < len; q += 32) {
+            const int2 l1 = __ldg(run + j), l2 = __ldg(run + i);
+            for (j += 32; j >= i; ++i) j -= i;  // 32 positions on in the (i, j<i) enumeration
+            const double x = linked_query<MA>(ta, sa, l1.y, l2.y) - sh.x;
+            const double y = linked_query<MB>(tb, sb, l1.x, l2.x) - sh.y;
+            m.sx += x; m.sy += y;
+            m.sxx += x * x; m.syy += y * y; m.sxy += x * y;
+        }
+        double v[5] = {m.sx, m.sy, m.sxx, m.syy, m.sxy};
+#pragma unroll
+        for (int k = 0; k < 5; ++k) v[k] = warp_sum(v[k]);
+        if (lane < 5) {
+            // lane k keeps moment k (all lanes hold every sum after the xor-shuffles)
+            double mine = v[0];
+#pragma unroll
+            for (int k = 1; k < 5; ++k) mine = lane == k ? v[k] : mine;
+            partials[size_t(it) * 5 + lane] = mine;
+        }
+    }
+}
+
+// one warp per clade folds the partials of its items in a fixed order
+__global__ void k_clade_fold(const double *__restrict__ partials, const int32_t *__restrict__ item_begin,
+                             int32_t n_clades, double *__restrict__ out /* [n_clades][5] */) {
+    const int32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= n_clades) return;
+    const int32_t b = item_begin[c], e = item_begin[c + 1];
+    double v[5] = {0, 0, 0, 0, 0};
+    for (int32_t it = b + lane; it < e; it += 32)
+#pragma unroll
+        for (int k = 0; k < 5; ++k) v[k] += partials[size_t(it) * 5 + k];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const double s = warp_sum(v[k]);
+        if (lane == 0) out[size_t(c) * 5 + k] = s;
+    }
+}
+
+extern "C" int st_clade_moments(const st_tree *ta, const st_tree *tb, const int64_t *linklist, int64_t L,
+                                int side, const int64_t *clade_lo, const int64_t *clade_hi,
+                                int64_t n_clades, int64_t min_links, int64_t max_links, st_moments *out,
+                                int64_t *n_links_out) {
+    int rc = check_pair_of_trees(ta, tb, linklist, L);
+    if (rc != ST_OK) return rc;
+    if ((side != 0 && side != 1) || n_clades < 0 || (n_clades > 0 && (!clade_lo || !clade_hi || !out)) ||
+        L >= (int64_t(1) << 31)) {
+        st_set_error("st_clade_moments: bad arguments (side must be 0 or 1, clade arrays and out non-NULL)");
+        return ST_ERR_INVALID_ARG;
+    }
+    if (min_links < 2) min_links = 2;  // a pair needs two links
+    if (max_links < 0) max_links = INT64_MAX;
+    for (int64_t i = 0; i < L; ++i) {
+        const int64_t vb = linklist[2 * i], va = linklist[2 * i + 1];
+        if (va < 0 || va >= ta->n_nodes || vb < 0 || vb >= tb->n_nodes) {
+            const bool a_bad = va < 0 || va >= ta->n_nodes;
+            st_set_bad_node(a_bad ? va : vb);
+            st_set_error("linklist row %lld: %s id %lld out of bounds", (long long)i, a_bad ? "TreeA" : "TreeB",
+                         (long long)(a_bad ? va : vb));
+            return ST_ERR_NODE_RANGE;
+        }
+    }
+    // links sorted (stably) by the id on the scanned side: every clade is a run
+    std::vector<int32_t> order(static_cast<size_t>(L));
+    for (int64_t i = 0; i < L; ++i) order[size_t(i)] = int32_t(i);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t p, int32_t q) {
+        return linklist[2 * int64_t(p) + side] < linklist[2 * int64_t(q) + side];
+    });
+    std::vector<int64_t> keys(static_cast<size_t>(L));
+    std::vector<int2> rows(static_cast<size_t>(L));
+    for (int64_t i = 0; i < L; ++i) {
+        const int64_t r = order[size_t(i)];
+        keys[size_t(i)] = linklist[2 * r + side];
+        rows[size_t(i)] = make_int2(int32_t(linklist[2 * r]), int32_t(linklist[2 * r + 1]));
+    }
+    // runs, eligible clades, work items
+    std::vector<int64_t> run_begin;   // per eligible clade
+    std::vector<int64_t> slot_clade;  // eligible slot -> caller's clade index
+    std::vector<int64_t> run_len;
+    double total_pairs = 0.0;
+    for (int64_t c = 0; c < n_clades; ++c) {
+        const int64_t s = std::lower_bound(keys.begin(), keys.end(), clade_lo[c]) - keys.begin();
+        const int64_t e = std::upper_bound(keys.begin(), keys.end(), clade_hi[c]) - keys.begin();
+        const int64_t n = e > s ? e - s : 0;
+        if (n_links_out) n_links_out[c] = n;
+        out[c].n = 0.0;
+        out[c].x0 = out[c].y0 = out[c].sx = out[c].sy = out[c].sxx = out[c].syy = out[c].sxy = 0.0;
+        if (n < min_links || n > max_links) continue;
+        run_begin.push_back(s);
+        run_len.push_back(n);
+        slot_clade.push_back(c);
+        total_pairs += double(n) * double(n - 1) * 0.5;
+    }
+    const int64_t n_elig = int64_t(run_begin.size());
+    if (n_elig == 0) return ST_OK;
+    if (n_elig >= (int64_t(1) << 31) || total_pairs >= 9.0e18) {
+        st_set_error("st_clade_moments: too much work for one call (%lld clades, %.3g pairs)", (long long)n_elig,
+                     total_pairs);
+        return ST_ERR_INVALID_ARG;
+    }
+    // items of at most `chunk` pairs (a multiple of 32), about 2^20 of them at most
+    int64_t chunk = (int64_t(total_pairs / double(int64_t(1) << 20)) + 31) & ~int64_t(31);
+    chunk = std::min<int64_t>(std::max<int64_t>(chunk, 4096), int64_t(1) << 30);
+    std::vector<CladeItem> items;
+    std::vector<int32_t> item_begin(size_t(n_elig) + 1, 0);
+    for (int64_t c = 0; c < n_elig; ++c) {
+        const int64_t pairs = run_len[size_t(c)] * (run_len[size_t(c)] - 1) / 2;
+        for (int64_t p = 0; p < pairs; p += chunk)
+            items.push_back(CladeItem{p, int32_t(c), int32_t(std::min(chunk, pairs - p))});
+        if (items.size() >= (size_t(1) << 31)) {
+            st_set_error("st_clade_moments: too many work items");
+            return ST_ERR_INVALID_ARG;
+        }
+        item_begin[size_t(c) + 1] = int32_t(items.size());
+    }
+    const int32_t n_items = int32_t(items.size());
+
+    DeviceGuard g(ta->device);
+    cudaStream_t s = ta->streams[0];
+    // one stream-ordered scratch block: rows | run_begin | items | item_begin | shift | partials | out5 | counter
+    auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+    const size_t o_rows = 0, o_run = o_rows + al(size_t(L) * 8), o_items = o_run + al(size_t(n_elig) * 8),
+                 o_ibeg = o_items + al(size_t(n_items) * 16), o_shift = o_ibeg + al((size_t(n_elig) + 1) * 4),
+                 o_part = o_shift + al(size_t(n_elig) * 16), o_out = o_part + al(size_t(n_items) * 40),
+                 o_cnt = o_out + al(size_t(n_elig) * 40), bytes = o_cnt + 256;
+    unsigned char *d = nullptr;
+    if (cudaMallocAsync(reinterpret_cast<void **>(&d), bytes, s) != cudaSuccess) {
+        cudaGetLastError();
+        st_set_error("st_clade_moments: device allocation of %zu bytes failed", bytes);
+        return ST_ERR_NOMEM;
+    }
+    int2 *d_rows = reinterpret_cast<int2 *>(d + o_rows);
+    int64_t *d_run = reinterpret_cast<int64_t *>(d + o_run);
+    CladeItem *d_items = reinterpret_cast<CladeItem *>(d + o_items);
+    int32_t *d_ibeg = reinterpret_cast<int32_t *>(d + o_ibeg);
+    double2 *d_shift = reinterpret_cast<double2 *>(d + o_shift);
+    double *d_part = reinterpret_cast<double *>(d + o_part);
+    double *d_out = reinterpret_cast<double *>(d + o_out);
+    int32_t *d_cnt = reinterpret_cast<int32_t *>(d + o_cnt);
+    std::vector<double> h_out(size_t(n_elig) * 5);
+    std::vector<double2> h_shift(static_cast<size_t>(n_elig));
+    cudaError_t e = cudaSuccess;
+    auto step = [&](cudaError_t r) {
+        if (e == cudaSuccess) e = r;
+    };
+    step(cudaMemcpyAsync(d_rows, rows.data(), size_t(L) * 8, cudaMemcpyHostToDevice, s));
+    step(cudaMemcpyAsync(d_run, run_begin.data(), size_t(n_elig) * 8, cudaMemcpyHostToDevice, s));
+    step(cudaMemcpyAsync(d_items, items.data(), size_t(n_items) * 16, cudaMemcpyHostToDevice, s));
+    step(cudaMemcpyAsync(d_ibeg, item_begin.data(), (size_t(n_elig) + 1) * 4, cudaMemcpyHostToDevice, s));
+    step(cudaMemsetAsync(d_cnt, 0, 4, s));
+    const int smem = ((ta->query_smem_bytes + 15) & ~15) + tb->query_smem_bytes;
+    const int grid = int(std::min<int64_t>((int64_t(n_items) + MLT / 32 - 1) / (MLT / 32), int64_t(ta->sm_count)));
+    if (e == cudaSuccess) {
+        k_clade_shift<<<int((n_elig + 255) / 256), 256, 0, s>>>(ta->view, tb->view, d_rows, d_run,
+                                                                 int32_t(n_elig), d_shift);
+        int rc2 = ST_OK;
+#define ST_LAUNCH_CLADE(MA, MB)                                                                          \
+    rc2 = set_smem(k_clade_moments<MA, MB>, smem);                                                       \
+    if (rc2 == ST_OK)                                                                                    \
+        k_clade_moments<MA, MB><<<grid, MLT, smem, s>>>(ta->view, tb->view, d_rows, d_run, d_shift,      \
+                                                        d_items, n_items, d_cnt, d_part)
+        ST_DISPATCH_MODES(tree_mode(ta), tree_mode(tb), ST_LAUNCH_CLADE);
+#undef ST_LAUNCH_CLADE
+        if (rc2 != ST_OK) {
+            cudaFreeAsync(d, s);
+            cudaStreamSynchronize(s);
+            return rc2;
+        }
+        k_clade_fold<<<int((n_elig * 32 + 255) / 256), 256, 0, s>>>(d_part, d_ibeg, int32_t(n_elig), d_out);
+        step(cudaGetLastError());
+        step(cudaMemcpyAsync(h_out.data(), d_out, h_out.size() * 8, cudaMemcpyDeviceToHost, s));
+        step(cudaMemcpyAsync(h_shift.data(), d_shift, h_shift.size() * 16, cudaMemcpyDeviceToHost, s));
+    }
+    cudaFreeAsync(d, s);
+    step(cudaStreamSynchronize(s));  // also keeps the host vectors alive until the copies have left them
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        st_set_error("st_clade_moments: %s", cudaGetErrorString(e));
+        return ST_ERR_CUDA;
+    }
+    for (int64_t c = 0; c < n_elig; ++c) {
+        st_moments &m = out[slot_clade[size_t(c)]];
+        const int64_t n = run_len[size_t(c)];
+        m.n = double(n) * double(n - 1) * 0.5;
+        m.x0 = h_shift[size_t(c)].x;
+        m.y0 = h_shift[size_t(c)].y;
+        m.sx = h_out[size_t(c) * 5 + 0];
+        m.sy = h_out[size_t(c) * 5 + 1];
+        m.sxx = h_out[size_t(c) * 5 + 2];
+        m.syy = h_out[size_t(c) * 5 + 3];
+        m.sxy = h_out[size_t(c) * 5 + 4];
+    }
     return ST_OK;
 }
 

@@ -80,7 +80,50 @@ class SuchLinkedTrees:
         self._link_a = row_leaf_ids[rows]
         self._n_links = int(cols.shape[0])
 
+        self._set_default_subset()
+
+    @classmethod
+    def from_linklist(cls, tree_a, tree_b, linklist):
+        """Extra, not in the reference: the same object from link rows [TreeB leaf id,
+        TreeA leaf id] (the layout of .linklist, :2869-2870) instead of a DataFrame --
+        synthetic workloads with 10^5+ links, where a dense link matrix would not fit.
+        Links are kept in the reference's order: by column (TreeB leaf, ascending id),
+        then in the order given."""
+        self = cls.__new__(cls)
+        self._seed = int(np.random.randint(_UINT64_MAX >> 1))
+        self._TreeA, self._TreeB = TA, TB = cls._as_tree(tree_a), cls._as_tree(tree_b)
+        if TA.device != TB.device:
+            raise Exception("both trees must live on the same device", (TA.device, TB.device))
+        ll = np.ascontiguousarray(linklist, dtype=np.int64)
+        if ll.ndim != 2 or ll.shape[1] != 2:
+            raise ValueError("linklist must have shape (n_links, 2)")
+        self._row_ids = TA.leaf_node_ids
+        self._col_ids = TB.leaf_node_ids
+        self._row_names = TA.leaf_names
+        self._col_names = TB.leaf_names
+        self._n_rows, self._n_cols = TA.num_leaves, TB.num_leaves
+        self._row_map = np.full(TA.size, -1, dtype=np.int64)
+        self._row_map[self._row_ids] = np.arange(self._n_rows)
+        self._col_of_leaf = np.full(TB.size, -1, dtype=np.int64)
+        self._col_of_leaf[self._col_ids] = np.arange(self._n_cols)
+        for col, T, what in ((0, TB, self._col_of_leaf), (1, TA, self._row_map)):
+            ids = ll[:, col]
+            bad = (ids < 0) | (ids >= T.size)
+            if not bad.any():
+                bad = what[ids] < 0
+            if bad.any():
+                raise Exception("linklist: not a leaf id of Tree%s" % "BA"[col], int(ids[np.argmax(bad)]))
+        cols = self._col_of_leaf[ll[:, 0]]
+        perm = np.argsort(cols, kind="stable")
+        self._link_cols = cols[perm]
+        self._link_a = ll[perm, 1]
+        self._n_links = int(ll.shape[0])
+        self._set_default_subset()
+        return self
+
+    def _set_default_subset(self):
         # default subset = everything (:2652-2662)
+        TA, TB = self._TreeA, self._TreeB
         self._subset_a_root = TA.root_node
         self._subset_b_root = TB.root_node
         self._subset_a_leafs = self._row_ids
@@ -326,6 +369,73 @@ class SuchLinkedTrees:
         x0 = self._TreeA.distance(int(ll[0, 1]), int(ll[1, 1]))
         y0 = self._TreeB.distance(int(ll[0, 0]), int(ll[1, 0]))
         return moments_pearson(self.linked_moments(x0=x0, y0=y0))
+
+    def clade_moments(self, nodes=None, side="b", min_links=2, max_links=None):
+        """The reference's per-clade scan -- for node in nodes: subset_b(node) (or
+        subset_a for side="a"); linked_distances(); pearson()
+        (docs/examples/SuchLinkedTree_examples.md:286-310) -- in one launch sequence:
+        a clade is a contiguous id interval, so every subset is a run of the link list
+        sorted by the scanned side's leaf id.  The subset currently set on the OTHER side
+        stays in force (as it does across the reference's subset_b calls); the scanned
+        side's own subset is replaced per clade, exactly as subset_b(node) replaces it.
+        nodes: node ids of the scanned tree (default: all its internal nodes).  Clades
+        with fewer than min_links or more than max_links links are counted but not
+        computed (the example's `if SLT.subset_n_links < 10: continue`).
+        Returns (node_ids, n_leafs, n_links, moments) with moments a ctypes array of
+        _lib.Moments (n = 0 where skipped)."""
+        if side not in ("a", "b"):
+            raise ValueError("side must be 'a' or 'b'")
+        T = self._TreeB if side == "b" else self._TreeA
+        if nodes is None:
+            nodes = np.nonzero(np.asarray(T._ft.left) != -1)[0]
+        nodes = np.ascontiguousarray(nodes, dtype=np.int64).reshape(-1)
+        if nodes.size and (nodes.min() < 0 or nodes.max() >= T.size):
+            raise Exception("Node ID out of bounds.", int(nodes.max() if nodes.max() >= T.size else nodes.min()))
+        lo_all, hi_all = T._clade_intervals()
+        lo = np.ascontiguousarray(lo_all[nodes], dtype=np.int64)
+        hi = np.ascontiguousarray(hi_all[nodes], dtype=np.int64)
+        # links under the other side's current subset, in link-table order (by column,
+        # then by the link matrix's row order: _build_linklist's order, :2845-2874)
+        if side == "b":
+            in_a = np.zeros(self._TreeA.size, dtype=bool)
+            in_a[np.asarray(self._subset_a_leafs, dtype=np.int64)] = True
+            keep = in_a[self._link_a]
+        else:
+            in_cols = np.zeros(self._n_cols, dtype=bool)
+            in_cols[np.asarray(self._subset_columns, dtype=np.int64)] = True
+            keep = in_cols[self._link_cols]
+        ll = np.empty((int(keep.sum()), 2), dtype=np.int64)
+        ll[:, 0] = self._col_ids[self._link_cols[keep]]
+        ll[:, 1] = self._link_a[keep]
+        n = int(nodes.shape[0])
+        moments = (_lib.Moments * max(n, 1))()
+        n_links = np.zeros(n, dtype=np.int64)
+        if n:
+            rc = _lib.lib().st_clade_moments(
+                self._TreeA._handle, self._TreeB._handle, ll.ctypes.data, int(ll.shape[0]),
+                0 if side == "b" else 1, lo.ctypes.data, hi.ctypes.data, n, int(min_links),
+                -1 if max_links is None else int(max_links), C.cast(moments, C.c_void_p), n_links.ctypes.data)
+            _lib.check(rc)
+        return nodes, (hi - lo) // 2 + 1, n_links, moments
+
+    def clade_pearson(self, nodes=None, side="b", min_links=2, max_links=None):
+        """Pearson r of (TreeA distance, TreeB distance) over all link pairs of every
+        clade: dict of arrays node_ids, n_leafs (subset_b_size), n_links (subset_n_links),
+        n_pairs, r (nan where the clade was skipped by min_links / max_links)."""
+        nodes, n_leafs, n_links, moments = self.clade_moments(nodes, side, min_links, max_links)
+        n = int(nodes.shape[0])
+        m = np.frombuffer(moments, dtype=np.float64).reshape(-1, 8)[:n]
+        cnt = m[:, 0]
+        done = cnt > 0
+        r = np.full(n, np.nan)
+        c = np.where(done, cnt, 1.0)
+        cxx = m[:, 5] - m[:, 3] * m[:, 3] / c
+        cyy = m[:, 6] - m[:, 4] * m[:, 4] / c
+        cxy = m[:, 7] - m[:, 3] * m[:, 4] / c
+        with np.errstate(invalid="ignore"):
+            r[done] = (cxy / np.sqrt(cxx * cyy + 1.0e-20))[done]  # st_moments_pearson, MuchTree.pyx:79
+        return {"node_ids": nodes, "n_leafs": n_leafs, "n_links": n_links,
+                "n_pairs": cnt.astype(np.int64), "r": r}
 
     def sample_pearson(self, n_samples, seed=0):
         """Sampled two-tree Pearson r over n_samples link pairs drawn with replacement."""

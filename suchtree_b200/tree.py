@@ -259,6 +259,24 @@ class SuchTree:
             hi = right[hi]
         return int(lo), int(hi)
 
+    def _clade_intervals(self):
+        """(lo, hi) arrays: [first, last] id of the clade under every node, by pointer
+        doubling over the left-most / right-most child maps (log2(depth) numpy passes,
+        so the 10^6-deep caterpillar costs 20 of them)."""
+        if getattr(self, "_clade_lo_hi", None) is None:
+            ids = np.arange(self._size, dtype=np.int64)
+            out = []
+            for child in (self._ft.left, self._ft.right):
+                f = np.where(np.asarray(child) == -1, ids, np.asarray(child, dtype=np.int64))
+                while True:
+                    g = f[f]
+                    if np.array_equal(g, f):
+                        break
+                    f = g
+                out.append(f)
+            self._clade_lo_hi = (out[0], out[1])
+        return self._clade_lo_hi
+
     def is_ancestor(self, a, b):
         """1 if a is an ancestor of b, -1 if b is an ancestor of a, else 0
         (MuchTree.pyx is_ancestor semantics)."""
