@@ -7,7 +7,7 @@ Everything numerical runs in libsuchtree_b200.so (hand-written sm_100a CUDA behi
 the C ABI of include/suchtree_b200.h); there is no CPU fallback.
 """
 from .exceptions import InvalidNodeError, NodeNotFoundError, SuchTreeError, TreeStructureError
-from .linked import SuchLinkedTrees, moments_pearson, pearson
+from .linked import SuchLinkedTrees, as_moments, moments_pearson, pearson
 from .tree import SuchTree
 
 __version__ = "0.1.0"
@@ -17,6 +17,7 @@ __all__ = [
     "SuchLinkedTrees",
     "pearson",
     "moments_pearson",
+    "as_moments",
     "SuchTreeError",
     "NodeNotFoundError",
     "InvalidNodeError",

@@ -736,18 +736,18 @@ extern "C" int st_clade_moments(const st_tree *ta, const st_tree *tb, const int6
             return ST_ERR_NODE_RANGE;
         }
     }
-    // links sorted (stably) by the id on the scanned side: every clade is a run
-    std::vector<int32_t> order(static_cast<size_t>(L));
-    for (int64_t i = 0; i < L; ++i) order[size_t(i)] = int32_t(i);
-    std::stable_sort(order.begin(), order.end(), [&](int32_t p, int32_t q) {
-        return linklist[2 * int64_t(p) + side] < linklist[2 * int64_t(q) + side];
-    });
-    std::vector<int64_t> keys(static_cast<size_t>(L));
+    // links sorted (stably) by the id on the scanned side -- a counting sort over the node ids,
+    // O(links + nodes) -- so that every clade is a run: first[v] = number of links with id < v
+    const int64_t n_side = side == 0 ? tb->n_nodes : ta->n_nodes;
+    std::vector<int32_t> first(static_cast<size_t>(n_side) + 1, 0);
+    for (int64_t i = 0; i < L; ++i) ++first[size_t(linklist[2 * i + side]) + 1];
+    for (int64_t v = 0; v < n_side; ++v) first[size_t(v) + 1] += first[size_t(v)];
     std::vector<int2> rows(static_cast<size_t>(L));
-    for (int64_t i = 0; i < L; ++i) {
-        const int64_t r = order[size_t(i)];
-        keys[size_t(i)] = linklist[2 * r + side];
-        rows[size_t(i)] = make_int2(int32_t(linklist[2 * r]), int32_t(linklist[2 * r + 1]));
+    {
+        std::vector<int32_t> next(first.begin(), first.end() - 1);
+        for (int64_t i = 0; i < L; ++i)
+            rows[size_t(next[size_t(linklist[2 * i + side])]++)] =
+                make_int2(int32_t(linklist[2 * i]), int32_t(linklist[2 * i + 1]));
     }
     // runs, eligible clades, work items
     std::vector<int64_t> run_begin;   // per eligible clade
@@ -755,9 +755,10 @@ extern "C" int st_clade_moments(const st_tree *ta, const st_tree *tb, const int6
     std::vector<int64_t> run_len;
     double total_pairs = 0.0;
     for (int64_t c = 0; c < n_clades; ++c) {
-        const int64_t s = std::lower_bound(keys.begin(), keys.end(), clade_lo[c]) - keys.begin();
-        const int64_t e = std::upper_bound(keys.begin(), keys.end(), clade_hi[c]) - keys.begin();
-        const int64_t n = e > s ? e - s : 0;
+        // links with clade_lo <= id <= clade_hi (bounds clamped to the tree)
+        const int64_t lo = std::max<int64_t>(clade_lo[c], 0), hi = std::min<int64_t>(clade_hi[c], n_side - 1);
+        const int64_t s = lo <= hi ? first[size_t(lo)] : 0;
+        const int64_t n = lo <= hi ? first[size_t(hi) + 1] - s : 0;
         if (n_links_out) n_links_out[c] = n;
         out[c].n = 0.0;
         out[c].x0 = out[c].y0 = out[c].sx = out[c].sy = out[c].sxx = out[c].syy = out[c].sxy = 0.0;

@@ -147,6 +147,7 @@ class SuchLinkedTrees:
     def _build_linklist(self):
         """rows [TreeB leaf id, TreeA leaf id], ordered by subset column, then by the
         link order inside the column, restricted to subset_a's leaves."""
+        self._subset_version = getattr(self, "_subset_version", 0) + 1
         in_a = np.zeros(self._TreeA.size, dtype=bool)
         in_a[np.asarray(self._subset_a_leafs, dtype=np.int64)] = True
         # stable selection of the links of each subset column, in subset-column order
@@ -381,8 +382,9 @@ class SuchLinkedTrees:
         nodes: node ids of the scanned tree (default: all its internal nodes).  Clades
         with fewer than min_links or more than max_links links are counted but not
         computed (the example's `if SLT.subset_n_links < 10: continue`).
-        Returns (node_ids, n_leafs, n_links, moments) with moments a ctypes array of
-        _lib.Moments (n = 0 where skipped)."""
+        Returns (node_ids, n_leafs, n_links, moments) with moments a float64 array
+        (n_clades, 8) whose rows are laid out as the C struct st_moments -- n, x0, y0, sx, sy,
+        sxx, syy, sxy; n = 0 where skipped -- see as_moments()."""
         if side not in ("a", "b"):
             raise ValueError("side must be 'a' or 'b'")
         T = self._TreeB if side == "b" else self._TreeA
@@ -394,46 +396,53 @@ class SuchLinkedTrees:
         lo_all, hi_all = T._clade_intervals()
         lo = np.ascontiguousarray(lo_all[nodes], dtype=np.int64)
         hi = np.ascontiguousarray(hi_all[nodes], dtype=np.int64)
-        # links under the other side's current subset, in link-table order (by column,
-        # then by the link matrix's row order: _build_linklist's order, :2845-2874)
-        if side == "b":
-            in_a = np.zeros(self._TreeA.size, dtype=bool)
-            in_a[np.asarray(self._subset_a_leafs, dtype=np.int64)] = True
-            keep = in_a[self._link_a]
-        else:
-            in_cols = np.zeros(self._n_cols, dtype=bool)
-            in_cols[np.asarray(self._subset_columns, dtype=np.int64)] = True
-            keep = in_cols[self._link_cols]
-        ll = np.empty((int(keep.sum()), 2), dtype=np.int64)
-        ll[:, 0] = self._col_ids[self._link_cols[keep]]
-        ll[:, 1] = self._link_a[keep]
+        ll = self._links_for_scan(side)
         n = int(nodes.shape[0])
-        moments = (_lib.Moments * max(n, 1))()
+        moments = np.zeros((n, 8), dtype=np.float64)  # rows laid out as st_moments
         n_links = np.zeros(n, dtype=np.int64)
         if n:
             rc = _lib.lib().st_clade_moments(
                 self._TreeA._handle, self._TreeB._handle, ll.ctypes.data, int(ll.shape[0]),
                 0 if side == "b" else 1, lo.ctypes.data, hi.ctypes.data, n, int(min_links),
-                -1 if max_links is None else int(max_links), C.cast(moments, C.c_void_p), n_links.ctypes.data)
+                -1 if max_links is None else int(max_links), moments.ctypes.data, n_links.ctypes.data)
             _lib.check(rc)
         return nodes, (hi - lo) // 2 + 1, n_links, moments
+
+    def _links_for_scan(self, side):
+        """Link rows [TreeB id, TreeA id] under the OTHER side's current subset, in link-table
+        order (by column, then the link matrix's row order: _build_linklist's order,
+        :2845-2874); kept until a subset changes."""
+        key = (side, self._subset_version)
+        if getattr(self, "_scan_links", None) is None or self._scan_links[0] != key:
+            if side == "b":
+                in_a = np.zeros(self._TreeA.size, dtype=bool)
+                in_a[np.asarray(self._subset_a_leafs, dtype=np.int64)] = True
+                keep = in_a[self._link_a]
+            else:
+                in_cols = np.zeros(self._n_cols, dtype=bool)
+                in_cols[np.asarray(self._subset_columns, dtype=np.int64)] = True
+                keep = in_cols[self._link_cols]
+            ll = np.empty((int(keep.sum()), 2), dtype=np.int64)
+            ll[:, 0] = self._col_ids[self._link_cols[keep]]
+            ll[:, 1] = self._link_a[keep]
+            self._scan_links = (key, ll)
+        return self._scan_links[1]
 
     def clade_pearson(self, nodes=None, side="b", min_links=2, max_links=None):
         """Pearson r of (TreeA distance, TreeB distance) over all link pairs of every
         clade: dict of arrays node_ids, n_leafs (subset_b_size), n_links (subset_n_links),
         n_pairs, r (nan where the clade was skipped by min_links / max_links)."""
-        nodes, n_leafs, n_links, moments = self.clade_moments(nodes, side, min_links, max_links)
-        n = int(nodes.shape[0])
-        m = np.frombuffer(moments, dtype=np.float64).reshape(-1, 8)[:n]
-        cnt = m[:, 0]
-        done = cnt > 0
-        r = np.full(n, np.nan)
-        c = np.where(done, cnt, 1.0)
-        cxx = m[:, 5] - m[:, 3] * m[:, 3] / c
-        cyy = m[:, 6] - m[:, 4] * m[:, 4] / c
-        cxy = m[:, 7] - m[:, 3] * m[:, 4] / c
+        nodes, n_leafs, n_links, m = self.clade_moments(nodes, side, min_links, max_links)
+        cnt = np.ascontiguousarray(m[:, 0])
+        done = np.nonzero(cnt > 0)[0]
+        r = np.full(nodes.shape[0], np.nan)
+        md = m[done]  # n, x0, y0, sx, sy, sxx, syy, sxy of the clades that were computed
+        c = md[:, 0]
+        cxx = md[:, 5] - md[:, 3] * md[:, 3] / c
+        cyy = md[:, 6] - md[:, 4] * md[:, 4] / c
+        cxy = md[:, 7] - md[:, 3] * md[:, 4] / c
         with np.errstate(invalid="ignore"):
-            r[done] = (cxy / np.sqrt(cxx * cyy + 1.0e-20))[done]  # st_moments_pearson, MuchTree.pyx:79
+            r[done] = cxy / np.sqrt(cxx * cyy + 1.0e-20)  # st_moments_pearson, MuchTree.pyx:79
         return {"node_ids": nodes, "n_leafs": n_leafs, "n_links": n_links,
                 "n_pairs": cnt.astype(np.int64), "r": r}
 
@@ -441,6 +450,11 @@ class SuchLinkedTrees:
         """Sampled two-tree Pearson r over n_samples link pairs drawn with replacement."""
         m = self.sample_moments(n_samples, seed=seed)
         return moments_pearson(m)
+
+
+def as_moments(row):
+    """One row of clade_moments()'s array as the _lib.Moments struct."""
+    return _lib.Moments(*(float(v) for v in row))
 
 
 def moments_pearson(m):

@@ -9,7 +9,7 @@ import pytest
 from conftest import DATA, GOLDEN
 
 import oracle as O
-from suchtree_b200 import SuchLinkedTrees, SuchTree, moments_pearson, synth
+from suchtree_b200 import SuchLinkedTrees, SuchTree, as_moments, moments_pearson, synth
 
 pytestmark = pytest.mark.gpu
 
@@ -83,11 +83,12 @@ def test_clade_scan_equals_the_products_own_loop(name):
     SLT.subset_b(T2.root_node)
     # moments of the root clade = the exhaustive moments of the whole link list
     _, _, nl, mom = SLT.clade_moments([T2.root_node])
-    assert nl[0] == SLT.n_links
-    assert moments_pearson(mom[0]) == pytest.approx(SLT.linked_pearson(), abs=1e-12)
-    whole = SLT.linked_moments(x0=mom[0].x0, y0=mom[0].y0)
+    assert nl[0] == SLT.n_links and mom.shape == (1, 8)
+    m0 = as_moments(mom[0])
+    assert moments_pearson(m0) == pytest.approx(SLT.linked_pearson(), abs=1e-12)
+    whole = SLT.linked_moments(x0=m0.x0, y0=m0.y0)
     for k in ("n", "sx", "sy", "sxx", "syy", "sxy"):
-        assert getattr(mom[0], k) == pytest.approx(getattr(whole, k), rel=1e-11, abs=1e-9)
+        assert getattr(m0, k) == pytest.approx(getattr(whole, k), rel=1e-11, abs=1e-9)
 
 
 @pytest.mark.parametrize("wide", [False, True])
