@@ -14,7 +14,7 @@ import ctypes as C
 
 import numpy as np
 
-from . import _lib
+from . import _lib, shard
 from .tree import SuchTree
 
 _UINT64_MAX = np.iinfo(np.uint64).max
@@ -428,10 +428,21 @@ class SuchLinkedTrees:
             self._scan_links = (key, ll)
         return self._scan_links[1]
 
-    def clade_pearson(self, nodes=None, side="b", min_links=2, max_links=None):
+    def clade_pearson(self, nodes=None, side="b", min_links=2, max_links=None, rank=None, world=None):
         """Pearson r of (TreeA distance, TreeB distance) over all link pairs of every
         clade: dict of arrays node_ids, n_leafs (subset_b_size), n_links (subset_n_links),
-        n_pairs, r (nan where the clade was skipped by min_links / max_links)."""
+        n_pairs, r (nan where the clade was skipped by min_links / max_links).
+        rank / world (one process per GPU): this rank computes -- and returns the rows of --
+        its share of the clades only, dealt out by link-pair count (shard.balanced_shares);
+        the shares of all ranks partition `nodes`, no collective is involved."""
+        if world is not None and int(world) > 1:
+            # counts only (nothing is eligible with max_links < min_links), then this rank's share
+            nodes, _, n_links, _ = self.clade_moments(nodes, side, 2, 1)
+            ok = n_links >= max(int(min_links), 2)
+            if max_links is not None:
+                ok &= n_links <= int(max_links)
+            weights = np.where(ok, n_links * (n_links - 1.0) * 0.5, 0.0)
+            nodes = nodes[shard.balanced_shares(weights, int(world))[int(rank)]]
         nodes, n_leafs, n_links, m = self.clade_moments(nodes, side, min_links, max_links)
         cnt = np.ascontiguousarray(m[:, 0])
         done = np.nonzero(cnt > 0)[0]

@@ -4,6 +4,7 @@ The index is replicated; work is partitioned with no data-path collective:
   * distances : contiguous ranges of the pair stream        -> pair_range()
   * matrix    : contiguous row blocks                        -> row_block()
   * sampler   : disjoint Philox sample ranges                -> pair_range()
+  * clade scan: clades dealt out by link-pair count           -> balanced_shares()
 The only exchange is the sampler's moment all-reduce (5 sums + n, fp64): NCCL over
 NVLink on GPUs, gloo in the CPU tests.
 """
@@ -25,6 +26,21 @@ def row_block(rank, world, n_rows, tile=64):
     per += (-per) % tile
     b = min(rank * per, n_rows)
     return b, min(b + per, n_rows)
+
+
+def balanced_shares(weights, world):
+    """Indices of the items each rank takes so that the summed weights come out close:
+    items sorted by weight (descending, ties by index) and dealt out boustrophedon
+    (0..world-1, world-1..0, ...).  Deterministic; every index appears exactly once; each
+    share is returned in ascending index order."""
+    import numpy as np
+
+    w = np.asarray(weights, dtype=np.float64)
+    order = np.lexsort((np.arange(w.shape[0]), -w))
+    pos = np.arange(w.shape[0])
+    lap, k = np.divmod(pos, world)
+    owner = np.where(lap % 2 == 0, k, world - 1 - k)
+    return [np.sort(order[owner == r]) for r in range(world)]
 
 
 def allreduce_moments(m, group=None, device=None):

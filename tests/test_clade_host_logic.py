@@ -153,3 +153,24 @@ def test_clade_intervals_on_deep_and_wide_trees():
             assert np.all(depth[lo[v]:hi[v] + 1][np.arange(lo[v], hi[v] + 1) != v] > depth[v])
             assert lo[v] == 0 or depth[lo[v] - 1] <= depth[v]
             assert hi[v] == ft.size - 1 or depth[hi[v] + 1] <= depth[v]
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_clade_scan_shares_partition_the_clades(slt, world):
+    """rank / world: every clade is computed by exactly one rank, with the same result as the
+    unsharded scan; the link-pair counts of the shares are close."""
+    S, T1, T2, fake = slt("fishworm")
+    whole = S.clade_pearson(min_links=4, max_links=150)
+    seen, loads = [], []
+    for rank in range(world):
+        part = S.clade_pearson(min_links=4, max_links=150, rank=rank, world=world)
+        idx = np.searchsorted(whole["node_ids"], part["node_ids"])
+        assert np.array_equal(whole["node_ids"][idx], part["node_ids"])
+        for k in ("n_leafs", "n_links", "n_pairs"):
+            assert np.array_equal(whole[k][idx], part[k])
+        assert np.array_equal(whole["r"][idx], part["r"], equal_nan=True)
+        seen.append(part["node_ids"])
+        loads.append(int(part["n_pairs"].sum()))
+    assert np.array_equal(np.sort(np.concatenate(seen)), whole["node_ids"])
+    assert sum(loads) == int(whole["n_pairs"].sum())
+    assert max(loads) - min(loads) <= int(whole["n_pairs"].max())

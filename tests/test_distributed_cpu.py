@@ -70,3 +70,18 @@ def test_shards_partition_the_work(world, n):
         for (b0, e0), (b1, e1) in zip(edges, edges[1:]):
             assert e0 == b1 and b0 <= e0
         assert all(b % 2 == 0 or b == n for b, _ in edges) or fn is shard.row_block
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_balanced_shares(world):
+    rng = np.random.default_rng(world)
+    for n in (0, 1, 5, 1000):
+        w = rng.integers(0, 50, n).astype(np.float64) ** 2
+        shares = shard.balanced_shares(w, world)
+        assert len(shares) == world
+        assert np.array_equal(np.sort(np.concatenate(shares)) if n else np.concatenate(shares), np.arange(n))
+        assert all(np.array_equal(s, np.sort(s)) for s in shares)
+        loads = [w[s].sum() for s in shares]
+        assert max(loads) - min(loads) <= (w.max() if n else 0)
+        again = shard.balanced_shares(w, world)
+        assert all(np.array_equal(a, b) for a, b in zip(shares, again))
