@@ -10,14 +10,17 @@ tree index is replicated, every rank owns its own 1e8-pair shard of the Philox
 pair stream (weak scaling, no data-path collective).  A step = ONE launch of the
 pair kernel over the rank's device-resident pairs.  `value` = pairs all ranks
 processed / max-over-ranks device time (CUDA events on the launching stream).
-`e2e` = the same metric through the drop-in call SuchTree.distances_bulk() on
-PINNED HOST int64 pairs (H2D + kernel + D2H inside the timed region).
+`e2e` = the same metric through the drop-in call with the REFERENCE'S signature:
+r = SuchTree.distances_bulk(pairs), pairs an ordinary (pageable) numpy int64 (n,2)
+array, r a fresh float64 array (H2D + kernel + D2H inside the timed region), with
+`e2e.roofline` = a concurrent pinned H2D + D2H copy of the same byte counts measured
+in the same run (all ranks at once for N>1).
 Rank 0 at N=1 also times the unmodified reference (oracle/_ref, its own Cython
 machine code) on a bounded sample of the same pairs -> `cpu_baseline`.
 
 Reference arm (--impl reference): the unmodified reference's distances_bulk() on
 the box's host cores (fork pool over contiguous pair blocks, the decomposition the
-reference's docs recommend), each step a bounded sample of the same workload.
+reference's docs recommend), every step the FULL 1e8-pair step of our arm.
 """
 import argparse
 import json
@@ -64,12 +67,15 @@ def host_cores():
 # --------------------------------------------------------------------------- #
 _REF_TREE = None
 _REF_PAIRS = None
+_REF_OUT = None
 
 
 def _ref_worker(span):
-    # the pair array and the tree are inherited through fork (copy-on-write), as in
-    # the multiprocessing recipe of the reference's docs; only results travel back
-    return _REF_TREE.distances_bulk(_REF_PAIRS[span[0]:span[1]])
+    # the pair array, the tree and the result array are inherited through fork (the result
+    # array is shared anonymous memory): only the span travels, as cheap as it can be made
+    # for the reference -- its own recipe returns the results through the pool's pipes
+    _REF_OUT[span[0]:span[1]] = _REF_TREE.distances_bulk(_REF_PAIRS[span[0]:span[1]])
+    return span[1] - span[0]
 
 
 class ReferenceCPU:
@@ -80,6 +86,7 @@ class ReferenceCPU:
         global _REF_TREE
         sys.path.insert(0, os.path.join(REPO, "oracle"))
         self.kind = "port"
+        self.pool = None
         mod = None
         try:
             import ref_loader
@@ -117,19 +124,43 @@ class ReferenceCPU:
             t0 = time.perf_counter()
             out = _REF_TREE.distances_bulk(pairs)
             return pairs.shape[0] / (time.perf_counter() - t0), out
+        pool, out = self.open_pool(pairs, cores)
+        try:
+            return pairs.shape[0] / self.run_pool(pairs.shape[0], cores), out.copy()
+        finally:
+            self.close_pool()
+
+    def open_pool(self, pairs, cores):
+        """fork Pool(cores) that sees `pairs` and a shared result array (threads do not
+        scale: the reference holds the GIL in distances_bulk)."""
+        import mmap
         import multiprocessing as mp
 
-        global _REF_PAIRS
+        global _REF_PAIRS, _REF_OUT
         _REF_PAIRS = pairs
-        ctx = mp.get_context("fork")  # threads do not scale: the reference holds the GIL
-        edges = np.linspace(0, pairs.shape[0], cores * 4 + 1).astype(np.int64)
-        spans = list(zip(edges[:-1], edges[1:]))
-        with ctx.Pool(cores) as pool:
-            pool.map(_ref_worker, [(0, 1000)] * cores)  # warm the workers
-            t0 = time.perf_counter()
-            res = pool.map(_ref_worker, spans)
-            dt = time.perf_counter() - t0
-        return pairs.shape[0] / dt, np.concatenate(res)
+        self._shm = mmap.mmap(-1, max(8, 8 * pairs.shape[0]))  # MAP_SHARED | MAP_ANONYMOUS: survives fork
+        _REF_OUT = np.frombuffer(self._shm, dtype=np.float64, count=pairs.shape[0])
+        self.pool = mp.get_context("fork").Pool(cores)
+        self.pool.map(_ref_worker, [(0, min(1000, pairs.shape[0]))] * cores)  # warm the workers
+        return self.pool, _REF_OUT
+
+    def run_pool(self, n, cores):
+        """seconds for one pass over the n pairs given to open_pool()"""
+        edges = np.linspace(0, n, cores * 4 + 1).astype(np.int64)
+        spans = list(zip(edges[:-1].tolist(), edges[1:].tolist()))
+        t0 = time.perf_counter()
+        done = sum(self.pool.map(_ref_worker, spans))
+        dt = time.perf_counter() - t0
+        assert done == n
+        return dt
+
+    def close_pool(self):
+        global _REF_PAIRS, _REF_OUT
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
+            self.pool = None
+        _REF_PAIRS = _REF_OUT = None
 
 
 def sample_pairs_host(n_leaves, seed, first, n):
@@ -149,18 +180,21 @@ def run_reference_arm(args):
     ft = synth.yule_tree(TREE_LEAVES, seed=TREE_SEED)
     ref = ReferenceCPU(ft)
     cores = host_cores()
-    # calibrate a bounded per-step sample: ~3 s of all-core work per step
     probe = sample_pairs_host(TREE_LEAVES, PAIR_SEED, 0, 200_000)
     rate1, _ = ref.run(probe, 1)
-    per_step = int(min(30_000_000, max(200_000, rate1 * cores * 0.6 * 3.0)))
-    per_step -= per_step % 2
+    # the same step as our arm: rank 0's 1e8 pairs of the Philox stream (all of them, every step)
+    per_step = args.pairs - args.pairs % 2
     pairs = sample_pairs_host(TREE_LEAVES, PAIR_SEED, 0, per_step)
-    for _ in range(max(args.warmup, 0) and 1):
-        ref.run(pairs[: per_step // 4], cores)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ref.run(pairs, cores)
-    dt = time.perf_counter() - t0
+    ref.open_pool(pairs, cores)
+    try:
+        for _ in range(min(max(args.warmup, 0), 1)):  # one warm pass is plenty for a CPU loop
+            ref.run_pool(per_step, cores)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ref.run_pool(per_step, cores)
+        dt = time.perf_counter() - t0
+    finally:
+        ref.close_pool()
     value = per_step * args.steps / dt
     line = {
         "impl": "reference",
@@ -177,10 +211,11 @@ def run_reference_arm(args):
         "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "tree_leaves": TREE_LEAVES, "pairs_per_step": per_step,
-                   "note": "bounded sample of the 1e8-pair step; pool start-up outside the rate"},
+                   "note": "the full step of our arm at N=1 (the CPU arm does not grow with --gpus); pool "
+                           "start-up outside the rate; results written to shared memory by the workers"},
         "cpu_baseline": {
             "value": value, "unit": UNIT, "cores": cores, "kind": ref.kind, "cpu_model": cpu_model(),
-            "sample": "%d pairs/step x %d steps of the cfg2 pair stream, fork Pool(%d) over "
+            "sample": "%d pairs/step x %d steps of the cfg2 pair stream (the whole step), fork Pool(%d) over "
                       "contiguous blocks; single core: %.3g pairs/s" % (per_step, args.steps, cores, rate1),
         },
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -379,24 +414,78 @@ def run_ours(args):
         host_pairs = pairs[: sample.shape[0]].cpu().numpy().astype(np.int64)
         parity = parity and bool(np.array_equal(host_pairs, sample))
 
-    # ---- e2e: the drop-in call on pinned host buffers
+    # ---- e2e: the drop-in call with the reference's own signature (MuchTree.pyx:872-909):
+    #      an ordinary pageable numpy int64 (n,2) array in, a FRESH float64 array out
+    import ctypes as C
+
     n_e2e = min(n_pairs, args.e2e_pairs)
-    h_pairs = torch.empty((n_e2e, 2), dtype=torch.int64).pin_memory()
-    h_pairs.copy_(pairs[:n_e2e].to(torch.int64))
-    h_out = torch.empty(n_e2e, dtype=torch.float64).pin_memory()
-    np_pairs, np_out = h_pairs.numpy(), h_out.numpy()
-    T.distances_bulk(np_pairs, out=np_out)  # warm-up: staging buffers
+    np_pairs = pairs[:n_e2e].cpu().numpy().astype(np.int64)  # pageable host memory, C-contiguous
+    assert np_pairs.flags.owndata and not _lib.lib().st_host_is_pinned(np_pairs.ctypes.data)
+    t0 = time.perf_counter()
+    r = T.distances_bulk(np_pairs)  # cold call: result pool and (maybe) staging are allocated here
+    e2e_first_s = time.perf_counter() - t0
+    e2e_ok = bool(torch.equal(torch.from_numpy(r).to(dev), out[:n_e2e]))
+    for _ in range(max(args.warmup, 3) - 1):
+        r = T.distances_bulk(np_pairs)
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 5))
-    for _ in range(e2e_steps):
-        T.distances_bulk(np_pairs, out=np_out)
+    for _ in range(args.steps):
+        r = T.distances_bulk(np_pairs)
     dt = time.perf_counter() - t0
-    te = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * n_e2e * e2e_steps / float(te.item())
-    e2e_ok = bool(torch.equal(h_out.to(dev), out[:n_e2e]))
+    e2e_ok = e2e_ok and bool(torch.equal(torch.from_numpy(r).to(dev), out[:n_e2e]))
+    in_registered = bool(_lib.lib().st_host_is_pinned(np_pairs.ctypes.data))
+
+    def all_max(x):
+        t_ = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        return float(t_.item())
+
+    e2e_value = world * n_e2e * args.steps / all_max(dt)
+
+    # variants, a few calls each (not the headline): (a) inputs never page-locked -- what a caller
+    # that hands in a NEW array every call gets; (b) round 1's extension: pinned in, pinned out=
+    variants = {}
+    reps = max(3, min(args.steps, 5))
+    os.environ["SUCHTREE_B200_REGISTER"] = "0"
+    np_pairs2 = np_pairs.copy()
+    r = T.distances_bulk(np_pairs2)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        r = T.distances_bulk(np_pairs2)
+    variants["pageable_in_never_registered"] = world * n_e2e * reps / all_max(time.perf_counter() - t0)
+    del os.environ["SUCHTREE_B200_REGISTER"]
+    del np_pairs2
+    h_pairs = torch.empty((n_e2e, 2), dtype=torch.int64).pin_memory()
+    h_pairs.copy_(torch.from_numpy(np_pairs))
+    h_out = torch.empty(n_e2e, dtype=torch.float64).pin_memory()
+    T.distances_bulk(h_pairs.numpy(), out=h_out.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        T.distances_bulk(h_pairs.numpy(), out=h_out.numpy())
+    variants["pinned_in_pinned_out_kwarg"] = world * n_e2e * reps / all_max(time.perf_counter() - t0)
+    del h_pairs, h_out, r
+
+    # the roofline of that call: what the host interface carries when NOTHING else happens --
+    # a pinned H2D copy of 16 B/pair and a concurrent pinned D2H copy of 8 B/pair, same chunking,
+    # all ranks at the same time (the ranks of one box share the host's memory system)
+    sec = C.c_double(0)
+    barrier()
+    rc_copy = _lib.lib().st_bench_copy(local, 16 * n_e2e, 8 * n_e2e, 64 << 20, 5, C.byref(sec))
+    copy_s = all_max(sec.value if rc_copy == 0 else float("nan"))
+    copy_pairs_per_s = world * n_e2e / copy_s
+    e2e_roofline = {
+        "bound": "host interface (PCIe Gen5 x16 per GPU; the host memory system when several ranks share it)",
+        "what": "cudaMemcpyAsync pinned H2D of 16 B/pair || pinned D2H of 8 B/pair, 64 MiB chunks, two streams, "
+                "%d rank(s) concurrently, measured in this run by st_bench_copy" % world,
+        "achieved": 24.0 * e2e_value / 1e9, "peak": 24.0 * copy_pairs_per_s / 1e9, "unit": "GB/s",
+        "frac": e2e_value / copy_pairs_per_s,
+        "peak_pairs_per_s": copy_pairs_per_s, "algorithmic_bytes_per_pair": 24,
+        "note": "frac can exceed 1: the pipeline packs 45 % of the ids to int32 on the host, so fewer bytes "
+                "cross PCIe than the plain copy moves",
+    }
 
     # ---- rooflines (rank 0's kernel; all ranks run the same launch)
     peak, peak_src = measured_peak()
@@ -404,10 +493,8 @@ def run_ours(args):
     achieved = 16.0 * n_pairs / per_launch_s / 1e9
     gather = None
     if rank == 0:
-        import ctypes as C
-
         sps = C.c_double(0)
-        rc = _lib.lib().st_bench_gather(local, int(T.index_info["index_bytes"]), 64, 5, C.byref(sps))
+        rc = _lib.bench_lib().st_bench_gather(local, int(T.index_info["index_bytes"]), 64, 5, C.byref(sps))
         if rc == 0:
             gather = {
                 "what": "random 32-byte-sector gathers over an index-sized buffer (%d bytes), measured by "
@@ -450,15 +537,22 @@ def run_ours(args):
         "cpu_baseline": cpu_baseline,
         "e2e": {
             "value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n_e2e, "d2h_bytes_per_step": 8 * n_e2e,
-            "pairs_per_step_per_gpu": n_e2e, "steps": e2e_steps, "matches_device_path": e2e_ok,
-            "call": "SuchTree.distances_bulk(int64 (n,2) pinned host array, out=pinned float64)",
+            "pairs_per_step_per_gpu": n_e2e, "steps": args.steps, "matches_device_path": e2e_ok,
+            "call": "r = SuchTree.distances_bulk(pairs): pairs = ordinary numpy int64 (n,2) array (the same "
+                    "array every step), r = fresh numpy float64 (n,) -- the reference's signature, "
+                    "MuchTree.pyx:872-909",
+            "input_registered_in_place": in_registered,
+            "first_call_s": e2e_first_s,
+            "roofline": e2e_roofline,
+            "variants_pairs_per_s": variants,
         },
         "gpu_launches": args.steps,
         "clocks": clocks,
         "parity_vs_reference_sample": parity,
     }
     if not args.no_other_workloads:
-        del pairs, out, h_pairs, h_out
+        del pairs, out, np_pairs
+        _lib.lib().st_host_trim(0)
         torch.cuda.empty_cache()
         try:
             line["other_workloads"] = run_other_workloads(args, rank, world, local, dev, peak)
@@ -489,6 +583,63 @@ def _timed(stream, fn, steps, warmup=3):
     e1.record(stream)
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) * 1e-3 / steps
+
+
+def cfg5_parity_vs_oracle(ft, T, block, n, n_shards, mat, dev):
+    """The cfg5 matrix against the oracle at full size (1e6 sampled elements +
+    row checksums).  Every row shard of the 8-GPU plan is computed into `block` in turn."""
+    import torch
+
+    from suchtree_b200 import shard
+
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import oracle as O
+
+    ot = O.OracleTree(ft.parent, ft.distance)
+    rng = np.random.default_rng(55)
+    TR, TC = 64, 512  # the writer's tile (st_matrix.cu)
+    n_checked = 0
+    bad = 0
+    rows_checked = 0
+    row_bad = 0
+    for sh in range(n_shards):
+        r0, r1 = shard.row_block(sh, n_shards, n)
+        if r1 <= r0:
+            continue
+        mat(r0, r1)
+        torch.cuda.synchronize()
+        rows = r1 - r0
+        k = 1_000_000 // n_shards
+        ri = [rng.integers(0, rows, k - 6000)]
+        ci = [rng.integers(0, n, k - 6000)]
+        # elements of the tiles ON the diagonal and just off it on both sides
+        d = rng.integers(0, rows, 3000)
+        off = rng.integers(-TC, TC + 1, 3000)
+        ri.append(d)
+        ci.append(np.clip(r0 + d + off, 0, n - 1))
+        # the last (partial) tile column and the shard's first / last tile rows
+        e = rng.integers(0, rows, 1500)
+        ri.append(e)
+        ci.append(rng.integers((n - 1) // TC * TC, n, 1500))
+        f = np.concatenate([rng.integers(0, min(TR, rows), 750), rng.integers(max(rows - TR, 0), rows, 750)])
+        ri.append(f)
+        ci.append(rng.integers(0, n, 1500))
+        ri, ci = np.concatenate(ri), np.concatenate(ci)
+        got = block[torch.from_numpy(ri).to(dev), torch.from_numpy(ci).to(dev)].cpu().numpy()
+        want = ot.distances_f64_climb(np.stack([2 * (r0 + ri), 2 * ci], axis=1).astype(np.int64))
+        bad += int(np.count_nonzero(got != want))
+        n_checked += int(ri.shape[0])
+        # whole rows: every element and the row sum (first, last and two random rows of the shard)
+        for rr in sorted({0, rows - 1, int(rng.integers(0, rows)), int(rng.integers(0, rows))}):
+            row = block[rr].cpu().numpy()
+            p = np.stack([np.full(n, 2 * (r0 + rr)), 2 * np.arange(n)], axis=1).astype(np.int64)
+            w = ot.distances_f64_climb(p)
+            rows_checked += 1
+            if not (np.array_equal(row, w) and float(row.sum()) == float(w.sum())):
+                row_bad += 1
+    return {"oracle": "O2 (oracle/st_oracle.c: fp64 path sums over the fp32-quantised edges, climbing MRCA)",
+            "shards": n_shards, "sampled_elements": n_checked, "sampled_mismatches": bad,
+            "whole_rows": rows_checked, "row_mismatches": row_bad, "bit_exact": bool(bad == 0 and row_bad == 0)}
 
 
 def run_other_workloads(args, rank, world, local, dev, peak):
@@ -570,7 +721,7 @@ def run_other_workloads(args, rank, world, local, dev, peak):
         # gather roofline for an index of this size (random sectors over the same footprint)
         sps = C.c_double(0)
         gfrac = None
-        if _lib.lib().st_bench_gather(local, int(T.index_info["index_bytes"]), 64, 3, C.byref(sps)) == 0 and sps.value > 0:
+        if _lib.bench_lib().st_bench_gather(local, int(T.index_info["index_bytes"]), 64, 3, C.byref(sps)) == 0 and sps.value > 0:
             gfrac = 2.0 * n3 / sec / sps.value
         res["cfg3_" + shape] = {
             "workload": "1M-leaf %s tree (depth %d), %d random leaf pairs per GPU per launch" % (shape, T.depth, n3),
@@ -587,35 +738,57 @@ def run_other_workloads(args, rank, world, local, dev, peak):
     ft = synth.yule_tree(TREE_LEAVES, seed=TREE_SEED)
     T = SuchTree.from_flat(ft, device=local)
     n = TREE_LEAVES
-    rb, re_ = shard.row_block(rank, max(world, 8), n)  # 12,500-row blocks as in the 8-GPU plan
+    n_shards = max(world, 8)  # 12,500-row blocks as in the 8-GPU plan
+    rb, re_ = shard.row_block(rank, n_shards, n)
     block = torch.empty((re_ - rb, n), dtype=torch.float64, device=dev)
-    from suchtree_b200 import _lib
 
-    def mat():
-        _lib.check(_lib.lib().st_distance_matrix(T._handle, None, n, rb, re_, block.data_ptr(), 1, sptr))
+    def mat(r0=rb, r1=re_):
+        _lib.check(_lib.lib().st_distance_matrix(T._handle, None, n, r0, r1, block.data_ptr(), 1, sptr))
 
     sec = max_over_ranks(_timed(stream, mat, steps=10))
     elems = (re_ - rb) * n
-    # spot check against the pair kernel (same index): 4096 random elements of the block
-    g = torch.Generator(device="cpu").manual_seed(11 + rank)
-    ri = torch.randint(0, re_ - rb, (4096,), generator=g)
-    ci = torch.randint(0, n, (4096,), generator=g)
-    chk_pairs = torch.stack([2 * (ri + rb), 2 * ci], dim=1).to(torch.int32).to(dev)
-    chk = torch.empty(4096, dtype=torch.float64, device=dev)
-    T.distances_device(chk_pairs.data_ptr(), 4096, chk.data_ptr(), idx_bits=32, stream=sptr)
-    torch.cuda.synchronize()
-    same = bool(torch.equal(block[ri.to(dev), ci.to(dev)], chk))
     fill_sec = _timed(stream, lambda: block.fill_(1.0), steps=10)  # plain write of the same bytes
     res["cfg5_matrix"] = {
         "workload": "rows [%d,%d) of the 100k x 100k all-leaves fp64 matrix per GPU, device-resident" % (rb, re_),
         "elements_per_s": world * elems / sec, "ms_per_block": sec * 1e3, "bytes_written_per_gpu": 8 * elems,
-        "hbm_frac": 8.0 * elems / sec / 1e9 / peak, "matches_pair_kernel_on_4096_samples": same,
+        "hbm_frac": 8.0 * elems / sec / 1e9 / peak,
         "plain_fill_gbs": 8.0 * elems / fill_sec / 1e9, "frac_of_plain_fill": fill_sec / sec,
     }
+    # full-size parity against the oracle (the checker; rank 0, N=1, beside the cpu_baseline leg):
+    # every one of the 8 row shards is computed in turn; 1e6 sampled elements in all -- drawn
+    # uniformly, plus the diagonal tiles, both triangle sides next to the diagonal, the last
+    # (partial) tile column / row -- and whole-row checksums, against O2 (fp64 path sums over the
+    # fp32-quantised edges, the climbing-MRCA restatement), bit for bit.
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        res["cfg5_matrix"]["parity_vs_oracle"] = cfg5_parity_vs_oracle(ft, T, block, n, n_shards, mat, dev)
     del block
     torch.cuda.empty_cache()
 
-    # ---- cfg4: sampled two-tree correlation, moments via NCCL
+    # ---- the drop-in call itself, to the host: pairwise_distances() over 20,000 leaves (3.2 GB),
+    #      about the most the reference's own implementation (n(n-1)/2 Python tuples) can attempt
+    if rank == 0:
+        nodes = list(range(0, 40_000, 2))
+        t0 = time.perf_counter()
+        D = T.pairwise_distances(nodes)  # cold: the pinned result block is allocated here
+        cold = time.perf_counter() - t0
+        del D
+        t0 = time.perf_counter()
+        D = T.pairwise_distances(nodes)
+        warm = time.perf_counter() - t0
+        sym = bool(np.array_equal(D[:64, :], D[:, :64].T)) and bool(np.all(np.diagonal(D) == 0.0))
+        chk = T.distances_bulk(np.array([[nodes[17], nodes[19_999]], [nodes[12_345], nodes[6_789]]], dtype=np.int64))
+        res["pairwise_distances_host_20k"] = {
+            "workload": "SuchTree.pairwise_distances(20,000 leaf ids) -> fresh (20000,20000) float64 numpy array "
+                        "(3.2 GB) in host memory",
+            "s_first_call": cold, "s_per_call": warm, "elements_per_s": 4e8 / warm, "d2h_gbs": 3.2 / warm,
+            "symmetric_zero_diagonal": sym,
+            "matches_distances_bulk": bool(D[17, 19_999] == chk[0] and D[12_345, 6_789] == chk[1]),
+        }
+        del D
+        _lib.lib().st_host_trim(0)
+
+    # ---- cfg4: sampled two-tree correlation; the six moment sums are all-reduced by NCCL on the
+    #      kernel's stream INSIDE the timed call (st_links_sample_moments(..., nccl_comm))
     fa, fb = synth.yule_tree(TREE_LEAVES, seed=4, names=True), synth.yule_tree(TREE_LEAVES, seed=5, names=True)
     TA, TB = SuchTree.from_flat(fa, device=local), SuchTree.from_flat(fb, device=local)
     rng = np.random.default_rng(6)
@@ -623,42 +796,64 @@ def run_other_workloads(args, rank, world, local, dev, peak):
     lb = 2 * rng.integers(0, TREE_LEAVES, TREE_LEAVES)
     linklist = np.ascontiguousarray(np.stack([lb, la], axis=1).astype(np.int64))
     n4 = args.cfg4_samples
-    from suchtree_b200 import _lib as L_
+    L_ = _lib
+    links = C.c_void_p()
+    L_.check(L_.lib().st_links_create(TA._handle, TB._handle, linklist.ctypes.data, linklist.shape[0], C.byref(links)))
+    comm = shard.MomentComm(local) if world > 1 else None
+    comm_h = comm.handle if comm is not None else None
 
-    import ctypes as C
-
-    def sample():
+    def sample(first=rank * n4, count=n4, c=comm_h):
         m = L_.Moments()
-        L_.check(L_.lib().st_sample_moments(TA._handle, TB._handle, linklist.ctypes.data, linklist.shape[0], 7,
-                                            rank * n4, n4, 0.0, 0.0, C.byref(m)))
+        L_.check(L_.lib().st_links_sample_moments(links, 7, first, count, 0.0, 0.0, c, C.byref(m)))
         return m
 
-    sample()
+    for _ in range(3):
+        sample()
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     reps = 10
     for _ in range(reps):
         m = sample()
     sec = max_over_ranks((time.perf_counter() - t0) / reps)
-    m = shard.allreduce_moments(m, device=dev)
-    res["cfg4_pearson_sampler"] = {
-        "workload": "two 100k-leaf Yule trees (seeds 4,5), 100k random links (seed 6), %d Philox-sampled "
-                    "link pairs per GPU per call, 5 moments all-reduced (NCCL)" % n4,
-        "samples_per_s": world * n4 / sec, "ms_per_call": sec * 1e3, "pearson_r": moments_pearson(m),
-        "timing": "host wall clock around the blocking C-ABI call (includes link upload + moment read-back)",
+    r_all = moments_pearson(m)
+    entry = {
+        "workload": "two 100k-leaf Yule trees (seeds 4,5), 100k random links (seed 6), %d Philox-sampled link "
+                    "pairs per GPU per call; %s" % (
+                        n4, "moments all-reduced by ncclAllReduce(sum, fp64, 6) on the kernel's stream inside "
+                            "every timed call" if world > 1 else "one GPU: no collective"),
+        "samples_per_s": world * n4 / sec, "ms_per_call": sec * 1e3, "pearson_r": r_all, "samples_in_r": m.n,
+        "timing": "host wall clock around the blocking C-ABI call (kernel + fold + all-reduce + 48-byte read-back); "
+                  "the link list is device-resident (st_links handle)",
     }
+    if world > 1:
+        # the all-reduced r must equal ONE GPU's r over the union of all ranks' sample ranges
+        m1 = sample(0, world * n4, None)
+        r_one = moments_pearson(m1)
+        entry["allreduce_check"] = {
+            "r_allreduced": r_all, "r_one_gpu_union_range": r_one, "abs_diff": abs(r_all - r_one),
+            "ok_1e-12": bool(abs(r_all - r_one) <= 1e-12 and m.n == m1.n),
+        }
+        # what the collective costs: the same call without it
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            sample(c=None)
+        entry["ms_per_call_without_allreduce"] = max_over_ranks((time.perf_counter() - t0) / reps) * 1e3
+    res["cfg4_pearson_sampler"] = entry
     # ---- exhaustive link pairs, fused moments (linked_distances + pearson in one pass):
     #      44,904 links as in the reference's bigtrees example -> 1.008e9 link pairs,
     #      one eighth of the pair range per GPU
     L = 44_904
     ll2 = np.ascontiguousarray(linklist[:L])
+    links2 = C.c_void_p()
+    L_.check(L_.lib().st_links_create(TA._handle, TB._handle, ll2.ctypes.data, L, C.byref(links2)))
     total = L * (L - 1) // 2
     pb, pe = shard.pair_range(rank, max(world, 8), total)
 
     def exhaustive():
         m = L_.Moments()
-        L_.check(L_.lib().st_linked_moments(TA._handle, TB._handle, ll2.ctypes.data, L, pb, pe - pb, 0.0, 0.0,
-                                            C.byref(m)))
+        L_.check(L_.lib().st_links_linked_moments(links2, pb, pe - pb, 0.0, 0.0, comm_h, C.byref(m)))
         return m
 
     exhaustive()
@@ -668,10 +863,15 @@ def run_other_workloads(args, rank, world, local, dev, peak):
         m2 = exhaustive()
     sec = max_over_ranks((time.perf_counter() - t0) / reps)
     res["linked_exhaustive_moments"] = {
-        "workload": "44,904 links (1.008e9 link pairs): pairs [%d,%d) per GPU, both trees, moments fused" % (pb, pe),
+        "workload": "44,904 links (1.008e9 link pairs): pairs [%d,%d) per GPU, both trees, moments fused%s" % (
+            pb, pe, ", all-reduced inside the call" if world > 1 else ""),
         "link_pairs_per_s": world * (pe - pb) / sec, "ms_per_call": sec * 1e3,
         "timing": "host wall clock around the blocking C-ABI call",
     }
+    L_.lib().st_links_destroy(links)
+    L_.lib().st_links_destroy(links2)
+    if comm is not None:
+        comm.close()
     del TA, TB
 
     # ---- the drop-in sampler API on the shape of the reference's published example

@@ -68,6 +68,9 @@ typedef struct st_tree_info {
 /* thread-local text of the last error raised on this thread ("" if none) */
 ST_API const char *st_last_error(void);
 ST_API int st_version(void);
+/* hash of the CUDA sources this binary was compiled from (suchtree_b200/build.py); the
+ * Python loader compares it with the sources on disk and rebuilds a stale library */
+ST_API const char *st_build_id(void);
 ST_API int st_device_count(int *count);
 
 /* ---- tree: replaces `cdef struct Node` + SuchTree.__init__'s fill/depth passes
@@ -242,14 +245,64 @@ ST_API double st_moments_pearson(const st_moments *m);
 /* ---- pearson(): replaces _pearson (MuchTree.pyx:62-79); x, y HOST double[n]. */
 ST_API int st_pearson(int device, const double *x, const double *y, int64_t n, double *r);
 
-/* ---- measurement helper: random 32-byte-sector gather bandwidth over a
- * `bytes`-sized device buffer (the L2-gather roofline of SURVEY.md §8d). */
-ST_API int st_bench_gather(int device, int64_t bytes, int64_t loads_per_thread, int iters,
-                    double *sectors_per_s);
-
 /* ---- measurement helper: rate (pairs/s) at which the host thread pool packs int64
  * id pairs into int32 pinned staging -- the host stage of st_distances(). */
 ST_API int st_bench_pack(int64_t n_pairs, int iters, double *pairs_per_s);
+
+/* ---- measurement helper: what the host interface can carry -- `iters` rounds of an H2D copy
+ * of h2d_bytes and a concurrent D2H copy of d2h_bytes between pinned host memory and the
+ * device, in chunks of chunk_bytes (<= 0: 64 MiB) on two streams; *seconds = wall time per
+ * round.  The roofline of st_distances(): 16 B/pair in, 8 B/pair out. */
+ST_API int st_bench_copy(int device, int64_t h2d_bytes, int64_t d2h_bytes, int64_t chunk_bytes, int iters,
+                  double *seconds);
+
+/* ---- page-locked host memory for results: SuchTree.distances_bulk returns a FRESH array
+ *      (MuchTree.pyx:907 `result = np.zeros(...)`); the shim takes it from this pool so that
+ * the D2H copies of st_distances() / st_distance_matrix() land in it directly instead of in
+ * staging + a host copy.  Freed blocks are cached (SUCHTREE_B200_PINNED_CACHE_MB, default
+ * 4096) and recycled by later calls of the same size class. */
+ST_API int st_host_alloc(int64_t bytes, void **out);
+ST_API int st_host_free(void *p);
+ST_API int st_host_trim(int64_t keep_bytes); /* drop cached blocks down to keep_bytes */
+/* page-lock / unlock a caller-owned array in place (cudaHostRegister): the host pipeline
+ * then DMAs straight out of it.  The shim registers large inputs it sees repeatedly and
+ * unregisters them when the array is garbage-collected. */
+ST_API int st_host_register(const void *p, int64_t bytes);
+ST_API int st_host_unregister(const void *p);
+ST_API int st_host_is_pinned(const void *p);
+
+/* ---- link-list handle: the device-resident form of SuchLinkedTrees.linklist
+ *      (MuchTree.pyx:2839-2874), built once and reused by every call below (the entry points
+ * above that take the raw `linklist` build one per call).  Both trees must outlive it. */
+typedef struct st_links st_links;
+ST_API int st_links_create(const st_tree *tree_a, const st_tree *tree_b, const int64_t *linklist,
+                    int64_t n_links, st_links **out);
+ST_API void st_links_destroy(st_links *links);
+/* = st_linked_distances / st_sample_linked_cycle on the handle */
+ST_API int st_links_linked_distances(const st_links *links, double *out_a, double *out_b, int64_t *ids_a,
+                              int64_t *ids_b);
+ST_API int st_links_sample_cycle(const st_links *links, uint64_t *seed, int32_t buckets, int32_t n,
+                          double *out_a, double *out_b, double *sums_a, double *sumsq_a,
+                          double *sums_b, double *sumsq_b);
+/* = st_sample_moments / st_linked_moments on the handle, plus the path's ONE collective:
+ * nccl_comm != NULL (an ncclComm_t, e.g. from st_nccl_comm_create) -> the six sums
+ * {n, sx, sy, sxx, syy, sxy} are all-reduced (ncclAllReduce, sum, fp64, in place) on the
+ * stream the moment kernel ran on, before the one device->host read; every rank of the
+ * communicator must make the call, with the same x0, y0.  *out then holds the moments of
+ * the union of all ranks' samples / pairs. */
+ST_API int st_links_sample_moments(const st_links *links, uint64_t seed, int64_t first_sample,
+                            int64_t n_samples, double x0, double y0, void *nccl_comm, st_moments *out);
+ST_API int st_links_linked_moments(const st_links *links, int64_t first_pair, int64_t n_pairs, double x0,
+                            double y0, void *nccl_comm, st_moments *out);
+
+/* ---- NCCL plumbing for the moment all-reduce (libnccl.so.2 is dlopen'ed on first use; a
+ *      single-GPU process never loads it).  id128: 128 bytes (ncclUniqueId) produced on one
+ * rank by st_nccl_unique_id and handed to the others by whatever rendezvous the host has
+ * (torch.distributed broadcast, MPI, a file).  *comm is an ncclComm_t. */
+ST_API int st_nccl_version(int *version);
+ST_API int st_nccl_unique_id(void *id128);
+ST_API int st_nccl_comm_create(int device, int world, int rank, const void *id128, void **comm);
+ST_API int st_nccl_comm_destroy(void *comm);
 
 #ifdef __cplusplus
 }

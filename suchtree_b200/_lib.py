@@ -50,6 +50,7 @@ _vp, _i64, _i32, _u64, _int = C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_
 SIGNATURES = {
     "st_last_error": (C.c_char_p, []),
     "st_version": (_int, []),
+    "st_build_id": (C.c_char_p, []),
     "st_device_count": (_int, [C.POINTER(_int)]),
     "st_tree_create": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _int, _int, C.POINTER(_vp)]),
     "st_tree_create_ex": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _int, _int, _int, C.POINTER(_vp)]),
@@ -81,28 +82,73 @@ SIGNATURES = {
     "st_moments_pearson": (C.c_double, [C.POINTER(Moments)]),
     "st_pearson": (_int, [_int, _vp, _vp, _i64, C.POINTER(C.c_double)]),
     "st_bench_pack": (_int, [_i64, _int, C.POINTER(C.c_double)]),
-    "st_bench_gather": (_int, [_int, _i64, _i64, _int, C.POINTER(C.c_double)]),
+    "st_bench_copy": (_int, [_int, _i64, _i64, _i64, _int, C.POINTER(C.c_double)]),
+    "st_host_alloc": (_int, [_i64, C.POINTER(_vp)]),
+    "st_host_free": (_int, [_vp]),
+    "st_host_trim": (_int, [_i64]),
+    "st_host_register": (_int, [_vp, _i64]),
+    "st_host_unregister": (_int, [_vp]),
+    "st_host_is_pinned": (_int, [_vp]),
+    "st_links_create": (_int, [_vp, _vp, _vp, _i64, C.POINTER(_vp)]),
+    "st_links_destroy": (None, [_vp]),
+    "st_links_linked_distances": (_int, [_vp, _vp, _vp, _vp, _vp]),
+    "st_links_sample_cycle": (_int, [_vp, C.POINTER(_u64), _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "st_links_sample_moments": (
+        _int, [_vp, _u64, _i64, _i64, C.c_double, C.c_double, _vp, C.POINTER(Moments)]),
+    "st_links_linked_moments": (
+        _int, [_vp, _i64, _i64, C.c_double, C.c_double, _vp, C.POINTER(Moments)]),
+    "st_nccl_version": (_int, [C.POINTER(_int)]),
+    "st_nccl_unique_id": (_int, [_vp]),
+    "st_nccl_comm_create": (_int, [_int, _int, _int, _vp, C.POINTER(_vp)]),
+    "st_nccl_comm_destroy": (_int, [_vp]),
 }
+
+# the bench-only library (include/suchtree_b200_bench.h): measurement tooling, not product
+BENCH_SIGNATURES = {
+    "st_bench_gather": (_int, [_int, _i64, _i64, _int, C.POINTER(C.c_double)]),
+    "st_bench_last_error": (C.c_char_p, []),
+}
+_bench_lib = None
+
+
+def _bind(L, signatures):
+    for name, (res, args) in signatures.items():
+        fn = getattr(L, name)  # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    return L
 
 
 def lib():
-    """Load (building first if needed) the CUDA library.  Raises if impossible."""
+    """Load (building first if needed) the CUDA library.  Raises if impossible.
+    A library whose embedded source hash (st_build_id) differs from the sources on
+    disk is stale: it is rebuilt before loading, never silently used."""
     global _lib
     if _lib is None:
         with _lock:
             if _lib is None:
                 path = _build.LIB
-                if not os.path.exists(path) or (
-                    os.environ.get("SUCHTREE_B200_REBUILD") and _build.needs_build()
-                ):
-                    path = _build.build()
-                L = C.CDLL(path)
-                for name, (res, args) in SIGNATURES.items():
-                    fn = getattr(L, name)  # AttributeError if the .so lacks a declared symbol
-                    fn.restype = res
-                    fn.argtypes = args
+                if _build.needs_build("product"):
+                    _build.build(which=("product",))
+                L = _bind(C.CDLL(path), SIGNATURES)
+                if _build.sources("product") and L.st_build_id().decode() != _build.source_id("product"):
+                    raise SuchTreeError(
+                        "libsuchtree_b200.so (build id %s) does not match the sources on disk (%s)"
+                        % (L.st_build_id().decode(), _build.source_id("product")))
                 _lib = L
     return _lib
+
+
+def bench_lib():
+    """The bench-only library (gather roofline probe and experiment kernels)."""
+    global _bench_lib
+    if _bench_lib is None:
+        with _lock:
+            if _bench_lib is None:
+                if _build.needs_build("bench"):
+                    _build.build(which=("bench",))
+                _bench_lib = _bind(C.CDLL(_build.BENCH_LIB), BENCH_SIGNATURES)
+    return _bench_lib
 
 
 def last_error():
@@ -125,3 +171,113 @@ def check(rc, tree_size=None):
     if rc == ST_ERR_LENGTH_MISMATCH:
         raise Exception(msg)
     raise SuchTreeError("CUDA path failed (no CPU fallback): " + msg)
+
+
+# --------------------------------------------------------------------------- #
+# page-locked result arrays and registered inputs
+# --------------------------------------------------------------------------- #
+class _PinnedBlock:
+    """A block of the library's pinned pool (st_host_alloc) exposed through the array
+    interface; it goes back to the pool when the last array viewing it dies."""
+
+    __slots__ = ("ptr", "__array_interface__", "__weakref__")
+
+    def __init__(self, shape, dtype):
+        import numpy as np
+
+        dt = np.dtype(dtype)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * dt.itemsize
+        p = _vp()
+        self.ptr = None
+        check(lib().st_host_alloc(nbytes, C.byref(p)))
+        self.ptr = p.value
+        self.__array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": dt.str,
+                                    "data": (self.ptr, False), "version": 3}
+
+    def __del__(self):
+        if self.ptr:
+            try:
+                lib().st_host_free(self.ptr)
+            except Exception:  # interpreter shutdown
+                pass
+            self.ptr = None
+
+
+def pinned_empty(shape, dtype):
+    """np.empty() in page-locked memory from the library's pool: an ordinary ndarray
+    (its .base keeps the block alive) that D2H copies can land in directly."""
+    import numpy as np
+
+    if not isinstance(shape, tuple):
+        shape = (int(shape),)
+    return np.asarray(_PinnedBlock(shape, dtype))
+
+
+PINNED_RESULT_MIN_BYTES = 4 << 20    # smaller results: plain np.empty (the small-call path copies anyway)
+REGISTER_MIN_BYTES = 64 << 20        # inputs at least this large are candidates for registration
+
+_registered = {}   # id(owner) -> [ptr, nbytes, sightings, registered, finalizer]
+_reg_lock = threading.Lock()
+
+
+def _register_policy():
+    """SUCHTREE_B200_REGISTER: 0 = never page-lock caller arrays, 1 = the first time a large
+    input is seen, 2 (default) = the second time the same array is seen (a one-off call
+    should not pay ~0.2 s/GB of pinning; a loop over the same array should)."""
+    try:
+        return int(os.environ.get("SUCHTREE_B200_REGISTER", "2"))
+    except ValueError:
+        return 2
+
+
+def _unregister(key, ptr):
+    with _reg_lock:
+        ent = _registered.pop(key, None)
+    if ent is not None and ent[3]:
+        try:
+            lib().st_host_unregister(ptr)
+        except Exception:
+            pass
+
+
+def maybe_register(arr):
+    """Called with a large C-contiguous input array: page-lock the buffer of the ndarray
+    that owns the memory once the policy says so.  The registration lives exactly as long
+    as the owner (weakref finaliser), so a freed-and-reused address is never mistaken
+    for a registered one.  Returns True when the array is (now) page-locked."""
+    import weakref
+
+    import numpy as np
+
+    policy = _register_policy()
+    if policy <= 0 or arr.nbytes < REGISTER_MIN_BYTES:
+        return False
+    owner = arr
+    while isinstance(owner.base, np.ndarray):
+        owner = owner.base
+    if owner.base is not None or not owner.flags.owndata:
+        return False  # memory owned by something we cannot track (mmap, bytes, another library)
+    ptr, nbytes, key = owner.ctypes.data, owner.nbytes, id(owner)
+    with _reg_lock:
+        ent = _registered.get(key)
+        if ent is not None and (ent[0] != ptr or ent[1] != nbytes):
+            ent = None  # the owner was resized in place: forget the old range
+            stale = _registered.pop(key)
+            if stale[3]:
+                lib().st_host_unregister(stale[0])
+            stale[4].detach()
+        if ent is None:
+            try:
+                fin = weakref.finalize(owner, _unregister, key, ptr)
+            except TypeError:
+                return False
+            ent = _registered[key] = [ptr, nbytes, 0, False, fin]
+        ent[2] += 1
+        if ent[3]:
+            return True
+        if ent[2] >= policy:
+            if lib().st_host_register(ptr, nbytes) == ST_OK:
+                ent[3] = True
+                return True
+            ent[2] = -(1 << 60)  # registration failed (locked-memory limit ...): do not retry every call
+    return False

@@ -1,10 +1,17 @@
-"""In-tree nvcc build of libsuchtree_b200.so (sm_100a only).
+"""In-tree nvcc build (sm_100a only) of
+
+    libsuchtree_b200.so        the product: csrc/*.cu behind include/suchtree_b200.h
+    libsuchtree_b200_bench.so  bench-only tooling: bench/*.cu behind include/suchtree_b200_bench.h
 
     python -m suchtree_b200.build [--force] [--verbose]
 
-The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
+The .so files are git-ignored but travel to the GPU box with the gpurun snapshot.
+Each binary carries the hash of the sources it was compiled from (st_build_id());
+the loader (suchtree_b200/_lib.py) rebuilds a library whose id differs from the
+sources on disk, so a stale binary can never be measured by accident.
 """
 import glob
+import hashlib
 import os
 import shutil
 import subprocess
@@ -12,8 +19,10 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+BENCH_SRC = os.path.join(HERE, "bench")
 LIB = os.path.join(HERE, "libsuchtree_b200.so")
-# the C header: <repo>/include in a checkout, <package>/include when pip-installed
+BENCH_LIB = os.path.join(HERE, "libsuchtree_b200_bench.so")
+# the C headers: <repo>/include in a checkout, <package>/include when pip-installed
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 if not os.path.exists(os.path.join(INCLUDE, "suchtree_b200.h")):
     INCLUDE = os.path.join(HERE, "include")
@@ -27,8 +36,6 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "-Xcompiler", "-fvisibility=hidden",
     "--expt-relaxed-constexpr",
-    "-shared",
-    "-cudart", "static",
 ]
 
 
@@ -39,16 +46,45 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
-def sources():
-    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+def sources(which="product"):
+    return sorted(glob.glob(os.path.join(CSRC if which == "product" else BENCH_SRC, "*.cu")))
 
 
-def needs_build():
-    if not os.path.exists(LIB):
+def _deps(which):
+    return (sources(which) + sorted(glob.glob(os.path.join(CSRC, "*.cuh")))
+            + sorted(glob.glob(os.path.join(INCLUDE, "*.h"))))
+
+
+def source_id(which="product"):
+    """sha1 over names + contents of everything the library is compiled from."""
+    h = hashlib.sha1()
+    for path in _deps(which):
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()[:16]
+
+
+def _id_file(lib):
+    return lib + ".id"
+
+
+def built_id(lib):
+    try:
+        with open(_id_file(lib)) as f:
+            return f.read().strip()
+    except OSError:
+        return None
+
+
+def needs_build(which="product"):
+    lib = LIB if which == "product" else BENCH_LIB
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+    if not sources(which):  # installed without sources: nothing to compare with
+        return False
+    return built_id(lib) != source_id(which)
 
 
 def _compile_one(args):
@@ -60,32 +96,49 @@ def _compile_one(args):
     return obj
 
 
-def build(force=False, verbose=False, extra=()):
-    """One object per translation unit (compiled in parallel, only the stale ones),
-    then one device-link-free shared library."""
-    if not force and not needs_build():
-        return LIB
+def _build_one(which, force, verbose, extra):
     from concurrent.futures import ThreadPoolExecutor
 
+    lib = LIB if which == "product" else BENCH_LIB
+    sid = source_id(which)
     os.makedirs(OBJ, exist_ok=True)
-    flags = [f for f in NVCC_FLAGS if f != "-shared"] + list(extra)
+    flags = list(NVCC_FLAGS) + list(extra)
     if verbose:
         flags = ["-Xptxas", "-v"] + flags
     hdr_t = max([os.path.getmtime(h) for h in glob.glob(os.path.join(CSRC, "*.cuh"))
                  + glob.glob(os.path.join(INCLUDE, "*.h"))] + [os.path.getmtime(__file__)])
     jobs, objs = [], []
-    for src in sources():
-        obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+    for src in sources(which):
+        base = os.path.basename(src)[:-3]
+        obj = os.path.join(OBJ, ("" if which == "product" else "bench_") + base + ".o")
         objs.append(obj)
-        if force or extra or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_t):
-            jobs.append((src, obj, flags, verbose))
+        f = flags
+        carries_id = base in ("st_index", "st_bench_gather")
+        if carries_id:  # the TU that answers st_build_id(): recompiled whenever anything changed
+            f = flags + ['-DST_BUILD_ID="%s"' % sid]
+        stale = not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_t)
+        if force or extra or stale or (carries_id and built_id(lib) != sid):
+            jobs.append((src, obj, f, verbose))
     with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as pool:
         list(pool.map(_compile_one, jobs))
     cmd = [_nvcc(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
-           "-Xcompiler", "-fPIC", "-o", LIB] + objs
+           "-Xcompiler", "-fPIC", "-o", lib] + objs + ["-ldl"]
+    if which != "product":
+        cmd += ["-lcuda"]  # cuTensorMapEncodeTiled of the gather4 experiment
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)
+    with open(_id_file(lib), "w") as f:
+        f.write(sid + "\n")
+    return lib
+
+
+def build(force=False, verbose=False, extra=(), which=("product", "bench")):
+    """One object per translation unit (compiled in parallel, only the stale ones),
+    then one device-link-free shared library per target."""
+    for w in which:
+        if force or extra or needs_build(w):
+            _build_one(w, force, verbose, extra)
     return LIB
 
 

@@ -19,6 +19,7 @@
 #include <new>
 
 #include "st_device.cuh"
+#include "st_hostctx.cuh"
 
 // ------------------------------------------------------------ error state ---
 static thread_local char g_err[512] = "";
@@ -34,7 +35,11 @@ void st_set_bad_node(int64_t id) { g_bad_node = id; }
 
 extern "C" const char *st_last_error(void) { return g_err; }
 extern "C" int64_t st_bad_node(void) { return g_bad_node; }
-extern "C" int st_version(void) { return 100; }
+extern "C" int st_version(void) { return 200; }
+#ifndef ST_BUILD_ID
+#define ST_BUILD_ID "unknown"
+#endif
+extern "C" const char *st_build_id(void) { return ST_BUILD_ID; }
 extern "C" int st_device_count(int *count) {
     if (!count) return ST_ERR_INVALID_ARG;
     *count = 0;
@@ -323,15 +328,6 @@ extern "C" void st_tree_destroy(st_tree *t) {
     }
     cudaFree(t->d_mst);
     cudaFree(t->d_status);
-    for (int i = 0; i < 3; ++i) {
-        if (t->d_stage_in[i]) cudaFree(t->d_stage_in[i]);
-        if (t->d_stage_out[i]) cudaFree(t->d_stage_out[i]);
-        if (t->d_stage_out2[i]) cudaFree(t->d_stage_out2[i]);
-        if (t->h_stage[i]) cudaFreeHost(t->h_stage[i]);
-        if (t->h_out_stage[i]) cudaFreeHost(t->h_out_stage[i]);
-        if (t->ev[i]) cudaEventDestroy(t->ev[i]);
-        if (t->streams[i]) cudaStreamDestroy(t->streams[i]);
-    }
     delete t;
 }
 
@@ -626,10 +622,7 @@ extern "C" int st_tree_create_ex(int device, int64_t n_nodes, const int32_t *par
     t->view.micro_shift = ms;
     t->view.st_levels = t->st_levels;
     t->view.m_levels = t->m_levels;
-    for (int i = 0; i < 3; ++i) {
-        ST_TRY_CUDA(cudaStreamCreateWithFlags(&t->streams[i], cudaStreamNonBlocking));
-        ST_TRY_CUDA(cudaEventCreateWithFlags(&t->ev[i], cudaEventDisableTiming));
-    }
+    st_hostctx_prewarm(device);  // staging of the host-buffer entry points: once per device, in the background
     *out = t;
     return ST_OK;
 }

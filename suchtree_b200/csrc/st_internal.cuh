@@ -117,23 +117,16 @@ struct st_tree {
     TreeView view{};
     int query_smem_bytes = 0;
 
-    // host-path scratch: streams + device/pinned staging, guarded by a mutex so
-    // concurrent host calls serialise on the staging buffers only
-    mutable std::mutex host_mu;
-    mutable cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
-    mutable void *d_stage_in[3] = {nullptr, nullptr, nullptr};
-    mutable void *d_stage_out[3] = {nullptr, nullptr, nullptr};
-    mutable void *d_stage_out2[3] = {nullptr, nullptr, nullptr};
-    mutable void *h_stage[3] = {nullptr, nullptr, nullptr};      // pinned, packed input ids
-    mutable void *h_out_stage[3] = {nullptr, nullptr, nullptr};  // pinned results (pageable user buffers)
-    mutable int64_t stage_pairs = 0;
-    mutable cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    // (host-buffer entry points take their streams, staging and status word from a lane of
+    //  the device's host context, st_hostctx.cuh: a tree handle owns no per-call state)
 };
 
 // ------------------------------------------------------- internal launches --
 // query kernels (st_query.cu)
+// status = NULL: the tree's own word (device API, read by st_check_range); host calls pass
+// their lane's word
 int st_launch_pairs(const st_tree *t, const void *d_pairs, int idx_bits, int64_t n, double *d_out,
-                    int32_t *d_mrca, cudaStream_t stream);
+                    int32_t *d_mrca, cudaStream_t stream, RangeStatus *status = nullptr);
 int st_read_range_status(const st_tree *t, cudaStream_t stream, bool *bad);
 
 static inline int st_ceil_log2_i64(int64_t x) {

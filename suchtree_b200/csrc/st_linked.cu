@@ -10,7 +10,10 @@
 #include <cmath>
 #include <vector>
 
+#include <new>
+
 #include "st_device.cuh"
+#include "st_hostctx.cuh"
 
 static const int LT = 256;
 
@@ -90,56 +93,17 @@ k_linked(const TreeView tv, const int32_t *__restrict__ col, int64_t k0, int64_t
     }
 }
 
-// ------------------------------------------------------------ link upload ---
-// Stream-ordered allocations (recycled by the device's default pool, see
-// st_tree_create): no driver-level malloc/free on the per-call path.
-struct DevLinks {
+// ------------------------------------------------------------ link handle ---
+// The link list lives on the device for as long as the caller keeps the handle: the
+// per-call O(L) id conversion, the pageable H2D copies and their synchronisation are
+// paid once (st_links_create), not by every sampler / moment / scan call.
+struct st_links {
+    const st_tree *ta = nullptr, *tb = nullptr;
+    int device = 0;
+    int64_t L = 0;
     int32_t *col_a = nullptr, *col_b = nullptr;  // linklist[:,1] (TreeA ids), linklist[:,0] (TreeB ids)
     int2 *rows = nullptr;                        // (b, a) per link, for the samplers
-    cudaStream_t stream = nullptr;
-    ~DevLinks() {
-        if (col_a) cudaFreeAsync(col_a, stream);
-        if (col_b) cudaFreeAsync(col_b, stream);
-        if (rows) cudaFreeAsync(rows, stream);
-    }
 };
-
-static int upload_links(const st_tree *ta, const st_tree *tb, const int64_t *linklist, int64_t L,
-                        DevLinks &d, bool want_cols = true, bool want_rows = true) {
-    d.stream = ta->streams[0];
-    std::vector<int32_t> a(L), b(L);
-    std::vector<int2> rows(L);
-    for (int64_t i = 0; i < L; ++i) {
-        int64_t vb = linklist[2 * i], va = linklist[2 * i + 1];
-        if (va < 0 || va >= ta->n_nodes) {
-            st_set_bad_node(va);
-            st_set_error("linklist row %lld: TreeA id %lld out of bounds", (long long)i, (long long)va);
-            return ST_ERR_NODE_RANGE;
-        }
-        if (vb < 0 || vb >= tb->n_nodes) {
-            st_set_bad_node(vb);
-            st_set_error("linklist row %lld: TreeB id %lld out of bounds", (long long)i, (long long)vb);
-            return ST_ERR_NODE_RANGE;
-        }
-        a[i] = int32_t(va);
-        b[i] = int32_t(vb);
-        rows[i] = make_int2(int32_t(vb), int32_t(va));
-    }
-    cudaStream_t s = d.stream;
-    if (want_cols) {
-        ST_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d.col_a), size_t(L) * 4, s));
-        ST_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d.col_b), size_t(L) * 4, s));
-        ST_CUDA(cudaMemcpyAsync(d.col_a, a.data(), size_t(L) * 4, cudaMemcpyHostToDevice, s));
-        ST_CUDA(cudaMemcpyAsync(d.col_b, b.data(), size_t(L) * 4, cudaMemcpyHostToDevice, s));
-    }
-    if (want_rows) {
-        ST_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d.rows), size_t(L) * 8, s));
-        ST_CUDA(cudaMemcpyAsync(d.rows, rows.data(), size_t(L) * 8, cudaMemcpyHostToDevice, s));
-    }
-    // the host vectors die with this frame: the copies (pageable source) must have left them
-    ST_CUDA(cudaStreamSynchronize(s));
-    return ST_OK;
-}
 
 static int check_pair_of_trees(const st_tree *ta, const st_tree *tb, const int64_t *linklist, int64_t L) {
     if (!ta || !tb || !linklist || L < 0) {
@@ -153,55 +117,144 @@ static int check_pair_of_trees(const st_tree *ta, const st_tree *tb, const int64
     return ST_OK;
 }
 
-template <typename K>
-static int set_smem(K kern, int bytes) {
-    if (bytes > 48 * 1024)
-        ST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+extern "C" void st_links_destroy(st_links *k) {
+    if (!k) return;
+    DeviceGuard g(k->device);
+    cudaFree(k->col_a);
+    cudaFree(k->col_b);
+    cudaFree(k->rows);
+    delete k;
+}
+
+extern "C" int st_links_create(const st_tree *ta, const st_tree *tb, const int64_t *linklist, int64_t L,
+                               st_links **out) {
+    if (!out) return ST_ERR_INVALID_ARG;
+    *out = nullptr;
+    int rc = check_pair_of_trees(ta, tb, linklist, L);
+    if (rc != ST_OK) return rc;
+    if (L >= (int64_t(1) << 31)) {
+        st_set_error("st_links_create: n_links must be < 2^31");
+        return ST_ERR_INVALID_ARG;
+    }
+    std::vector<int32_t> a(static_cast<size_t>(L)), b(static_cast<size_t>(L));
+    std::vector<int2> rows(static_cast<size_t>(L));
+    for (int64_t i = 0; i < L; ++i) {
+        int64_t vb = linklist[2 * i], va = linklist[2 * i + 1];
+        if (va < 0 || va >= ta->n_nodes) {
+            st_set_bad_node(va);
+            st_set_error("linklist row %lld: TreeA id %lld out of bounds", (long long)i, (long long)va);
+            return ST_ERR_NODE_RANGE;
+        }
+        if (vb < 0 || vb >= tb->n_nodes) {
+            st_set_bad_node(vb);
+            st_set_error("linklist row %lld: TreeB id %lld out of bounds", (long long)i, (long long)vb);
+            return ST_ERR_NODE_RANGE;
+        }
+        a[size_t(i)] = int32_t(va);
+        b[size_t(i)] = int32_t(vb);
+        rows[size_t(i)] = make_int2(int32_t(vb), int32_t(va));
+    }
+    DeviceGuard g(ta->device);
+    st_links *k = new (std::nothrow) st_links();
+    if (!k) return ST_ERR_NOMEM;
+    k->ta = ta;
+    k->tb = tb;
+    k->device = ta->device;
+    k->L = L;
+    const size_t n = size_t(std::max<int64_t>(L, 1));
+    if (cudaMalloc(reinterpret_cast<void **>(&k->col_a), n * 4) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void **>(&k->col_b), n * 4) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void **>(&k->rows), n * 8) != cudaSuccess ||
+        cudaMemcpy(k->col_a, a.data(), size_t(L) * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(k->col_b, b.data(), size_t(L) * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(k->rows, rows.data(), size_t(L) * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
+        st_set_error("st_links_create: %s", cudaGetErrorString(cudaGetLastError()));
+        st_links_destroy(k);
+        return ST_ERR_CUDA;
+    }
+    *out = k;
+    return ST_OK;
+}
+
+// entry points that take the raw link list build a handle for the call
+struct TempLinks {
+    st_links *k = nullptr;
+    ~TempLinks() { st_links_destroy(k); }
+};
+
+// 6 moment sums {n, sx, sy, sxx, syy, sxy} at lane->d_scratch -> host, through the path's one
+// collective when a communicator is given: ncclAllReduce(sum, fp64, 6) enqueued on the
+// stream the kernels ran on (st_nccl.cu)
+int st_nccl_allreduce_sum_f64(void *comm, double *d_buf, int count, cudaStream_t stream);
+static int finish_moments(HostLane *lane, cudaStream_t s, void *nccl_comm, const char *who, double x0,
+                          double y0, st_moments *out) {
+    if (nccl_comm) {
+        const int rc = st_nccl_allreduce_sum_f64(nccl_comm, lane->d_scratch, 6, s);
+        if (rc != ST_OK) {
+            cudaStreamSynchronize(s);
+            return rc;
+        }
+    }
+    cudaMemcpyAsync(lane->h_scratch, lane->d_scratch, 6 * sizeof(double), cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        st_set_error("%s: %s", who, cudaGetErrorString(e));
+        return ST_ERR_CUDA;
+    }
+    const double *h = lane->h_scratch;
+    out->n = h[0];
+    out->x0 = x0;
+    out->y0 = y0;
+    out->sx = h[1]; out->sy = h[2]; out->sxx = h[3]; out->syy = h[4]; out->sxy = h[5];
     return ST_OK;
 }
 
 // ------------------------------------------------------ linked_distances ----
-extern "C" int st_linked_distances(const st_tree *ta, const st_tree *tb, const int64_t *linklist,
-                                   int64_t L, double *out_a, double *out_b, int64_t *ids_a,
-                                   int64_t *ids_b) {
-    int rc = check_pair_of_trees(ta, tb, linklist, L);
-    if (rc != ST_OK) return rc;
-    const int64_t total = L * (L - 1) / 2;
+extern "C" int st_links_linked_distances(const st_links *k, double *out_a, double *out_b, int64_t *ids_a,
+                                         int64_t *ids_b) {
+    if (!k) {
+        st_set_error("st_links_linked_distances: NULL handle");
+        return ST_ERR_INVALID_ARG;
+    }
+    const st_tree *ta = k->ta, *tb = k->tb;
+    const int64_t L = k->L, total = L * (L - 1) / 2;
     if (total <= 0) return ST_OK;
     if (!out_a || !out_b) {
         st_set_error("st_linked_distances: NULL output");
         return ST_ERR_INVALID_ARG;
     }
     DeviceGuard g(ta->device);
-    DevLinks dl;
-    rc = upload_links(ta, tb, linklist, L, dl, true, false);
-    if (rc != ST_OK) return rc;
-    rc = set_smem(k_linked, std::max(ta->query_smem_bytes, tb->query_smem_bytes));
+    LaneGuard lg(ta->device);
+    HostLane *lane = lg.lane;
+    if (!lane) return ST_ERR_CUDA;
+    int rc = st_raise_smem(k_linked, ta->device, std::max(ta->query_smem_bytes, tb->query_smem_bytes));
     if (rc != ST_OK) return rc;
 
     const int64_t C = std::min<int64_t>(total, int64_t(1) << 22);
     double *d_out[2] = {nullptr, nullptr};
     int64_t *d_ids[2] = {nullptr, nullptr};
-    cudaStream_t st[2] = {ta->streams[0], ta->streams[1]};
-    std::lock_guard<std::mutex> lock(ta->host_mu);
+    cudaStream_t st[2] = {lane->streams[0], lane->streams[1]};
     auto cleanup = [&]() {
         for (int i = 0; i < 2; ++i) {
-            cudaFree(d_out[i]);
-            cudaFree(d_ids[i]);
+            if (d_out[i]) cudaFreeAsync(d_out[i], st[i]);
+            if (d_ids[i]) cudaFreeAsync(d_ids[i], st[i]);
         }
     };
     for (int i = 0; i < 2; ++i) {
-        if (cudaMalloc(&d_out[i], size_t(C) * 8) != cudaSuccess ||
-            ((ids_a || ids_b) && cudaMalloc(&d_ids[i], size_t(C) * 16) != cudaSuccess)) {
+        if (cudaMallocAsync(reinterpret_cast<void **>(&d_out[i]), size_t(C) * 8, st[i]) != cudaSuccess ||
+            ((ids_a || ids_b) &&
+             cudaMallocAsync(reinterpret_cast<void **>(&d_ids[i]), size_t(C) * 16, st[i]) != cudaSuccess)) {
+            cudaGetLastError();
             cleanup();
-            st_set_error("st_linked_distances: cudaMalloc failed");
+            st_set_error("st_linked_distances: device allocation failed");
             return ST_ERR_NOMEM;
         }
     }
     int slot = 0;
     for (int tree = 0; tree < 2; ++tree) {
         const st_tree *t = tree ? tb : ta;
-        const int32_t *col = tree ? dl.col_b : dl.col_a;
+        const int32_t *col = tree ? k->col_b : k->col_a;
         double *out = tree ? out_b : out_a;
         int64_t *ids = tree ? ids_b : ids_a;
         for (int64_t k0 = 0; k0 < total; k0 += C, slot ^= 1) {
@@ -214,15 +267,24 @@ extern "C" int st_linked_distances(const st_tree *ta, const st_tree *tb, const i
                 cudaMemcpyAsync(ids + 2 * k0, d_ids[slot], size_t(m) * 16, cudaMemcpyDeviceToHost, st[slot]);
         }
     }
+    cleanup();
     cudaError_t e0 = cudaStreamSynchronize(st[0]), e1 = cudaStreamSynchronize(st[1]);
     cudaError_t e2 = cudaGetLastError();
-    cleanup();
     if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess) {
         st_set_error("st_linked_distances: %s",
                      cudaGetErrorString(e0 != cudaSuccess ? e0 : (e1 != cudaSuccess ? e1 : e2)));
         return ST_ERR_CUDA;
     }
     return ST_OK;
+}
+
+extern "C" int st_linked_distances(const st_tree *ta, const st_tree *tb, const int64_t *linklist,
+                                   int64_t L, double *out_a, double *out_b, int64_t *ids_a,
+                                   int64_t *ids_b) {
+    TempLinks tl;
+    int rc = st_links_create(ta, tb, linklist, L, &tl.k);
+    if (rc != ST_OK) return rc;
+    return st_links_linked_distances(tl.k, out_a, out_b, ids_a, ids_b);
 }
 
 // ------------------------------------------- xorshift64*: exact jump-ahead --
@@ -281,8 +343,7 @@ static const int XS_RUN = 8;  // consecutive samples per thread after one jump
 // which = 0: TreeB (linklist[:,0]).  Sample q consumes draws 2q, 2q+1 of the stream.
 __global__ void __launch_bounds__(LT)
 k_sample_xs(const TreeView tv, const int2 *__restrict__ links, uint64_t n_links, int which,
-            uint64_t seed, const uint64_t *__restrict__ jump, int64_t total, int32_t n_per_bucket,
-            double *__restrict__ out, double *__restrict__ sums, double *__restrict__ sumsq) {
+            uint64_t seed, const uint64_t *__restrict__ jump, int64_t total, double *__restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t tables_bar;
     const SmemTables sm = st_load_tables(tv, smem_raw, &tables_bar);
@@ -290,56 +351,80 @@ k_sample_xs(const TreeView tv, const int2 *__restrict__ links, uint64_t n_links,
     for (int64_t r = int64_t(blockIdx.x) * LT + threadIdx.x; r < runs; r += int64_t(gridDim.x) * LT) {
         const int64_t q0 = r * XS_RUN;
         uint64_t s = seed, steps = 2ull * uint64_t(q0);
-        for (int k = 0; steps; ++k, steps >>= 1)
+        for (int k = 0; steps && k < XS_LEVELS; ++k, steps >>= 1)
             if (steps & 1) s = xs_apply_dev(jump + k * 64, s);
-        double acc = 0.0, acc2 = 0.0;
-        int64_t cur_bucket = q0 / n_per_bucket;
         for (int u = 0; u < XS_RUN && q0 + u < total; ++u) {
             s ^= s >> 12; s ^= s << 25; s ^= s >> 27;
             int l1 = int((s * 2685821657736338717ull) % n_links);  // `cdef int l1` (MuchTree.pyx:3009)
             s ^= s >> 12; s ^= s << 25; s ^= s >> 27;
             int l2 = int((s * 2685821657736338717ull) % n_links);
             int2 r1 = __ldg(links + l1), r2 = __ldg(links + l2);
-            double d = which ? linked_query(tv, sm, r1.y, r2.y) : linked_query(tv, sm, r1.x, r2.x);
-            out[q0 + u] = d;
-            int64_t bkt = (q0 + u) / n_per_bucket;
-            if (bkt != cur_bucket) {
-                atomicAdd(sums + cur_bucket, acc);
-                atomicAdd(sumsq + cur_bucket, acc2);
-                acc = acc2 = 0.0;
-                cur_bucket = bkt;
-            }
-            acc += d;
-            acc2 += d * d;
+            out[q0 + u] = which ? linked_query(tv, sm, r1.y, r2.y) : linked_query(tv, sm, r1.x, r2.x);
         }
-        atomicAdd(sums + cur_bucket, acc);
-        atomicAdd(sumsq + cur_bucket, acc2);
     }
 }
 
-extern "C" int st_sample_linked_cycle(const st_tree *ta, const st_tree *tb, const int64_t *linklist,
-                                      int64_t L, uint64_t *seed, int32_t buckets, int32_t n,
-                                      double *out_a, double *out_b, double *sums_a, double *sumsq_a,
-                                      double *sums_b, double *sumsq_b) {
-    int rc = check_pair_of_trees(ta, tb, linklist, L);
-    if (rc != ST_OK) return rc;
+// Per-bucket sum d and sum d^2 (MuchTree.pyx:3045-3052) from the materialised distances, in a
+// FIXED order: one CTA per (bucket, tree); thread t adds elements t, t+256, ... in order, then a
+// fixed shuffle / shared-memory tree.  Bit-reproducible run to run (the reference's bucket
+// statistics are): the `deviation < sigma` stopping test can never flip between runs.
+__global__ void __launch_bounds__(256)
+k_bucket_sums(const double *__restrict__ d, int32_t n_per_bucket, int32_t buckets,
+              double *__restrict__ stats /* [tree][sum|sumsq][buckets] */) {
+    const int b = blockIdx.x, tree = blockIdx.y;
+    const double *x = d + (size_t(tree) * buckets + b) * n_per_bucket;
+    double s = 0.0, s2 = 0.0;
+    for (int i = threadIdx.x; i < n_per_bucket; i += 256) {
+        const double v = x[i];
+        s += v;
+        s2 += v * v;
+    }
+    __shared__ double red[2][8];
+    for (int o = 16; o; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = s;
+        red[1][threadIdx.x >> 5] = s2;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+        stats[(size_t(tree) * 2 + threadIdx.x) * buckets + b] = t;
+    }
+}
+
+extern "C" int st_links_sample_cycle(const st_links *k, uint64_t *seed, int32_t buckets, int32_t n,
+                                     double *out_a, double *out_b, double *sums_a, double *sumsq_a,
+                                     double *sums_b, double *sumsq_b) {
+    if (!k) {
+        st_set_error("st_links_sample_cycle: NULL handle");
+        return ST_ERR_INVALID_ARG;
+    }
+    const st_tree *ta = k->ta, *tb = k->tb;
+    const int64_t L = k->L;
     if (!seed || buckets < 1 || n < 1 || L < 1 || !out_a || !out_b || !sums_a || !sumsq_a || !sums_b ||
         !sumsq_b) {
         st_set_error("st_sample_linked_cycle: bad arguments");
         return ST_ERR_INVALID_ARG;
     }
-    DeviceGuard g(ta->device);
-    DevLinks dl;
-    rc = upload_links(ta, tb, linklist, L, dl, false, true);
-    if (rc != ST_OK) return rc;
-    rc = set_smem(k_sample_xs, std::max(ta->query_smem_bytes, tb->query_smem_bytes));
-    if (rc != ST_OK) return rc;
     const int64_t total = int64_t(buckets) * n;
+    if (2ull * uint64_t(total) >= (uint64_t(1) << XS_LEVELS)) {  // the jump table has XS_LEVELS levels
+        st_set_error("st_sample_linked_cycle: 2*buckets*n must be < 2^%d", XS_LEVELS);
+        return ST_ERR_INVALID_ARG;
+    }
+    DeviceGuard g(ta->device);
+    LaneGuard lg(ta->device);
+    HostLane *lane = lg.lane;
+    if (!lane) return ST_ERR_CUDA;
+    int rc = st_raise_smem(k_sample_xs, ta->device, std::max(ta->query_smem_bytes, tb->query_smem_bytes));
+    if (rc != ST_OK) return rc;
     const XsJump &J = xs_table();
     uint64_t *d_jump = nullptr;
     double *d_out = nullptr, *d_stats = nullptr;
-    std::lock_guard<std::mutex> lock(ta->host_mu);
-    cudaStream_t s = ta->streams[0];
+    cudaStream_t s = lane->streams[0];
     auto cleanup = [&]() {  // stream-ordered scratch: recycled by the pool, no driver malloc per cycle
         if (d_jump) cudaFreeAsync(d_jump, s);
         if (d_out) cudaFreeAsync(d_out, s);
@@ -348,20 +433,20 @@ extern "C" int st_sample_linked_cycle(const st_tree *ta, const st_tree *tb, cons
     if (cudaMallocAsync(reinterpret_cast<void **>(&d_jump), sizeof(J.col), s) != cudaSuccess ||
         cudaMallocAsync(reinterpret_cast<void **>(&d_out), size_t(total) * 8 * 2, s) != cudaSuccess ||
         cudaMallocAsync(reinterpret_cast<void **>(&d_stats), size_t(buckets) * 8 * 4, s) != cudaSuccess) {
+        cudaGetLastError();
         cleanup();
         st_set_error("st_sample_linked_cycle: device allocation failed");
         return ST_ERR_NOMEM;
     }
     cudaMemcpyAsync(d_jump, J.col, sizeof(J.col), cudaMemcpyHostToDevice, s);
-    cudaMemsetAsync(d_stats, 0, size_t(buckets) * 8 * 4, s);
     const int64_t runs = (total + XS_RUN - 1) / XS_RUN;
     for (int tree = 0; tree < 2; ++tree) {
         const st_tree *t = tree ? tb : ta;
         int grid = int(std::min<int64_t>((runs + LT - 1) / LT, int64_t(t->sm_count) * 8));
-        k_sample_xs<<<grid, LT, t->query_smem_bytes, s>>>(
-            t->view, dl.rows, uint64_t(L), tree ? 0 : 1, *seed, d_jump, total, n, d_out + tree * total,
-            d_stats + (tree ? 2 : 0) * buckets, d_stats + (tree ? 3 : 1) * buckets);
+        k_sample_xs<<<grid, LT, t->query_smem_bytes, s>>>(t->view, k->rows, uint64_t(L), tree ? 0 : 1, *seed,
+                                                          d_jump, total, d_out + tree * total);
     }
+    k_bucket_sums<<<dim3(unsigned(buckets), 2), 256, 0, s>>>(d_out, n, buckets, d_stats);
     std::vector<double> stats(size_t(buckets) * 4);
     cudaMemcpyAsync(out_a, d_out, size_t(total) * 8, cudaMemcpyDeviceToHost, s);
     cudaMemcpyAsync(out_b, d_out + total, size_t(total) * 8, cudaMemcpyDeviceToHost, s);
@@ -373,7 +458,7 @@ extern "C" int st_sample_linked_cycle(const st_tree *ta, const st_tree *tb, cons
         st_set_error("st_sample_linked_cycle: %s", cudaGetErrorString(e));
         return ST_ERR_CUDA;
     }
-    for (int i = 0; i < buckets; ++i) {
+    for (int i = 0; i < buckets; ++i) {  // stats: [TreeA sum | TreeA sumsq | TreeB sum | TreeB sumsq][buckets]
         sums_a[i] += stats[i];
         sumsq_a[i] += stats[buckets + i];
         sums_b[i] += stats[2 * buckets + i];
@@ -381,6 +466,16 @@ extern "C" int st_sample_linked_cycle(const st_tree *ta, const st_tree *tb, cons
     }
     *seed = xs_jump_host(*seed, 2ull * uint64_t(total));
     return ST_OK;
+}
+
+extern "C" int st_sample_linked_cycle(const st_tree *ta, const st_tree *tb, const int64_t *linklist,
+                                      int64_t L, uint64_t *seed, int32_t buckets, int32_t n,
+                                      double *out_a, double *out_b, double *sums_a, double *sumsq_a,
+                                      double *sums_b, double *sumsq_b) {
+    TempLinks tl;
+    int rc = st_links_create(ta, tb, linklist, L, &tl.k);
+    if (rc != ST_OK) return rc;
+    return st_links_sample_cycle(tl.k, seed, buckets, n, out_a, out_b, sums_a, sumsq_a, sums_b, sumsq_b);
 }
 
 // ------------------------------------------------ Philox sampler + moments --
@@ -448,47 +543,48 @@ k_sample_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ 
     }
 }
 
-__global__ void k_reduce_partials(int grid, const double *__restrict__ partials, double *__restrict__ out) {
+// out[6] = {n, sx, sy, sxx, syy, sxy}: the payload of the moment all-reduce
+__global__ void k_reduce_partials(int grid, const double *__restrict__ partials, double n,
+                                  double *__restrict__ out) {
     // one warp per moment, fixed order -> deterministic
     const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (k >= 5) return;
     double s = 0;
     for (int i = lane; i < grid; i += 32) s += partials[size_t(i) * 5 + k];
     s = warp_sum(s);
-    if (lane == 0) out[k] = s;
+    if (lane == 0) out[k + 1] = s;
+    if (threadIdx.x == 0) out[0] = n;
 }
 
-extern "C" int st_sample_moments(const st_tree *ta, const st_tree *tb, const int64_t *linklist,
-                                 int64_t L, uint64_t seed, int64_t first_sample, int64_t n_samples,
-                                 double x0, double y0, st_moments *out) {
-    int rc = check_pair_of_trees(ta, tb, linklist, L);
-    if (rc != ST_OK) return rc;
-    if (!out || L < 1 || L >= (int64_t(1) << 32) || n_samples < 0 || first_sample < 0) {
+extern "C" int st_links_sample_moments(const st_links *k, uint64_t seed, int64_t first_sample,
+                                       int64_t n_samples, double x0, double y0, void *nccl_comm,
+                                       st_moments *out) {
+    if (!k || !out || k->L < 1 || n_samples < 0 || first_sample < 0) {
         st_set_error("st_sample_moments: bad arguments");
         return ST_ERR_INVALID_ARG;
     }
+    const st_tree *ta = k->ta, *tb = k->tb;
     out->n = double(n_samples);
     out->x0 = x0;
     out->y0 = y0;
     out->sx = out->sy = out->sxx = out->syy = out->sxy = 0.0;
-    if (n_samples == 0) return ST_OK;
+    if (n_samples == 0 && !nccl_comm) return ST_OK;  // (with a communicator every rank must enter the collective)
     DeviceGuard g(ta->device);
-    DevLinks dl;
-    rc = upload_links(ta, tb, linklist, L, dl, false, true);
-    if (rc != ST_OK) return rc;
+    LaneGuard lg(ta->device);
+    HostLane *lane = lg.lane;
+    if (!lane) return ST_ERR_CUDA;
     const int smem = ((ta->query_smem_bytes + 15) & ~15) + tb->query_smem_bytes;
     // 1024-thread CTAs with both trees' tables: one CTA per SM
     const int64_t calls = (n_samples + 1) / 2 + 1;
     int grid = int(std::min<int64_t>((calls + MLT - 1) / MLT, int64_t(ta->sm_count)));
-    cudaStream_t s = ta->streams[0];
-    double *d_part = nullptr;  // [grid][5] partials, then 5 folded sums
-    ST_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d_part), size_t(grid + 1) * 5 * 8, s));
-    double *d_out = d_part + size_t(grid) * 5;
+    cudaStream_t s = lane->streams[0];
+    double *d_part = nullptr;  // [grid][5] partials
+    ST_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d_part), size_t(grid) * 5 * 8, s));
     int rc_launch = ST_OK;
-#define ST_LAUNCH_SAMPLE(MA, MB)                                                                         \
-    rc_launch = set_smem(k_sample_moments<MA, MB>, smem);                                                \
-    if (rc_launch == ST_OK)                                                                              \
-        k_sample_moments<MA, MB><<<grid, MLT, smem, s>>>(ta->view, tb->view, dl.rows, uint32_t(L), seed, \
+#define ST_LAUNCH_SAMPLE(MA, MB)                                                                        \
+    rc_launch = st_raise_smem(k_sample_moments<MA, MB>, ta->device, smem);                              \
+    if (rc_launch == ST_OK)                                                                             \
+        k_sample_moments<MA, MB><<<grid, MLT, smem, s>>>(ta->view, tb->view, k->rows, uint32_t(k->L), seed, \
                                                          first_sample, n_samples, x0, y0, d_part)
     ST_DISPATCH_MODES(tree_mode(ta), tree_mode(tb), ST_LAUNCH_SAMPLE);
 #undef ST_LAUNCH_SAMPLE
@@ -496,18 +592,18 @@ extern "C" int st_sample_moments(const st_tree *ta, const st_tree *tb, const int
         cudaFreeAsync(d_part, s);
         return rc_launch;
     }
-    k_reduce_partials<<<1, 160, 0, s>>>(grid, d_part, d_out);
-    double h[5];
-    cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, s);
+    k_reduce_partials<<<1, 160, 0, s>>>(grid, d_part, double(n_samples), lane->d_scratch);
     cudaFreeAsync(d_part, s);
-    cudaError_t e = cudaStreamSynchronize(s);
-    if (e == cudaSuccess) e = cudaGetLastError();
-    if (e != cudaSuccess) {
-        st_set_error("st_sample_moments: %s", cudaGetErrorString(e));
-        return ST_ERR_CUDA;
-    }
-    out->sx = h[0]; out->sy = h[1]; out->sxx = h[2]; out->syy = h[3]; out->sxy = h[4];
-    return ST_OK;
+    return finish_moments(lane, s, nccl_comm, "st_sample_moments", x0, y0, out);
+}
+
+extern "C" int st_sample_moments(const st_tree *ta, const st_tree *tb, const int64_t *linklist,
+                                 int64_t L, uint64_t seed, int64_t first_sample, int64_t n_samples,
+                                 double x0, double y0, st_moments *out) {
+    TempLinks tl;
+    int rc = st_links_create(ta, tb, linklist, L, &tl.k);
+    if (rc != ST_OK) return rc;
+    return st_links_sample_moments(tl.k, seed, first_sample, n_samples, x0, y0, nullptr, out);
 }
 
 // ------------------------------------- exhaustive link pairs, fused moments --
@@ -562,13 +658,15 @@ k_linked_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ 
     }
 }
 
-extern "C" int st_linked_moments(const st_tree *ta, const st_tree *tb, const int64_t *linklist,
-                                 int64_t L, int64_t first_pair, int64_t n_pairs, double x0, double y0,
-                                 st_moments *out) {
-    int rc = check_pair_of_trees(ta, tb, linklist, L);
-    if (rc != ST_OK) return rc;
-    const int64_t total = L * (L - 1) / 2;
-    if (!out || first_pair < 0 || n_pairs < 0 || first_pair + n_pairs > total) {
+extern "C" int st_links_linked_moments(const st_links *k, int64_t first_pair, int64_t n_pairs, double x0,
+                                       double y0, void *nccl_comm, st_moments *out) {
+    if (!k || !out) {
+        st_set_error("st_linked_moments: NULL handle or output");
+        return ST_ERR_INVALID_ARG;
+    }
+    const st_tree *ta = k->ta, *tb = k->tb;
+    const int64_t L = k->L, total = L * (L - 1) / 2;
+    if (first_pair < 0 || n_pairs < 0 || first_pair + n_pairs > total) {
         st_set_error("st_linked_moments: bad arguments (pairs [%lld, %lld) of %lld)", (long long)first_pair,
                      (long long)(first_pair + n_pairs), (long long)total);
         return ST_ERR_INVALID_ARG;
@@ -577,22 +675,21 @@ extern "C" int st_linked_moments(const st_tree *ta, const st_tree *tb, const int
     out->x0 = x0;
     out->y0 = y0;
     out->sx = out->sy = out->sxx = out->syy = out->sxy = 0.0;
-    if (n_pairs == 0) return ST_OK;
+    if (n_pairs == 0 && !nccl_comm) return ST_OK;
     DeviceGuard g(ta->device);
-    DevLinks dl;
-    rc = upload_links(ta, tb, linklist, L, dl, false, true);
-    if (rc != ST_OK) return rc;
+    LaneGuard lg(ta->device);
+    HostLane *lane = lg.lane;
+    if (!lane) return ST_ERR_CUDA;
     const int smem = ((ta->query_smem_bytes + 15) & ~15) + tb->query_smem_bytes;
-    int grid = int(std::min<int64_t>((n_pairs + MLT - 1) / MLT, int64_t(ta->sm_count)));
-    cudaStream_t s = ta->streams[0];
+    int grid = int(std::max<int64_t>(1, std::min<int64_t>((n_pairs + MLT - 1) / MLT, int64_t(ta->sm_count))));
+    cudaStream_t s = lane->streams[0];
     double *d_part = nullptr;
-    ST_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d_part), size_t(grid + 1) * 5 * 8, s));
-    double *d_out = d_part + size_t(grid) * 5;
+    ST_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d_part), size_t(grid) * 5 * 8, s));
     int rc_launch = ST_OK;
-#define ST_LAUNCH_LINKED(MA, MB)                                                                  \
-    rc_launch = set_smem(k_linked_moments<MA, MB>, smem);                                         \
-    if (rc_launch == ST_OK)                                                                       \
-        k_linked_moments<MA, MB><<<grid, MLT, smem, s>>>(ta->view, tb->view, dl.rows, first_pair, \
+#define ST_LAUNCH_LINKED(MA, MB)                                                                 \
+    rc_launch = st_raise_smem(k_linked_moments<MA, MB>, ta->device, smem);                       \
+    if (rc_launch == ST_OK)                                                                      \
+        k_linked_moments<MA, MB><<<grid, MLT, smem, s>>>(ta->view, tb->view, k->rows, first_pair, \
                                                          n_pairs, x0, y0, d_part)
     ST_DISPATCH_MODES(tree_mode(ta), tree_mode(tb), ST_LAUNCH_LINKED);
 #undef ST_LAUNCH_LINKED
@@ -600,18 +697,18 @@ extern "C" int st_linked_moments(const st_tree *ta, const st_tree *tb, const int
         cudaFreeAsync(d_part, s);
         return rc_launch;
     }
-    k_reduce_partials<<<1, 160, 0, s>>>(grid, d_part, d_out);
-    double h[5];
-    cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, s);
+    k_reduce_partials<<<1, 160, 0, s>>>(grid, d_part, double(n_pairs), lane->d_scratch);
     cudaFreeAsync(d_part, s);
-    cudaError_t e = cudaStreamSynchronize(s);
-    if (e == cudaSuccess) e = cudaGetLastError();
-    if (e != cudaSuccess) {
-        st_set_error("st_linked_moments: %s", cudaGetErrorString(e));
-        return ST_ERR_CUDA;
-    }
-    out->sx = h[0]; out->sy = h[1]; out->sxx = h[2]; out->syy = h[3]; out->sxy = h[4];
-    return ST_OK;
+    return finish_moments(lane, s, nccl_comm, "st_linked_moments", x0, y0, out);
+}
+
+extern "C" int st_linked_moments(const st_tree *ta, const st_tree *tb, const int64_t *linklist,
+                                 int64_t L, int64_t first_pair, int64_t n_pairs, double x0, double y0,
+                                 st_moments *out) {
+    TempLinks tl;
+    int rc = st_links_create(ta, tb, linklist, L, &tl.k);
+    if (rc != ST_OK) return rc;
+    return st_links_linked_moments(tl.k, first_pair, n_pairs, x0, y0, nullptr, out);
 }
 
 // ----------------------------------------------- per-clade scan, one launch --
@@ -793,7 +890,10 @@ extern "C" int st_clade_moments(const st_tree *ta, const st_tree *tb, const int6
     const int32_t n_items = int32_t(items.size());
 
     DeviceGuard g(ta->device);
-    cudaStream_t s = ta->streams[0];
+    LaneGuard lg(ta->device);
+    HostLane *lane = lg.lane;
+    if (!lane) return ST_ERR_CUDA;
+    cudaStream_t s = lane->streams[0];
     // one stream-ordered scratch block: rows | run_begin | items | item_begin | shift | partials | out5 | counter
     auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
     const size_t o_rows = 0, o_run = o_rows + al(size_t(L) * 8), o_items = o_run + al(size_t(n_elig) * 8),
@@ -832,7 +932,7 @@ extern "C" int st_clade_moments(const st_tree *ta, const st_tree *tb, const int6
                                                                  int32_t(n_elig), d_shift);
         int rc2 = ST_OK;
 #define ST_LAUNCH_CLADE(MA, MB)                                                                          \
-    rc2 = set_smem(k_clade_moments<MA, MB>, smem);                                                       \
+    rc2 = st_raise_smem(k_clade_moments<MA, MB>, ta->device, smem);                                                     \
     if (rc2 == ST_OK)                                                                                    \
         k_clade_moments<MA, MB><<<grid, MLT, smem, s>>>(ta->view, tb->view, d_rows, d_run, d_shift,      \
                                                         d_items, n_items, d_cnt, d_part)

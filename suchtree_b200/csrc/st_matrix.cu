@@ -21,6 +21,7 @@
 #include <algorithm>
 
 #include "st_device.cuh"
+#include "st_hostctx.cuh"
 
 static const int MT = 256;       // threads per CTA
 static const int TC = 2 * MT;    // columns per tile (two per thread -> 16-byte stores)
@@ -516,37 +517,48 @@ extern "C" int st_distance_matrix(const st_tree *t, const int64_t *ids, int64_t 
     }
     if (n == 0 || row_begin == row_end) return ST_OK;
     DeviceGuard g(t->device);
-    cudaStream_t s = out_on_device ? static_cast<cudaStream_t>(stream) : t->streams[0];
+    if (out_on_device && !ids)  // nothing of the host is involved: asynchronous on the caller's stream
+        return launch_matrix(t, nullptr, true, n, row_begin, row_end, out, static_cast<cudaStream_t>(stream));
+
+    // a host id list and/or a host result: this call's streams, scratch and status word
+    // come from a lane of the device's host context
+    LaneGuard lg(t->device);
+    HostLane *lane = lg.lane;
+    if (!lane) return ST_ERR_CUDA;
+    cudaStream_t s = out_on_device ? static_cast<cudaStream_t>(stream) : lane->streams[0];
 
     // node list -> device int32 (+ range check, + sortedness)
     int32_t *d_ids = nullptr;
     bool sorted = true;
-    int64_t *d_ids64 = nullptr;
-    int *d_flag = nullptr;
     int rc = ST_OK;
-    auto cleanup = [&]() {
-        cudaFree(d_ids);
-        cudaFree(d_ids64);
-        cudaFree(d_flag);
-    };
     if (ids) {
+        int64_t *d_ids64 = nullptr;
+        int *d_flag = nullptr;
         ST_CUDA(cudaMalloc(&d_ids, size_t(n) * 4));
         if (cudaMalloc(&d_ids64, size_t(n) * 8) != cudaSuccess || cudaMalloc(&d_flag, 4) != cudaSuccess) {
-            cleanup();
+            cudaFree(d_ids);
+            cudaFree(d_ids64);
             st_set_error("st_distance_matrix: cudaMalloc failed");
             return ST_ERR_NOMEM;
         }
         cudaMemcpyAsync(d_ids64, ids, size_t(n) * 8, cudaMemcpyHostToDevice, s);
         cudaMemsetAsync(d_flag, 0, 4, s);
         k_narrow_ids<<<unsigned((n + 255) / 256), 256, 0, s>>>(n, d_ids64, d_ids, int32_t(t->n_nodes),
-                                                              t->d_status, d_flag);
+                                                              lane->d_status, d_flag);
         int unsorted = 0;
         cudaMemcpyAsync(&unsorted, d_flag, 4, cudaMemcpyDeviceToHost, s);
-        bool bad = false;
-        rc = st_read_range_status(t, s, &bad);  // synchronises s
-        if (rc == ST_OK && bad) rc = ST_ERR_NODE_RANGE;
+        unsigned long long mxb = 0;
+        long long mnb = 0;
+        rc = st_lane_read_status(lane, s, &mxb, &mnb);  // synchronises s
+        cudaFree(d_ids64);
+        cudaFree(d_flag);
+        if (rc == ST_OK && (mxb != 0 || mnb != 0)) {
+            st_set_bad_node(mxb != 0 ? (int64_t)mxb : (int64_t)mnb);
+            st_set_error("node id %lld out of bounds (tree size %lld)", (long long)st_bad_node(), (long long)t->n_nodes);
+            rc = ST_ERR_NODE_RANGE;
+        }
         if (rc != ST_OK) {
-            cleanup();
+            cudaFree(d_ids);
             return rc;
         }
         sorted = !unsorted;
@@ -554,29 +566,34 @@ extern "C" int st_distance_matrix(const st_tree *t, const int64_t *ids, int64_t 
 
     if (out_on_device) {
         rc = launch_matrix(t, d_ids, sorted, n, row_begin, row_end, out, s);
-        if (d_ids) cudaStreamSynchronize(s);  // d_ids is freed below
-        cleanup();
+        cudaStreamSynchronize(s);  // d_ids is freed below
+        cudaFree(d_ids);
         return rc;
     }
 
-    // host output: row bands through two device buffers / two streams
-    std::lock_guard<std::mutex> lock(t->host_mu);
-    const int64_t band_bytes = int64_t(256) << 20;
+    // host output: row bands through two device buffers on two of the lane's streams -- the
+    // kernel of band k+1 runs while band k crosses PCIe.  A page-locked result (the Python
+    // shim's arrays come from the pinned pool) takes the D2H copies directly at PCIe rate;
+    // a pageable one goes through the driver's staged copy.
+    const int64_t band_bytes = int64_t(64) << 20;
     int64_t band_rows = std::max<int64_t>(TR, (band_bytes / (n * 8)) / TR * TR);
     band_rows = std::min<int64_t>(band_rows, ((row_end - row_begin) + TR - 1) / TR * TR);
     double *d_band[2] = {nullptr, nullptr};
     for (int i = 0; i < 2; ++i) {
-        if (cudaMalloc(&d_band[i], size_t(band_rows) * n * 8) != cudaSuccess) {
-            cudaFree(d_band[0]);
-            cleanup();
-            st_set_error("st_distance_matrix: cudaMalloc of a %lld-row band failed", (long long)band_rows);
+        if (cudaMallocAsync(reinterpret_cast<void **>(&d_band[i]), size_t(band_rows) * n * 8, lane->streams[i]) !=
+            cudaSuccess) {
+            cudaGetLastError();
+            if (d_band[0]) cudaFreeAsync(d_band[0], lane->streams[0]);
+            cudaStreamSynchronize(lane->streams[0]);
+            cudaFree(d_ids);
+            st_set_error("st_distance_matrix: device allocation of a %lld-row band failed", (long long)band_rows);
             return ST_ERR_NOMEM;
         }
     }
     int k = 0;
     for (int64_t r = row_begin; r < row_end && rc == ST_OK; r += band_rows, ++k) {
         const int b = k & 1;
-        cudaStream_t sb = t->streams[b];
+        cudaStream_t sb = lane->streams[b];
         const int64_t re = std::min(row_end, r + band_rows);
         rc = launch_matrix(t, d_ids, sorted, n, r, re, d_band[b], sb);
         if (rc != ST_OK) break;
@@ -586,8 +603,9 @@ extern "C" int st_distance_matrix(const st_tree *t, const int64_t *ids, int64_t 
             rc = ST_ERR_CUDA;
         }
     }
-    cudaStreamSynchronize(t->streams[0]);
-    cudaStreamSynchronize(t->streams[1]);
+    for (int i = 0; i < 2; ++i) cudaFreeAsync(d_band[i], lane->streams[i]);
+    cudaStreamSynchronize(lane->streams[0]);
+    cudaStreamSynchronize(lane->streams[1]);
     if (rc == ST_OK) {
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) {
@@ -595,8 +613,6 @@ extern "C" int st_distance_matrix(const st_tree *t, const int64_t *ids, int64_t 
             rc = ST_ERR_CUDA;
         }
     }
-    cudaFree(d_band[0]);
-    cudaFree(d_band[1]);
-    cleanup();
+    cudaFree(d_ids);
     return rc;
 }

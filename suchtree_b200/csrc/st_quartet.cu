@@ -10,6 +10,7 @@
 #include <algorithm>
 
 #include "st_device.cuh"
+#include "st_hostctx.cuh"
 
 static const int QQT = 256;
 
@@ -111,26 +112,29 @@ k_quartets(const TreeView tv, const int64_t *__restrict__ quartets, int64_t n,
 
 template <int M>
 static int launch_quartets_m(const st_tree *t, const int64_t *d_q, int64_t n, int64_t *d_out,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, RangeStatus *status) {
     auto kern = k_quartets<M>;
     const int smem = t->query_smem_bytes;
-    if (smem > 48 * 1024) ST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int rc = st_raise_smem(kern, t->device, smem);
+    if (rc != ST_OK) return rc;
     int per_sm = 0;
     ST_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, QQT, smem));
     if (per_sm < 1) per_sm = 1;
     const int grid = int(std::min<int64_t>((n + QQT - 1) / QQT, int64_t(t->sm_count) * per_sm));
     const int aligned = (reinterpret_cast<uintptr_t>(d_q) % 32 == 0) && (reinterpret_cast<uintptr_t>(d_out) % 32 == 0);
-    kern<<<grid, QQT, smem, stream>>>(t->view, d_q, n, d_out, aligned);
+    TreeView view = t->view;
+    if (status) view.status = status;
+    kern<<<grid, QQT, smem, stream>>>(view, d_q, n, d_out, aligned);
     ST_CUDA(cudaGetLastError());
     return ST_OK;
 }
 
 static int launch_quartets(const st_tree *t, const int64_t *d_q, int64_t n, int64_t *d_out,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, RangeStatus *status = nullptr) {
     if (n == 0) return ST_OK;
-    if (t->compact) return launch_quartets_m<1>(t, d_q, n, d_out, stream);
-    if (t->compact_tables) return launch_quartets_m<3>(t, d_q, n, d_out, stream);
-    return launch_quartets_m<0>(t, d_q, n, d_out, stream);
+    if (t->compact) return launch_quartets_m<1>(t, d_q, n, d_out, stream, status);
+    if (t->compact_tables) return launch_quartets_m<3>(t, d_q, n, d_out, stream, status);
+    return launch_quartets_m<0>(t, d_q, n, d_out, stream, status);
 }
 
 extern "C" int st_quartet_topologies_device(const st_tree *t, const int64_t *d_quartets, int64_t n,
@@ -153,21 +157,23 @@ extern "C" int st_quartet_topologies(const st_tree *t, const int64_t *quartets, 
     }
     if (n == 0) return ST_OK;
     DeviceGuard g(t->device);
-    std::lock_guard<std::mutex> lock(t->host_mu);
+    LaneGuard lg(t->device);
+    HostLane *lane = lg.lane;
+    if (!lane) return ST_ERR_CUDA;
     const bool contiguous = (s0 == 4 && s1 == 1);
     const int64_t C = std::min<int64_t>(n, int64_t(1) << 21);
     int64_t *d_in[2] = {nullptr, nullptr}, *d_o[2] = {nullptr, nullptr};
     int64_t *h_pack = nullptr;
     auto cleanup = [&]() {
         for (int i = 0; i < 2; ++i) {
-            if (d_in[i]) cudaFreeAsync(d_in[i], t->streams[i]);
-            if (d_o[i]) cudaFreeAsync(d_o[i], t->streams[i]);
+            if (d_in[i]) cudaFreeAsync(d_in[i], lane->streams[i]);
+            if (d_o[i]) cudaFreeAsync(d_o[i], lane->streams[i]);
         }
         if (h_pack) cudaFreeHost(h_pack);
     };
     for (int i = 0; i < 2; ++i) {
-        if (cudaMallocAsync(reinterpret_cast<void **>(&d_in[i]), size_t(C) * 32, t->streams[i]) != cudaSuccess ||
-            cudaMallocAsync(reinterpret_cast<void **>(&d_o[i]), size_t(C) * 32, t->streams[i]) != cudaSuccess) {
+        if (cudaMallocAsync(reinterpret_cast<void **>(&d_in[i]), size_t(C) * 32, lane->streams[i]) != cudaSuccess ||
+            cudaMallocAsync(reinterpret_cast<void **>(&d_o[i]), size_t(C) * 32, lane->streams[i]) != cudaSuccess) {
             cleanup();
             st_set_error("st_quartet_topologies: device allocation failed");
             return ST_ERR_NOMEM;
@@ -182,7 +188,7 @@ extern "C" int st_quartet_topologies(const st_tree *t, const int64_t *quartets, 
     int c = 0;
     for (int64_t done = 0; done < n && rc == ST_OK; ++c) {
         const int b = c & 1;
-        cudaStream_t st = t->streams[b];
+        cudaStream_t st = lane->streams[b];
         const int64_t m = std::min(C, n - done);
         const int64_t *src = quartets + done * s0;
         if (!contiguous) {
@@ -197,7 +203,7 @@ extern "C" int st_quartet_topologies(const st_tree *t, const int64_t *quartets, 
             rc = ST_ERR_CUDA;
             break;
         }
-        rc = launch_quartets(t, d_in[b], m, d_o[b], st);
+        rc = launch_quartets(t, d_in[b], m, d_o[b], st, lane->d_status);
         if (rc != ST_OK) break;
         if (cudaMemcpyAsync(out + done * 4, d_o[b], size_t(m) * 32, cudaMemcpyDeviceToHost, st) != cudaSuccess) {
             st_set_error("st_quartet_topologies: D2H copy failed");
@@ -205,15 +211,22 @@ extern "C" int st_quartet_topologies(const st_tree *t, const int64_t *quartets, 
         }
         done += m;
     }
-    cudaError_t e0 = cudaStreamSynchronize(t->streams[0]), e1 = cudaStreamSynchronize(t->streams[1]);
+    cudaError_t e0 = cudaStreamSynchronize(lane->streams[0]), e1 = cudaStreamSynchronize(lane->streams[1]);
     cleanup();
     if (rc == ST_OK && (e0 != cudaSuccess || e1 != cudaSuccess)) {
         st_set_error("st_quartet_topologies: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
         rc = ST_ERR_CUDA;
     }
+    unsigned long long mxb = 0;
+    long long mnb = 0;
+    const int rc2 = st_lane_read_status(lane, lane->streams[0], &mxb, &mnb);  // also clears the word for the next call
     if (rc != ST_OK) return rc;
-    bool bad = false;
-    rc = st_read_range_status(t, t->streams[0], &bad);
-    if (rc != ST_OK) return rc;
-    return bad ? ST_ERR_NODE_RANGE : ST_OK;
+    if (rc2 != ST_OK) return rc2;
+    if (mxb != 0 || mnb != 0) {
+        // the reference reports max_id when it is >= size, else min_id (MuchTree.pyx:1303-1310)
+        st_set_bad_node(mxb != 0 ? (int64_t)mxb : (int64_t)mnb);
+        st_set_error("node id %lld out of bounds (tree size %lld)", (long long)st_bad_node(), (long long)t->n_nodes);
+        return ST_ERR_NODE_RANGE;
+    }
+    return ST_OK;
 }

@@ -23,6 +23,7 @@
 #endif
 
 #include "st_device.cuh"
+#include "st_hostctx.cuh"
 #include "st_hostpool.cuh"
 
 // P pairs per thread per iteration, fetched as raw 64-bit words by 16-byte (P = 2,
@@ -179,7 +180,7 @@ k_pairs(const TreeView tv, const IdxT *__restrict__ pairs, int64_t n, double *__
 // ------------------------------------------------------------------ launch --
 template <typename IdxT, int P, int M>
 static int launch_variant_m(const st_tree *t, const void *d_pairs, int64_t n, double *d_out,
-                            int32_t *d_mrca, cudaStream_t stream) {
+                            int32_t *d_mrca, cudaStream_t stream, RangeStatus *status) {
     // 2 pairs/thread: 2 x 512 threads x 64 registers; 4 pairs/thread needs ~80 registers:
     // 3 x 256 threads (8 gathers in flight per thread)
 #ifndef ST_QT_P2
@@ -208,17 +209,19 @@ static int launch_variant_m(const st_tree *t, const void *d_pairs, int64_t n, do
     int64_t want = (items + QT - 1) / QT;
     int grid = int(std::min<int64_t>(want, int64_t(t->sm_count) * per_sm));
     if (grid < 1) grid = 1;
-    kern<<<grid, QT, smem, stream>>>(t->view, static_cast<const IdxT *>(d_pairs), n, d_out, d_mrca);
+    TreeView view = t->view;
+    if (status) view.status = status;  // host calls bring their own status word (st_hostctx.cuh)
+    kern<<<grid, QT, smem, stream>>>(view, static_cast<const IdxT *>(d_pairs), n, d_out, d_mrca);
     ST_CUDA(cudaGetLastError());
     return ST_OK;
 }
 
 template <typename IdxT, int P>
 static int launch_variant(const st_tree *t, const void *d_pairs, int64_t n, double *d_out,
-                          int32_t *d_mrca, cudaStream_t stream) {
-    if (t->compact) return launch_variant_m<IdxT, P, 1>(t, d_pairs, n, d_out, d_mrca, stream);
-    if (t->compact_tables) return launch_variant_m<IdxT, P, 3>(t, d_pairs, n, d_out, d_mrca, stream);
-    return launch_variant_m<IdxT, P, 0>(t, d_pairs, n, d_out, d_mrca, stream);
+                          int32_t *d_mrca, cudaStream_t stream, RangeStatus *status) {
+    if (t->compact) return launch_variant_m<IdxT, P, 1>(t, d_pairs, n, d_out, d_mrca, stream, status);
+    if (t->compact_tables) return launch_variant_m<IdxT, P, 3>(t, d_pairs, n, d_out, d_mrca, stream, status);
+    return launch_variant_m<IdxT, P, 0>(t, d_pairs, n, d_out, d_mrca, stream, status);
 }
 
 static int st_pairs_per_thread() {  // SUCHTREE_B200_PPT = 1 | 2 | 4 (experiments)
@@ -231,7 +234,7 @@ static int st_pairs_per_thread() {  // SUCHTREE_B200_PPT = 1 | 2 | 4 (experiment
 }
 
 int st_launch_pairs(const st_tree *t, const void *d_pairs, int idx_bits, int64_t n, double *d_out,
-                    int32_t *d_mrca, cudaStream_t stream) {
+                    int32_t *d_mrca, cudaStream_t stream, RangeStatus *status) {
     if (n == 0) return ST_OK;
     if (idx_bits != 32 && idx_bits != 64) {
         st_set_error("idx_bits must be 32 or 64 (got %d)", idx_bits);
@@ -244,13 +247,13 @@ int st_launch_pairs(const st_tree *t, const void *d_pairs, int idx_bits, int64_t
     };
     const int ppt = st_pairs_per_thread();
     if (idx_bits == 32) {
-        if (ppt >= 4 && aligned(32, 32, 16)) return launch_variant<int32_t, 4>(t, d_pairs, n, d_out, d_mrca, stream);
-        if (ppt >= 2 && aligned(16, 16, 8)) return launch_variant<int32_t, 2>(t, d_pairs, n, d_out, d_mrca, stream);
-        return launch_variant<int32_t, 1>(t, d_pairs, n, d_out, d_mrca, stream);
+        if (ppt >= 4 && aligned(32, 32, 16)) return launch_variant<int32_t, 4>(t, d_pairs, n, d_out, d_mrca, stream, status);
+        if (ppt >= 2 && aligned(16, 16, 8)) return launch_variant<int32_t, 2>(t, d_pairs, n, d_out, d_mrca, stream, status);
+        return launch_variant<int32_t, 1>(t, d_pairs, n, d_out, d_mrca, stream, status);
     }
-    if (ppt >= 4 && aligned(32, 32, 16)) return launch_variant<int64_t, 4>(t, d_pairs, n, d_out, d_mrca, stream);
-    if (ppt >= 2 && aligned(32, 16, 8)) return launch_variant<int64_t, 2>(t, d_pairs, n, d_out, d_mrca, stream);
-    return launch_variant<int64_t, 1>(t, d_pairs, n, d_out, d_mrca, stream);
+    if (ppt >= 4 && aligned(32, 32, 16)) return launch_variant<int64_t, 4>(t, d_pairs, n, d_out, d_mrca, stream, status);
+    if (ppt >= 2 && aligned(32, 16, 8)) return launch_variant<int64_t, 2>(t, d_pairs, n, d_out, d_mrca, stream, status);
+    return launch_variant<int64_t, 1>(t, d_pairs, n, d_out, d_mrca, stream, status);
 }
 
 int st_read_range_status(const st_tree *t, cudaStream_t stream, bool *bad) {
@@ -338,53 +341,17 @@ extern "C" int st_random_leaf_pairs_device(const st_tree *t, uint64_t seed, int6
 }
 
 // -------------------------------------------------------------- host API ----
-// Chunked 3-slot pipeline: pack(chunk c+1) on the host pool | H2D + kernel + D2H of
-// chunk c on one of three streams | copy-out(chunk c-2).  The caller's int64 ids
-// (the drop-in dtype, any strides, pageable or pinned) are packed to int32 into
-// pinned staging by the host thread pool: half the PCIe bytes (8 instead of 16 per
-// pair), which is what bounds this path.  Results go straight to the caller's
-// buffer when it is pinned, else through pinned staging + a parallel copy.
-// With too few host threads and a pinned contiguous input, the int64 array is
-// copied as it is and the kernel reads int64 (no host pass at all).
-static const int64_t ST_STAGE_PAIRS_MAX = int64_t(1) << 22;
-
-static bool is_pinned(const void *p) {
-    if (!p) return false;
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
-    }
-    return a.type == cudaMemoryTypeHost;
-}
-
-static int ensure_stage(const st_tree *t, int64_t n, bool need_h_in, bool need_h_out) {
-    int64_t want = 4096;
-    while (want < n && want < ST_STAGE_PAIRS_MAX) want <<= 1;
-    if (want > t->stage_pairs) {
-        for (int i = 0; i < 3; ++i) {
-            cudaFree(t->d_stage_in[i]);
-            cudaFree(t->d_stage_out[i]);
-            cudaFree(t->d_stage_out2[i]);
-            if (t->h_stage[i]) cudaFreeHost(t->h_stage[i]);
-            if (t->h_out_stage[i]) cudaFreeHost(t->h_out_stage[i]);
-            t->d_stage_in[i] = t->d_stage_out[i] = t->d_stage_out2[i] = t->h_stage[i] = t->h_out_stage[i] = nullptr;
-        }
-        t->stage_pairs = 0;
-        for (int i = 0; i < 3; ++i) {
-            ST_CUDA(cudaMalloc(&t->d_stage_in[i], size_t(want) * 16));
-            ST_CUDA(cudaMalloc(&t->d_stage_out[i], size_t(want) * 8));
-            ST_CUDA(cudaMalloc(&t->d_stage_out2[i], size_t(want) * 4));
-        }
-        t->stage_pairs = want;
-    }
-    for (int i = 0; i < 3; ++i) {
-        if (need_h_in && !t->h_stage[i]) ST_CUDA(cudaMallocHost(&t->h_stage[i], size_t(t->stage_pairs) * 16));
-        if (need_h_out && !t->h_out_stage[i])
-            ST_CUDA(cudaMallocHost(&t->h_out_stage[i], size_t(t->stage_pairs) * 8));
-    }
-    return ST_OK;
-}
+// Chunked 3-slot pipeline on a LANE of the device's host context (st_hostctx.cuh):
+// pack(chunk c+1) on the host pool | H2D + kernel + D2H of chunk c on one of the lane's
+// three streams | copy-out(chunk c-2).  The caller's int64 ids (the drop-in dtype, any
+// strides, pageable or pinned) are packed to int32 into pinned staging by the host
+// thread pool: half the PCIe bytes (8 instead of 16 per pair).  Results go straight to
+// the caller's buffer when it is page-locked (the Python shim's result arrays come from
+// the pinned pool, st_host_alloc), else through pinned staging + a parallel copy.
+// A pinned (or registered) contiguous input is partly DMA'd as it is and read by the
+// int64 kernel variant (no host pass over that part).
+// Every call owns its lane's range-status word: concurrent callers on one tree neither
+// queue on a mutex nor see each other's out-of-range flags.
 
 // int64 ids -> int32, OR of everything seen (bit 31 and above set <=> some id is
 // negative or >= 2^31: the rare error path then finds the exact id)
@@ -469,14 +436,10 @@ static void report_range(const int64_t *src, int64_t s0, int64_t s1, int64_t n, 
 // Latency path for small and medium calls (distance(a,b), common_ancestor(a,b), lists up to
 // 2^18 pairs): the ids are packed on the host into pinned staging, ONE kernel reads them and
 // writes the results through the pinned mappings (zero-copy over PCIe), one synchronisation.
-static const int64_t ST_SMALL_CALL = 4096;      // host-side range check, scalar pack
-static const int64_t ST_MEDIUM_CALL = 262144;   // pool pack, device-side range check
-
-static int host_pairs_small(const st_tree *t, const int64_t *pairs, int64_t s0, int64_t s1, int64_t n,
-                            double *out_d, int32_t *out_m) {
-    int rc = ensure_stage(t, n, true, true);
-    if (rc != ST_OK) return rc;
-    int32_t *hp = static_cast<int32_t *>(t->h_stage[0]);
+static int host_pairs_small(const st_tree *t, HostLane *lane, const int64_t *pairs, int64_t s0, int64_t s1,
+                            int64_t n, double *out_d, int32_t *out_m) {
+    int rc = ST_OK;
+    int32_t *hp = static_cast<int32_t *>(lane->h_small_in);
     const bool tiny = n <= ST_SMALL_CALL;
     if (tiny) {
         int64_t mx = INT64_MIN, mn = INT64_MAX;
@@ -497,22 +460,20 @@ static int host_pairs_small(const st_tree *t, const int64_t *pairs, int64_t s0, 
         report_range(pairs, s0, s1, n, 2, t->n_nodes);
         return ST_ERR_NODE_RANGE;
     }
-    void *ho = t->h_out_stage[0];
-    cudaStream_t st = t->streams[0];
+    void *ho = lane->h_small_out;
+    cudaStream_t st = lane->streams[0];
     rc = st_launch_pairs(t, hp, 32, n, out_d ? static_cast<double *>(ho) : nullptr,
-                         out_m ? static_cast<int32_t *>(ho) : nullptr, st);
+                         out_m ? static_cast<int32_t *>(ho) : nullptr, st, lane->d_status);
     if (rc != ST_OK) return rc;
     if (tiny) {
-        ST_CUDA(cudaStreamSynchronize(st));
+        ST_CUDA(cudaStreamSynchronize(st));  // ids were checked on the host: the status word stays clear
     } else {
-        // ids in [n_nodes, 2^31) are caught by the kernel: its status word rides the same
-        // stream (a copy to pageable memory returns when it has completed: one wait in all)
-        RangeStatus h{};
-        ST_CUDA(cudaMemcpyAsync(&h, t->d_status, sizeof(h), cudaMemcpyDeviceToHost, st));
-        ST_CUDA(cudaStreamSynchronize(st));
-        if (h.max_bad != 0 || h.min_bad != 0) {
-            ST_CUDA(cudaMemsetAsync(t->d_status, 0, sizeof(RangeStatus), st));
-            ST_CUDA(cudaStreamSynchronize(st));
+        // ids in [n_nodes, 2^31) are caught by the kernel: the lane's status word rides the same stream
+        unsigned long long mxb = 0;
+        long long mnb = 0;
+        rc = st_lane_read_status(lane, st, &mxb, &mnb);
+        if (rc != ST_OK) return rc;
+        if (mxb != 0 || mnb != 0) {
             report_range(pairs, s0, s1, n, 2, t->n_nodes);
             return ST_ERR_NODE_RANGE;
         }
@@ -526,21 +487,24 @@ static int host_pairs_small(const st_tree *t, const int64_t *pairs, int64_t s0, 
 
 static int host_pairs_run(const st_tree *t, const int64_t *pairs, int64_t s0, int64_t s1, int64_t n,
                           double *out_d, int32_t *out_m) {
-    if (!t || n < 0 || (n > 0 && (!pairs || (!out_d && !out_m)))) {
+    if (!t || n < 0 || (n > 0 && (!pairs || (!out_d == !out_m)))) {  // exactly one output
         st_set_error("bad arguments (NULL pointer or negative n)");
         return ST_ERR_INVALID_ARG;
     }
     if (n == 0) return ST_OK;
     DeviceGuard g(t->device);
-    std::lock_guard<std::mutex> lock(t->host_mu);
-    if (n <= ST_MEDIUM_CALL && !(out_d && out_m)) return host_pairs_small(t, pairs, s0, s1, n, out_d, out_m);
+    LaneGuard lg(t->device);
+    HostLane *lane = lg.lane;
+    if (!lane) return ST_ERR_CUDA;
+    if (n <= ST_MEDIUM_CALL) return host_pairs_small(t, lane, pairs, s0, s1, n, out_d, out_m);
     const bool contiguous = (s1 == 1 && s0 == 2);
-    const bool out_pinned = is_pinned(out_d ? static_cast<void *>(out_d) : static_cast<void *>(out_m));
+    const bool out_pinned = st_is_pinned(out_d ? static_cast<void *>(out_d) : static_cast<void *>(out_m));
+    const bool in_pinned = contiguous && st_is_pinned(pairs) && st_is_pinned(pairs + 2 * n - 1);
     bool pack = true;
-    if (contiguous && st_host_threads() < 4 && is_pinned(pairs)) pack = false;
+    if (in_pinned && st_host_threads() < 4) pack = false;
     if (const char *e = getenv("SUCHTREE_B200_HOST_PATH")) {
-        if (e[0] == 'd' && contiguous) pack = false;  // "direct"
-        if (e[0] == 'p') pack = true;                 // "pack"
+        if (e[0] == 'd' && in_pinned) pack = false;  // "direct"
+        if (e[0] == 'p') pack = true;                // "pack"
     }
     // hybrid: PCIe wants the ids packed (8 instead of 16 B/pair), host memory bandwidth
     // wants them left alone (packing costs 24 B/pair of host traffic on top of the DMA's):
@@ -551,76 +515,93 @@ static int host_pairs_run(const st_tree *t, const int64_t *pairs, int64_t s0, in
     if (const char *e = getenv("LOCAL_WORLD_SIZE"))
         if (atoi(e) > 1) pack_fraction = 0.0;
     if (const char *e = getenv("SUCHTREE_B200_PACK_FRACTION")) pack_fraction = std::min(1.0, std::max(0.0, atof(e)));
-    const bool hybrid = pack && contiguous && pack_fraction < 1.0 && is_pinned(pairs);
-    int rc = ensure_stage(t, n, pack, !out_pinned);
+    const bool hybrid = pack && pack_fraction < 1.0 && in_pinned;
+    int rc = st_lane_ensure_stage(lane, n, pack, !out_pinned);
     if (rc != ST_OK) return rc;
-    const int64_t C = t->stage_pairs;
+    const int64_t C = lane->stage_pairs;
     const size_t out_elem = out_d ? 8 : 4;
     char *user_out = out_d ? reinterpret_cast<char *>(out_d) : reinterpret_cast<char *>(out_m);
-    int64_t chunk_begin[3] = {0, 0, 0}, chunk_len[3] = {0, 0, 0};
+    int64_t chunk_begin[ST_LANE_SLOTS] = {0, 0, 0}, chunk_len[ST_LANE_SLOTS] = {0, 0, 0};
     auto copy_out = [&](int s) {  // results of the chunk last issued on slot s -> caller's buffer
         if (!out_pinned && chunk_len[s] > 0)
-            parallel_copy(user_out + size_t(chunk_begin[s]) * out_elem, t->h_out_stage[s],
+            parallel_copy(user_out + size_t(chunk_begin[s]) * out_elem, lane->h_out[s],
                           size_t(chunk_len[s]) * out_elem);
         chunk_len[s] = 0;
+    };
+    auto quiesce = [&]() {  // error exits: nothing of this call may still be in flight on the lane
+        for (int k = 0; k < ST_LANE_SLOTS; ++k) cudaStreamSynchronize(lane->streams[k]);
+        unsigned long long mxb = 0;
+        long long mnb = 0;
+        st_lane_read_status(lane, lane->streams[0], &mxb, &mnb);  // clears anything the kernels flagged
     };
     int64_t done = 0;
     int c = 0;
     for (; done < n; ++c) {
-        const int s = c % 3;
+        const int s = c % ST_LANE_SLOTS;
         const int64_t m = std::min(C, n - done);
-        cudaStream_t st = t->streams[s];
-        if (c >= 3) {
-            ST_CUDA(cudaEventSynchronize(t->ev[s]));  // slot s: device buffers and staging are free again
+        cudaStream_t st = lane->streams[s];
+        if (c >= ST_LANE_SLOTS) {
+            ST_CUDA(cudaEventSynchronize(lane->ev[s]));  // slot s: device buffers and staging are free again
             copy_out(s);
         }
         const int64_t *src = pairs + done * s0;
-        double *dd_out = out_d ? static_cast<double *>(t->d_stage_out[s]) : nullptr;
-        int32_t *dm_out = out_m ? static_cast<int32_t *>(t->d_stage_out2[s]) : nullptr;
+        double *dd_out = out_d ? static_cast<double *>(lane->d_out[s]) : nullptr;
+        int32_t *dm_out = out_m ? static_cast<int32_t *>(lane->d_out2[s]) : nullptr;
         // first mp pairs: packed to int32 by the host pool; the rest (hybrid mode, pinned
         // contiguous input): DMA'd as int64 while the pool packs
         const int64_t mp = pack ? (hybrid ? (int64_t(double(m) * pack_fraction) & ~int64_t(3)) : m) : 0;
-        char *d_in = static_cast<char *>(t->d_stage_in[s]);
+        char *d_in = static_cast<char *>(lane->d_in[s]);
         if (mp < m)
             ST_CUDA(cudaMemcpyAsync(d_in + size_t(mp) * 8, src + 2 * mp, size_t(m - mp) * 16,
                                     cudaMemcpyHostToDevice, st));
         if (mp > 0) {
-            int32_t *hp = static_cast<int32_t *>(t->h_stage[s]);
+            int32_t *hp = static_cast<int32_t *>(lane->h_in[s]);
             const uint64_t acc = pack_pairs(src, s0, s1, mp, hp, 2);
             if (acc >> 31) {  // a negative id, or one beyond int32: cannot be a node of any tree
-                for (int k = 0; k < 3; ++k) cudaStreamSynchronize(t->streams[k]);
-                bool dummy = false;
-                st_read_range_status(t, t->streams[0], &dummy);  // clear anything the kernels flagged
+                quiesce();
                 report_range(pairs, s0, s1, n, 2, t->n_nodes);
                 return ST_ERR_NODE_RANGE;
             }
             ST_CUDA(cudaMemcpyAsync(d_in, hp, size_t(mp) * 8, cudaMemcpyHostToDevice, st));
-            rc = st_launch_pairs(t, d_in, 32, mp, dd_out, dm_out, st);
-            if (rc != ST_OK) return rc;
+            rc = st_launch_pairs(t, d_in, 32, mp, dd_out, dm_out, st, lane->d_status);
+            if (rc != ST_OK) {
+                quiesce();
+                return rc;
+            }
         }
         if (mp < m) {
             rc = st_launch_pairs(t, d_in + size_t(mp) * 8, 64, m - mp, dd_out ? dd_out + mp : nullptr,
-                                 dm_out ? dm_out + mp : nullptr, st);
-            if (rc != ST_OK) return rc;
+                                 dm_out ? dm_out + mp : nullptr, st, lane->d_status);
+            if (rc != ST_OK) {
+                quiesce();
+                return rc;
+            }
         }
-        void *dst = out_pinned ? static_cast<void *>(user_out + size_t(done) * out_elem) : t->h_out_stage[s];
+        void *dst = out_pinned ? static_cast<void *>(user_out + size_t(done) * out_elem) : lane->h_out[s];
         const void *dsrc = out_d ? static_cast<const void *>(dd_out) : static_cast<const void *>(dm_out);
         ST_CUDA(cudaMemcpyAsync(dst, dsrc, size_t(m) * out_elem, cudaMemcpyDeviceToHost, st));
-        ST_CUDA(cudaEventRecord(t->ev[s], st));
+        ST_CUDA(cudaEventRecord(lane->ev[s], st));
         chunk_begin[s] = done;
         chunk_len[s] = m;
         done += m;
     }
     // drain in issue order
-    for (int k = 0; k < 3 && k < c; ++k) {
-        const int s = (c - std::min(c, 3) + k) % 3;
-        ST_CUDA(cudaStreamSynchronize(t->streams[s]));
+    for (int k = 0; k < ST_LANE_SLOTS && k < c; ++k) {
+        const int s = (c - std::min(c, ST_LANE_SLOTS) + k) % ST_LANE_SLOTS;
+        ST_CUDA(cudaStreamSynchronize(lane->streams[s]));
         copy_out(s);
     }
-    bool bad = false;
-    rc = st_read_range_status(t, t->streams[0], &bad);
+    unsigned long long mxb = 0;
+    long long mnb = 0;
+    rc = st_lane_read_status(lane, lane->streams[0], &mxb, &mnb);
     if (rc != ST_OK) return rc;
-    return bad ? ST_ERR_NODE_RANGE : ST_OK;
+    if (mxb != 0 || mnb != 0) {
+        // the reference reports max_id when it is >= size, else min_id (MuchTree.pyx:899-903)
+        st_set_bad_node(mxb != 0 ? (int64_t)mxb : (int64_t)mnb);
+        st_set_error("node id %lld out of bounds (tree size %lld)", (long long)st_bad_node(), (long long)t->n_nodes);
+        return ST_ERR_NODE_RANGE;
+    }
+    return ST_OK;
 }
 
 // measurement helper: rate of the host-side id packing alone (pinned src and dst)

@@ -11,6 +11,7 @@ Link bookkeeping stays on the host (small, pandas-driven); every distance, the
 sampler's random stream and the moment reductions run in libsuchtree_b200.so.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -20,9 +21,12 @@ from .tree import SuchTree
 _UINT64_MAX = np.iinfo(np.uint64).max
 
 
-def pearson(x, y, device=0):
+def pearson(x, y, device=None):
     """Pearson correlation of two float64 vectors; MuchTree.pyx:81-87 (two-pass
-    formula of :62-79 with fp64 accumulators on the GPU)."""
+    formula of :62-79 with fp64 accumulators on the GPU).  device: default LOCAL_RANK
+    (one process per GPU), like SuchTree."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
     x = _as_f64_vector(x)
     y = _as_f64_vector(y)
     if not len(x) == len(y):
@@ -244,6 +248,32 @@ class SuchLinkedTrees:
     def _linklist_c(self):
         return np.ascontiguousarray(self.linklist, dtype=np.int64)
 
+    def _links(self):
+        """Device-resident link list (st_links handle) of the current subset; rebuilt only
+        when subset_a / subset_b changed the list."""
+        ver = self._subset_version
+        cur = getattr(self, "_links_handle", None)
+        if cur is None or cur[0] != ver:
+            self._drop_links()
+            h = C.c_void_p()
+            ll = self._linklist_c()
+            _lib.check(_lib.lib().st_links_create(self._TreeA._handle, self._TreeB._handle, ll.ctypes.data,
+                                                  self._subset_n_links, C.byref(h)))
+            self._links_handle = (ver, h)
+        return self._links_handle[1]
+
+    def _drop_links(self):
+        cur = getattr(self, "_links_handle", None)
+        if cur is not None and cur[1].value:
+            try:
+                _lib.lib().st_links_destroy(cur[1])
+            except Exception:
+                pass
+        self._links_handle = None
+
+    def __del__(self):
+        self._drop_links()
+
     # ---- linked_distances (:2900-2934) ---------------------------------------
     def linked_distances(self):
         L = self._subset_n_links
@@ -253,10 +283,8 @@ class SuchLinkedTrees:
         out_a = np.zeros(size, dtype=np.float64)
         out_b = np.zeros(size, dtype=np.float64)
         if size:
-            ll = self._linklist_c()
-            rc = _lib.lib().st_linked_distances(
-                self._TreeA._handle, self._TreeB._handle, ll.ctypes.data, L,
-                out_a.ctypes.data, out_b.ctypes.data, ids_a.ctypes.data, ids_b.ctypes.data)
+            rc = _lib.lib().st_links_linked_distances(
+                self._links(), out_a.ctypes.data, out_b.ctypes.data, ids_a.ctypes.data, ids_b.ctypes.data)
             _lib.check(rc)
         return {
             "TreeA": out_a,
@@ -278,7 +306,7 @@ class SuchLinkedTrees:
         sigma = float(np.float32(sigma))  # `float sigma` argument
         buckets, n, maxcycles = int(buckets), int(n), int(maxcycles)
         L = self._subset_n_links
-        ll = self._linklist_c()
+        links = self._links()
         sums_a = np.zeros(buckets)
         sums_b = np.zeros(buckets)
         sumsq_a = np.zeros(buckets)
@@ -291,8 +319,8 @@ class SuchLinkedTrees:
         while True:
             da = np.empty(buckets * n)
             db = np.empty(buckets * n)
-            rc = lib.st_sample_linked_cycle(
-                self._TreeA._handle, self._TreeB._handle, ll.ctypes.data, L, C.byref(seed), buckets, n,
+            rc = lib.st_links_sample_cycle(
+                links, C.byref(seed), buckets, n,
                 da.ctypes.data, db.ctypes.data, sums_a.ctypes.data, sumsq_a.ctypes.data,
                 sums_b.ctypes.data, sumsq_b.ctypes.data)
             self._seed = int(seed.value)
@@ -332,29 +360,30 @@ class SuchLinkedTrees:
         }
 
     # ---- throughput path (not in the reference API) --------------------------
-    def sample_moments(self, n_samples, seed=0, first_sample=0, x0=0.0, y0=0.0):
+    def sample_moments(self, n_samples, seed=0, first_sample=0, x0=0.0, y0=0.0, comm=None):
         """Philox-sampled link pairs, moments fused on the device; returns the
-        _lib.Moments struct (all-reduce its sums across ranks, then moments_pearson)."""
-        ll = self._linklist_c()
+        _lib.Moments struct.  comm: a shard.MomentComm (one process per GPU) -- the six sums
+        are then all-reduced by NCCL on the kernel's stream inside the call, and the struct
+        holds the moments of ALL ranks' samples (every rank must call, same x0 / y0)."""
         m = _lib.Moments()
-        rc = _lib.lib().st_sample_moments(
-            self._TreeA._handle, self._TreeB._handle, ll.ctypes.data, self._subset_n_links,
-            int(seed), int(first_sample), int(n_samples), float(x0), float(y0), C.byref(m))
+        rc = _lib.lib().st_links_sample_moments(
+            self._links(), int(seed), int(first_sample), int(n_samples), float(x0), float(y0),
+            None if comm is None else comm.handle, C.byref(m))
         _lib.check(rc)
         return m
 
-    def linked_moments(self, first_pair=0, n_pairs=None, x0=0.0, y0=0.0):
+    def linked_moments(self, first_pair=0, n_pairs=None, x0=0.0, y0=0.0, comm=None):
         """Moments of (d_A, d_B) over the link pairs [first_pair, first_pair + n_pairs) of
-        linked_distances()'s enumeration, fused on the device (nothing materialised)."""
+        linked_distances()'s enumeration, fused on the device (nothing materialised).
+        comm: as in sample_moments()."""
         L = self._subset_n_links
         total = (L * (L - 1)) // 2
         if n_pairs is None:
             n_pairs = total - first_pair
-        ll = self._linklist_c()
         m = _lib.Moments()
-        rc = _lib.lib().st_linked_moments(
-            self._TreeA._handle, self._TreeB._handle, ll.ctypes.data, L, int(first_pair), int(n_pairs),
-            float(x0), float(y0), C.byref(m))
+        rc = _lib.lib().st_links_linked_moments(
+            self._links(), int(first_pair), int(n_pairs), float(x0), float(y0),
+            None if comm is None else comm.handle, C.byref(m))
         _lib.check(rc)
         return m
 
@@ -457,10 +486,15 @@ class SuchLinkedTrees:
         return {"node_ids": nodes, "n_leafs": n_leafs, "n_links": n_links,
                 "n_pairs": cnt.astype(np.int64), "r": r}
 
-    def sample_pearson(self, n_samples, seed=0):
-        """Sampled two-tree Pearson r over n_samples link pairs drawn with replacement."""
-        m = self.sample_moments(n_samples, seed=seed)
-        return moments_pearson(m)
+    def sample_pearson(self, n_samples, seed=0, comm=None):
+        """Sampled two-tree Pearson r over n_samples link pairs drawn with replacement.
+        With comm (shard.MomentComm, one process per GPU) n_samples is the WHOLE job's
+        sample count: every rank draws its own contiguous share of the Philox stream, the
+        moments are all-reduced inside the call and every rank returns the same r."""
+        if comm is None:
+            return moments_pearson(self.sample_moments(n_samples, seed=seed))
+        b, e = shard.pair_range(comm.rank, comm.world, int(n_samples))
+        return moments_pearson(self.sample_moments(e - b, seed=seed, first_sample=b, comm=comm))
 
 
 def as_moments(row):

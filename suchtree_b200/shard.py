@@ -6,9 +6,53 @@ The index is replicated; work is partitioned with no data-path collective:
   * sampler   : disjoint Philox sample ranges                -> pair_range()
   * clade scan: clades dealt out by link-pair count           -> balanced_shares()
 The only exchange is the sampler's moment all-reduce (5 sums + n, fp64): NCCL over
-NVLink on GPUs, gloo in the CPU tests.
+NVLink on GPUs -- enqueued by the library on the moment kernel's own stream
+(MomentComm -> st_links_sample_moments(..., nccl_comm)) -- gloo in the CPU tests
+(allreduce_moments).
 """
 import ctypes as C
+
+
+class MomentComm:
+    """The library's own NCCL communicator for the moment all-reduce (one per process,
+    one process per GPU).  The 128-byte ncclUniqueId is made on rank 0 and handed to the
+    other ranks through torch.distributed (any backend: it is plumbing only)."""
+
+    def __init__(self, device, rank=None, world=None, group=None):
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+
+        self.rank = dist.get_rank(group) if rank is None else int(rank)
+        self.world = dist.get_world_size(group) if world is None else int(world)
+        ident = np.zeros(128, dtype=np.uint8)
+        if self.rank == 0:
+            _lib.check(_lib.lib().st_nccl_unique_id(ident.ctypes.data))
+        if dist.get_backend(group) == "nccl":
+            t = torch.from_numpy(ident).to(torch.device("cuda", int(device)))
+            dist.broadcast(t, src=0, group=group)
+            ident = t.cpu().numpy()
+        else:
+            t = torch.from_numpy(ident)
+            dist.broadcast(t, src=0, group=group)
+        self.handle = C.c_void_p()
+        _lib.check(_lib.lib().st_nccl_comm_create(int(device), self.world, self.rank, ident.ctypes.data,
+                                                  C.byref(self.handle)))
+
+    def close(self):
+        from . import _lib
+
+        if self.handle is not None and self.handle.value:
+            _lib.lib().st_nccl_comm_destroy(self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def pair_range(rank, world, n_total, align=2):

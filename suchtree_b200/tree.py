@@ -309,8 +309,16 @@ class SuchTree:
         return np.concatenate(out) if out else np.empty(0, np.int64)
 
     def get_descendants(self, node):
-        lo, hi = self._clade_interval(self._validate_node(node))
-        return np.arange(lo, hi + 1, dtype=np.int64)
+        """Generator over the ids of `node` and everything below it, in the reference's
+        order: the start node first, then breadth-first queue order (MuchTree.pyx:396-425)."""
+        left, right = self._ft.left, self._ft.right
+        to_visit = [self._validate_node(node)]
+        for cur in to_visit:  # the list grows while it is iterated, as in the reference
+            l = int(left[cur])
+            if l != -1:
+                to_visit.append(l)
+                to_visit.append(int(right[cur]))
+            yield int(cur)
 
     def traverse_preorder(self, from_node=None):
         """Node ids in preorder (root, left, right); MuchTree.pyx:1502-1536."""
@@ -343,7 +351,24 @@ class SuchTree:
         """Distance from a node to the root; MuchTree.pyx:813-850.  The reference walks
         to the root adding fp32 edges; here it is one lookup in the device-built root
         distances (fp64 sum of the same fp32-quantised edges)."""
-        return float(self._root_distances()[self._validate_node(node)])
+        node_id = self._validate_node(node)
+        if self._has_minus_one_edge():
+            # the reference's walk stops at the first edge whose length is exactly -1 (the
+            # root's sentinel, MuchTree.pyx:845-849) -- also when a real edge has that length
+            d, i = np.float32(0.0), node_id
+            dist, parent = self._ft.distance, self._ft.parent
+            while i != self._root and dist[i] != -1:
+                d = np.float32(d + dist[i])
+                i = int(parent[i])
+            return float(d)
+        return float(self._root_distances()[node_id])
+
+    def _has_minus_one_edge(self):
+        if getattr(self, "_minus_one_edge", None) is None:
+            m = np.asarray(self._ft.distance) == -1
+            m[self._root] = False
+            self._minus_one_edge = bool(m.any())
+        return self._minus_one_edge
 
     def get_distance_to_root(self, node):
         _deprecation_warning("get_distance_to_root()", "distance_to_root()")
@@ -442,7 +467,14 @@ class SuchTree:
         pairs = self._coerce_pairs(pairs)
         n = pairs.shape[0]
         if out is None:
-            result = np.empty(n, dtype=np.float64)
+            # a fresh array, as the reference returns (MuchTree.pyx:907); large ones come from
+            # the library's page-locked pool so that the D2H copies land in them directly
+            if n * 8 >= _lib.PINNED_RESULT_MIN_BYTES:
+                result = _lib.pinned_empty((n,), np.float64)
+            else:
+                result = np.empty(n, dtype=np.float64)
+            if pairs.flags.c_contiguous:
+                _lib.maybe_register(pairs)  # large inputs seen repeatedly are page-locked in place
         else:  # extension: caller-provided (e.g. pinned) float64 result buffer
             result = out
             if not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.shape == (n,)
@@ -642,7 +674,10 @@ class SuchTree:
         else:
             ids_ptr = np.array([self._validate_node(nd) for nd in nodes], dtype=np.int64)
             n = ids_ptr.shape[0]
-        out = np.zeros((n, n), dtype=np.float64)
+        if n * n * 8 >= _lib.PINNED_RESULT_MIN_BYTES:
+            out = _lib.pinned_empty((n, n), np.float64)  # every element is written by the kernels
+        else:
+            out = np.zeros((n, n), dtype=np.float64)
         if n:
             rc = _lib.lib().st_distance_matrix(
                 self._handle, None if ids_ptr is None else ids_ptr.ctypes.data, n, 0, n,

@@ -193,6 +193,21 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), name
     assert L.st_version() >= 100
+    # the binary was compiled from the sources on disk (a stale .so is rebuilt, never used)
+    from suchtree_b200 import build as B
+
+    assert L.st_build_id().decode() == B.source_id("product")
+
+
+def test_bench_library_exports_every_declared_symbol():
+    header = open(os.path.join(REPO, "include", "suchtree_b200_bench.h")).read()
+    declared = set(re.findall(r"^ST_BENCH_API [^;(]*?\b(st_[a-z0-9_]+)\(", header, flags=re.M))
+    assert declared == set(_lib.BENCH_SIGNATURES), declared ^ set(_lib.BENCH_SIGNATURES)
+    B = _lib.bench_lib()
+    for name in declared:
+        assert hasattr(B, name), name
+    # measurement tooling stays out of the product library
+    assert not hasattr(_lib.lib(), "st_bench_gather")
 
 
 def test_no_cpu_fallback_without_device():
