@@ -162,6 +162,9 @@ ST_API int st_quartet_topologies(const st_tree *tree, const int64_t *quartets, i
  * reported by the next st_check_range(). */
 ST_API int st_quartet_topologies_device(const st_tree *tree, const int64_t *d_quartets, int64_t n,
                                  int64_t *d_out, void *stream);
+/* the same with int32 ids in and out (32 instead of 64 streamed bytes per quartet) */
+ST_API int st_quartet_topologies_device32(const st_tree *tree, const int32_t *d_quartets, int64_t n,
+                                   int32_t *d_out, void *stream);
 
 /* deterministic synthetic input: n random leaf-id pairs (ids 2*k, k uniform in
  * [0, n_leaves)), Philox4x32-10 keyed by `seed`, counter = first_pair + i, as

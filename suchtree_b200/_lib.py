@@ -69,6 +69,7 @@ SIGNATURES = {
     "st_check_range": (_int, [_vp, _vp]),
     "st_quartet_topologies": (_int, [_vp, _vp, _i64, _i64, _i64, _vp]),
     "st_quartet_topologies_device": (_int, [_vp, _vp, _i64, _vp, _vp]),
+    "st_quartet_topologies_device32": (_int, [_vp, _vp, _i64, _vp, _vp]),
     "st_random_leaf_pairs_device": (_int, [_vp, _u64, _i64, _i64, _vp, _int, _vp]),
     "st_distance_matrix": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int, _vp]),
     "st_linked_distances": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),

@@ -315,7 +315,7 @@ extern "C" void st_tree_destroy(st_tree *t) {
     if (!t) return;
     DeviceGuard g(t->device);
     cudaFree(t->d_rec);
-    cudaFree(t->d_rec16);
+    cudaFree(t->d_rec16_base);
     cudaFree(t->d_depth);
     if (t->d_tables) {
         cudaFree(t->d_tables);  // d_stk / d_brd / d_stk32 / d_brd8 / d_bid point into it
@@ -551,8 +551,20 @@ extern "C" int st_tree_create_ex(int device, int64_t n_nodes, const int32_t *par
         if (const char *e = getenv("SUCHTREE_B200_LAYOUT"))
             if (e[0] == 't') inexact = 1;  // "tables": keep the wide records (experiments)
         if (!inexact) {
+            // Two 16-byte records share a 32-byte sector.  A leaf's parent is its in-order
+            // neighbour (id - 1 or id + 1): slot = id + shift with the shift that puts most leaves
+            // into the SAME sector as their parent, so that a query whose MRCA is the parent of
+            // one endpoint (ladder-like trees: always) finds rd[mrca] in a sector it loads anyway
+            // (st_ld_rec_paired).  n + 2 slots, zero padded: the paired load never leaves the array.
+            int64_t votes[2] = {0, 0};
+            for (int64_t v = 0; v < n_nodes; v += 2)
+                if (left[v] == -1 && parent[v] >= 0) ++votes[parent[v] == v + 1 ? 0 : 1];
+            t->rec16_shift = votes[1] > votes[0] ? 1 : 0;
+            if (const char *e = getenv("SUCHTREE_B200_REC_SHIFT")) t->rec16_shift = atoi(e) & 1;
             int64_t rbytes = 0;
-            ST_TRY2(dev_alloc(&t->d_rec16, size_t(n), &rbytes));
+            ST_TRY2(dev_alloc(&t->d_rec16_base, size_t(n) + 2, &rbytes));
+            ST_TRY2_CUDA(cudaMemsetAsync(t->d_rec16_base, 0, (size_t(n) + 2) * sizeof(NodeRec16), s));
+            t->d_rec16 = t->d_rec16_base + t->rec16_shift;
             k_compact_records<<<grid, TPB, 0, s>>>(n, bs, t->d_rec, t->d_rec16);
             ST_TRY2_CUDA(cudaGetLastError());
             ST_TRY2_CUDA(cudaDeviceSynchronize());

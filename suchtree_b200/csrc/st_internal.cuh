@@ -106,7 +106,9 @@ struct st_tree {
     int32_t *d_depth = nullptr;
     uint64_t *d_stk = nullptr;
     double2 *d_brd = nullptr;
-    NodeRec16 *d_rec16 = nullptr;
+    NodeRec16 *d_rec16 = nullptr;       // = d_rec16_base + rec16_shift: record of node v at slot v + shift
+    NodeRec16 *d_rec16_base = nullptr;  // allocation: n_nodes + 2 slots, zero padded, 32-byte aligned
+    int rec16_shift = 0;                // 0 | 1: chosen so that most leaves share a 32-byte sector with their parent
     uint32_t *d_stk32 = nullptr;
     double *d_brd8 = nullptr;
     int32_t *d_bid = nullptr;

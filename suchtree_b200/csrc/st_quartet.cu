@@ -1,127 +1,249 @@
 // Batched quartet topologies.
 //
 // Replaces SuchTree._quartet_topologies (MuchTree.pyx:1331-1376): six _mrca calls
-// per quartet (each an O(depth^2) pointer chase in the reference) become six
-// range-minimum lookups over the four endpoint records -- 4 random sectors (2 in
-// the compact layout's half-sector records) + 64 B streamed (int64x4 in, int64x4
-// out) per quartet.  The selection rule is the reference's, literally: C[j] = how
-// many of the six MRCAs equal M[j]; the first j with C[j] == 1 picks row j of the
-// permutation table I (:1319-1320); no such j -> row 5.
+// per quartet (each an O(depth^2) pointer chase in the reference) become THREE
+// range-minimum depth lookups over the four (sorted) endpoint records -- 4 random
+// sectors + 64 B streamed (int64x4 in, int64x4 out; 32 B with int32 ids on the device)
+// per quartet.  The selection rule is the reference's: C[j] = how many of the six
+// MRCAs equal M[j]; the first j with C[j] == 1 picks row j of the permutation table I
+// (:1319-1320); no such j -> row 5 -- with MRCA equality decided from depths (below).
 #include <algorithm>
+#include <cstdlib>
 
 #include "st_device.cuh"
 #include "st_hostctx.cuh"
 
 static const int QQT = 256;
+#ifndef ST_QPT_DEFAULT
+#define ST_QPT_DEFAULT 2
+#endif
 
-struct Quad {
-    long long v[4];
+// The reference's rule needs only the EQUALITY PATTERN of the six pair MRCAs, and that
+// follows from their DEPTHS alone: two MRCAs that share an endpoint lie on that endpoint's
+// root path, so they are the same node iff their depths are equal; for the three splits
+// into disjoint pairs, M(p,q) == M(r,s) iff the depths are equal and M(p,r) is at least as
+// deep (then both are the node at that depth on the common part of p's and r's root paths).
+// With the four ids sorted (x0 <= x1 <= x2 <= x3, in-order ranks), every pair's MRCA depth is
+// a minimum of the three ADJACENT range minima d1 = D(x0,x1), d2 = D(x1,x2), d3 = D(x2,x3):
+// three range-minimum lookups instead of six, no MRCA ids, no root distances -- 8 of the
+// record's 16 bytes (compact layout) per endpoint.
+template <typename IdxT>
+struct QuadT {
+    IdxT v[4];
 };
 
-__device__ __forceinline__ Quad quad_load(const int64_t *p, bool aligned) {
-    Quad q;
+template <typename IdxT>
+__device__ __forceinline__ QuadT<IdxT> quad_load(const IdxT *p, bool aligned) {
+    QuadT<IdxT> q;
     if (aligned) {
-        asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0,%1,%2,%3}, [%4];"
-                     : "=l"(q.v[0]), "=l"(q.v[1]), "=l"(q.v[2]), "=l"(q.v[3])
-                     : "l"(p));
+        if (sizeof(IdxT) == 8) {
+            uint64_t w[4];
+            st_ld_stream_256(p, w);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) q.v[k] = IdxT(w[k]);
+        } else {
+            const int4 w = st_ld_stream_int4(p);
+            q.v[0] = IdxT(w.x); q.v[1] = IdxT(w.y); q.v[2] = IdxT(w.z); q.v[3] = IdxT(w.w);
+        }
     } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) q.v[k] = __ldg(reinterpret_cast<const long long *>(p) + k);
+        for (int k = 0; k < 4; ++k) q.v[k] = __ldg(p + k);
     }
     return q;
 }
-__device__ __forceinline__ void quad_store(int64_t *p, bool aligned, long long a, long long b,
-                                           long long c, long long d) {
+template <typename IdxT>
+__device__ __forceinline__ void quad_store(IdxT *p, bool aligned, IdxT a, IdxT b, IdxT c, IdxT d) {
     if (aligned) {
-        asm volatile("st.global.L1::no_allocate.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b),
-                     "l"(c), "l"(d)
-                     : "memory");
+        if (sizeof(IdxT) == 8)
+            asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.b64 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p),
+                         "l"((long long)a), "l"((long long)b), "l"((long long)c), "l"((long long)d),
+                         "l"(st_policy_evict_first())
+                         : "memory");
+        else
+            st_st_stream_i32x4(reinterpret_cast<int32_t *>(p), int32_t(a), int32_t(b), int32_t(c), int32_t(d));
     } else {
         p[0] = a; p[1] = b; p[2] = c; p[3] = d;
     }
 }
 
+// (depth of the suffix argmin, depth of the prefix argmin) of one node: the second half
+// of its record -- one 8-byte (compact) or 16-byte (wide) load, <= one sector
+struct RecKeys {
+    uint32_t suf_depth, pre_depth;
+};
 template <int M>
-__global__ void __launch_bounds__(QQT)
-k_quartets(const TreeView tv, const int64_t *__restrict__ quartets, int64_t n,
-           int64_t *__restrict__ out, int aligned) {
+__device__ __forceinline__ RecKeys st_ld_keys(const TreeView &tv, int32_t id) {
+    RecKeys r;
+    if (st_compact<M>(tv)) {
+        uint32_t sf, pr;
+        asm volatile("ld.global.nc.v2.b32 {%0,%1}, [%2];"
+                     : "=r"(sf), "=r"(pr)
+                     : "l"(reinterpret_cast<const char *>(tv.rec16 + id) + 8));
+        r.suf_depth = sf >> tv.block_shift;
+        r.pre_depth = pr >> tv.block_shift;
+    } else {
+        uint64_t sf, pr;
+        asm volatile("ld.global.nc.v2.b64 {%0,%1}, [%2];"
+                     : "=l"(sf), "=l"(pr)
+                     : "l"(reinterpret_cast<const char *>(tv.rec + id) + 16));
+        r.suf_depth = uint32_t(sf >> 32);
+        r.pre_depth = uint32_t(pr >> 32);
+    }
+    return r;
+}
+
+// depth of the minimum-depth node among ids [lo, hi] (lo <= hi): the depth of MRCA(lo, hi)
+template <int M>
+__device__ __forceinline__ uint32_t st_rmq_depth(const TreeView &tv, const SmemTables &sm, int32_t lo,
+                                                 int32_t hi, uint32_t suf_lo, uint32_t pre_hi) {
+    if (lo == hi) return uint32_t(__ldg(tv.depth + lo));  // repeated id: MRCA(a,a) = a
+    const int32_t blo = lo >> tv.block_shift, bhi = hi >> tv.block_shift;
+    if (blo == bhi)
+        return uint32_t(st_rmq_inblock(tv.depth, tv.mst, tv.n_micro, tv.micro_shift, lo, hi) >> 32);
+    uint32_t best = min(suf_lo, pre_hi);
+    const int32_t span = bhi - blo - 1;
+    if (span > 0) {
+        const int k = 31 - __clz(span);
+        if (st_ctab<M>(tv)) {
+            const uint32_t *lvl = sm.stk32 + k * tv.n_blocks;
+            best = min(best, min(lvl[blo + 1], lvl[bhi - (1 << k)]) >> tv.table_shift);
+        } else {
+            const uint64_t *lvl = sm.stk + k * tv.n_blocks;
+            best = min(best, uint32_t(st_min64(lvl[blo + 1], lvl[bhi - (1 << k)]) >> 32));
+        }
+    }
+    return best;
+}
+
+// index of the pair (u, v), u != v, in the reference's order ab ac ad bc bd cd
+__device__ __forceinline__ int quartet_pair_index(int u, int v) {
+    const int a = min(u, v), b = max(u, v);
+    return 2 * a + b - 1 - (a == 2);
+}
+
+// P quartets per thread per iteration: 4P independent record gathers in flight
+template <int M, typename IdxT, int P, int MINB>
+__global__ void __launch_bounds__(QQT, MINB)
+k_quartets(const TreeView tv, const IdxT *__restrict__ quartets, int64_t n, IdxT *__restrict__ out,
+           int aligned) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t tables_bar;
     const SmemTables sm = st_load_tables<M>(tv, smem_raw, &tables_bar);
     const long long nn = tv.n_nodes;
-    for (int64_t i = int64_t(blockIdx.x) * QQT + threadIdx.x; i < n; i += int64_t(gridDim.x) * QQT) {
-        const Quad q = quad_load(quartets + 4 * i, aligned != 0);
-        // range check of quartet_topologies_bulk (MuchTree.pyx:1303-1310), on the device
-        long long mx = q.v[0], mn = q.v[0];
+    const int64_t groups = (n + P - 1) / P;
+    for (int64_t g = int64_t(blockIdx.x) * QQT + threadIdx.x; g < groups; g += int64_t(gridDim.x) * QQT) {
+        QuadT<IdxT> q[P];
+        int32_t x[P][4];  // ids sorted ascending
+        int pos[P][4];    // pos[r] = position in the input quartet of the id of rank r
+        bool ok[P];
+        RecKeys rk[P][4];
 #pragma unroll
-        for (int k = 1; k < 4; ++k) {
-            mx = q.v[k] > mx ? q.v[k] : mx;
-            mn = q.v[k] < mn ? q.v[k] : mn;
-        }
-        if (mn < 0 || mx >= nn) {
-            if (mx >= nn) atomicMax(&tv.status->max_bad, (unsigned long long)mx);
-            if (mn < 0) atomicMin(&tv.status->min_bad, mn);
-            quad_store(out + 4 * i, aligned != 0, -1, -1, -1, -1);
-            continue;
-        }
-        int32_t id[4];
-        RecRaw r[4];
+        for (int t = 0; t < P; ++t) {
+            const int64_t i = g * P + t;
+            ok[t] = i < n;
+            if (ok[t]) q[t] = quad_load<IdxT>(quartets + 4 * i, aligned != 0);
+            else q[t].v[0] = q[t].v[1] = q[t].v[2] = q[t].v[3] = 0;
+            // range check of quartet_topologies_bulk (MuchTree.pyx:1303-1310), on the device
+            long long mx = q[t].v[0], mn = q[t].v[0];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) id[k] = int32_t(q.v[k]);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) r[k] = st_ld_rec<M>(tv, id[k]);
-        // the six pairs in the reference's order: ab ac ad bc bd cd
-        int32_t m[6];
-        int p = 0;
-#pragma unroll
-        for (int x = 0; x < 3; ++x) {
-#pragma unroll
-            for (int y = x + 1; y < 4; ++y, ++p) {
-                if (id[x] == id[y]) {
-                    m[p] = id[x];
-                } else {
-                    const bool xl = id[x] < id[y];
-                    bool ft;
-                    const uint64_t k = st_rmq<M>(tv, sm, xl ? id[x] : id[y], xl ? id[y] : id[x],
-                                                 xl ? r[x].suf : r[y].suf, xl ? r[y].pre : r[x].pre, &ft);
-                    m[p] = st_mrca_id<M>(tv, sm, k, ft);
-                }
+            for (int k = 1; k < 4; ++k) {
+                mx = (long long)q[t].v[k] > mx ? (long long)q[t].v[k] : mx;
+                mn = (long long)q[t].v[k] < mn ? (long long)q[t].v[k] : mn;
             }
-        }
-        int j = 5;
+            if (mn < 0 || mx >= nn) {
+                if (mx >= nn) atomicMax(&tv.status->max_bad, (unsigned long long)mx);
+                if (mn < 0) atomicMin(&tv.status->min_bad, mn);
+                quad_store<IdxT>(out + 4 * i, aligned != 0, IdxT(-1), IdxT(-1), IdxT(-1), IdxT(-1));
+                ok[t] = false;
+            }
 #pragma unroll
-        for (int a = 5; a >= 0; --a) {
-            int c = 0;
+            for (int k = 0; k < 4; ++k) {
+                x[t][k] = ok[t] ? int32_t(q[t].v[k]) : 0;
+                pos[t][k] = k;
+            }
+            // 5-comparator sorting network on (id, position)
+#define ST_CE(a, b)                                          \
+    {                                                        \
+        const bool sw = x[t][a] > x[t][b];                   \
+        const int32_t xa = x[t][a], xb = x[t][b];            \
+        const int pa = pos[t][a], pb = pos[t][b];            \
+        x[t][a] = sw ? xb : xa; x[t][b] = sw ? xa : xb;      \
+        pos[t][a] = sw ? pb : pa; pos[t][b] = sw ? pa : pb;  \
+    }
+            ST_CE(0, 1) ST_CE(2, 3) ST_CE(0, 2) ST_CE(1, 3) ST_CE(1, 2)
+#undef ST_CE
+        }
 #pragma unroll
-            for (int b = 0; b < 6; ++b) c += (m[a] == m[b]);
-            if (c == 1) j = a;  // descending scan: the smallest such index wins
+        for (int t = 0; t < P; ++t)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) rk[t][k] = st_ld_keys<M>(tv, x[t][k]);
+#pragma unroll
+        for (int t = 0; t < P; ++t) {
+            if (!ok[t]) continue;
+            const uint32_t d1 = st_rmq_depth<M>(tv, sm, x[t][0], x[t][1], rk[t][0].suf_depth, rk[t][1].pre_depth);
+            const uint32_t d2 = st_rmq_depth<M>(tv, sm, x[t][1], x[t][2], rk[t][1].suf_depth, rk[t][2].pre_depth);
+            const uint32_t d3 = st_rmq_depth<M>(tv, sm, x[t][2], x[t][3], rk[t][2].suf_depth, rk[t][3].pre_depth);
+            // MRCA depths of the six pairs of RANKS: 01 02 03 12 13 23
+            const uint32_t D01 = d1, D12 = d2, D23 = d3, D02 = min(d1, d2), D13 = min(d2, d3), D03 = min(D02, d3);
+            // C[k] = how many of the six MRCAs equal pair k's (itself included).  Pairs sharing a
+            // rank: equal depths.  Disjoint splits: 01|23 needs d2 >= d1 besides (M(x0,x2) at least as
+            // deep as M(x0,x1)); 02|13 and 03|12: the linking MRCA M(x0,x1) is never shallower.
+            const int e01_02 = D01 == D02, e01_03 = D01 == D03, e01_12 = D01 == D12, e01_13 = D01 == D13;
+            const int e01_23 = (D01 == D23) & (d2 >= d1);
+            const int e02_03 = D02 == D03, e02_12 = D02 == D12, e02_13 = D02 == D13, e02_23 = D02 == D23;
+            const int e03_12 = D03 == D12, e03_13 = D03 == D13, e03_23 = D03 == D23;
+            const int e12_13 = D12 == D13, e12_23 = D12 == D23, e13_23 = D13 == D23;
+            const int c01 = 1 + e01_02 + e01_03 + e01_12 + e01_13 + e01_23;
+            const int c02 = 1 + e01_02 + e02_03 + e02_12 + e02_13 + e02_23;
+            const int c03 = 1 + e01_03 + e02_03 + e03_12 + e03_13 + e03_23;
+            const int c12 = 1 + e01_12 + e02_12 + e03_12 + e12_13 + e12_23;
+            const int c13 = 1 + e01_13 + e02_13 + e03_13 + e12_13 + e13_23;
+            const int c23 = 1 + e01_23 + e02_23 + e03_23 + e12_23 + e13_23;
+            // the reference scans the pairs of input POSITIONS in the order ab ac ad bc bd cd and
+            // takes the first whose MRCA is unique; none -> the fall-through row 5
+            int j = 5;
+            j = min(j, c01 == 1 ? quartet_pair_index(pos[t][0], pos[t][1]) : 5);
+            j = min(j, c02 == 1 ? quartet_pair_index(pos[t][0], pos[t][2]) : 5);
+            j = min(j, c03 == 1 ? quartet_pair_index(pos[t][0], pos[t][3]) : 5);
+            j = min(j, c12 == 1 ? quartet_pair_index(pos[t][1], pos[t][2]) : 5);
+            j = min(j, c13 == 1 ? quartet_pair_index(pos[t][1], pos[t][3]) : 5);
+            j = min(j, c23 == 1 ? quartet_pair_index(pos[t][2], pos[t][3]) : 5);
+            // rows of I: {0,1,2,3} {0,2,1,3} {0,3,1,2} {1,2,0,3} {1,3,0,2} {2,3,0,1}
+            const IdxT a = q[t].v[0], b = q[t].v[1], c = q[t].v[2], d = q[t].v[3];
+            IdxT o0, o1, o2, o3;
+            switch (j) {
+                case 0: o0 = a; o1 = b; o2 = c; o3 = d; break;
+                case 1: o0 = a; o1 = c; o2 = b; o3 = d; break;
+                case 2: o0 = a; o1 = d; o2 = b; o3 = c; break;
+                case 3: o0 = b; o1 = c; o2 = a; o3 = d; break;
+                case 4: o0 = b; o1 = d; o2 = a; o3 = c; break;
+                default: o0 = c; o1 = d; o2 = a; o3 = b; break;
+            }
+            quad_store<IdxT>(out + 4 * (g * P + t), aligned != 0, o0, o1, o2, o3);
         }
-        // rows of I: {0,1,2,3} {0,2,1,3} {0,3,1,2} {1,2,0,3} {1,3,0,2} {2,3,0,1}
-        long long o0, o1, o2, o3;
-        switch (j) {
-            case 0: o0 = q.v[0]; o1 = q.v[1]; o2 = q.v[2]; o3 = q.v[3]; break;
-            case 1: o0 = q.v[0]; o1 = q.v[2]; o2 = q.v[1]; o3 = q.v[3]; break;
-            case 2: o0 = q.v[0]; o1 = q.v[3]; o2 = q.v[1]; o3 = q.v[2]; break;
-            case 3: o0 = q.v[1]; o1 = q.v[2]; o2 = q.v[0]; o3 = q.v[3]; break;
-            case 4: o0 = q.v[1]; o1 = q.v[3]; o2 = q.v[0]; o3 = q.v[2]; break;
-            default: o0 = q.v[2]; o1 = q.v[3]; o2 = q.v[0]; o3 = q.v[1]; break;
-        }
-        quad_store(out + 4 * i, aligned != 0, o0, o1, o2, o3);
     }
 }
 
-template <int M>
-static int launch_quartets_m(const st_tree *t, const int64_t *d_q, int64_t n, int64_t *d_out,
+static int st_quartets_per_thread() {  // SUCHTREE_B200_QPT = 1 | 2 (read per launch: tests flip it)
+    const char *e = getenv("SUCHTREE_B200_QPT");
+    const int x = e ? atoi(e) : ST_QPT_DEFAULT;
+    return (x == 1 || x == 2) ? x : ST_QPT_DEFAULT;
+}
+
+template <int M, typename IdxT, int P, int MINB>
+static int launch_quartets_p(const st_tree *t, const IdxT *d_q, int64_t n, IdxT *d_out,
                              cudaStream_t stream, RangeStatus *status) {
-    auto kern = k_quartets<M>;
+    auto kern = k_quartets<M, IdxT, P, MINB>;
     const int smem = t->query_smem_bytes;
     int rc = st_raise_smem(kern, t->device, smem);
     if (rc != ST_OK) return rc;
     int per_sm = 0;
     ST_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, QQT, smem));
     if (per_sm < 1) per_sm = 1;
-    const int grid = int(std::min<int64_t>((n + QQT - 1) / QQT, int64_t(t->sm_count) * per_sm));
-    const int aligned = (reinterpret_cast<uintptr_t>(d_q) % 32 == 0) && (reinterpret_cast<uintptr_t>(d_out) % 32 == 0);
+    const int64_t groups = (n + P - 1) / P;
+    const int grid = int(std::min<int64_t>((groups + QQT - 1) / QQT, int64_t(t->sm_count) * per_sm));
+    const uintptr_t al = 4 * sizeof(IdxT);
+    const int aligned = (reinterpret_cast<uintptr_t>(d_q) % al == 0) && (reinterpret_cast<uintptr_t>(d_out) % al == 0);
     TreeView view = t->view;
     if (status) view.status = status;
     kern<<<grid, QQT, smem, stream>>>(view, d_q, n, d_out, aligned);
@@ -129,12 +251,20 @@ static int launch_quartets_m(const st_tree *t, const int64_t *d_q, int64_t n, in
     return ST_OK;
 }
 
-static int launch_quartets(const st_tree *t, const int64_t *d_q, int64_t n, int64_t *d_out,
+template <int M, typename IdxT>
+static int launch_quartets_m(const st_tree *t, const IdxT *d_q, int64_t n, IdxT *d_out,
+                             cudaStream_t stream, RangeStatus *status) {
+    if (st_quartets_per_thread() == 2) return launch_quartets_p<M, IdxT, 2, 3>(t, d_q, n, d_out, stream, status);
+    return launch_quartets_p<M, IdxT, 1, 4>(t, d_q, n, d_out, stream, status);
+}
+
+template <typename IdxT>
+static int launch_quartets(const st_tree *t, const IdxT *d_q, int64_t n, IdxT *d_out,
                            cudaStream_t stream, RangeStatus *status = nullptr) {
     if (n == 0) return ST_OK;
-    if (t->compact) return launch_quartets_m<1>(t, d_q, n, d_out, stream, status);
-    if (t->compact_tables) return launch_quartets_m<3>(t, d_q, n, d_out, stream, status);
-    return launch_quartets_m<0>(t, d_q, n, d_out, stream, status);
+    if (t->compact) return launch_quartets_m<1, IdxT>(t, d_q, n, d_out, stream, status);
+    if (t->compact_tables) return launch_quartets_m<3, IdxT>(t, d_q, n, d_out, stream, status);
+    return launch_quartets_m<0, IdxT>(t, d_q, n, d_out, stream, status);
 }
 
 extern "C" int st_quartet_topologies_device(const st_tree *t, const int64_t *d_quartets, int64_t n,
@@ -144,7 +274,17 @@ extern "C" int st_quartet_topologies_device(const st_tree *t, const int64_t *d_q
         return ST_ERR_INVALID_ARG;
     }
     DeviceGuard g(t->device);
-    return launch_quartets(t, d_quartets, n, d_out, static_cast<cudaStream_t>(stream));
+    return launch_quartets<int64_t>(t, d_quartets, n, d_out, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int st_quartet_topologies_device32(const st_tree *t, const int32_t *d_quartets, int64_t n,
+                                              int32_t *d_out, void *stream) {
+    if (!t || n < 0 || (n > 0 && (!d_quartets || !d_out))) {
+        st_set_error("st_quartet_topologies_device32: bad arguments");
+        return ST_ERR_INVALID_ARG;
+    }
+    DeviceGuard g(t->device);
+    return launch_quartets<int32_t>(t, d_quartets, n, d_out, static_cast<cudaStream_t>(stream));
 }
 
 // host buffers: chunks through stream-ordered device scratch, H2D | kernel | D2H
@@ -203,7 +343,7 @@ extern "C" int st_quartet_topologies(const st_tree *t, const int64_t *quartets, 
             rc = ST_ERR_CUDA;
             break;
         }
-        rc = launch_quartets(t, d_in[b], m, d_o[b], st, lane->d_status);
+        rc = launch_quartets<int64_t>(t, d_in[b], m, d_o[b], st, lane->d_status);
         if (rc != ST_OK) break;
         if (cudaMemcpyAsync(out + done * 4, d_o[b], size_t(m) * 32, cudaMemcpyDeviceToHost, st) != cudaSuccess) {
             st_set_error("st_quartet_topologies: D2H copy failed");

@@ -23,6 +23,9 @@
 #endif
 
 #include "st_device.cuh"
+#ifndef ST_PAIRED_DEFAULT
+#define ST_PAIRED_DEFAULT 0
+#endif
 #include "st_hostctx.cuh"
 #include "st_hostpool.cuh"
 
@@ -106,9 +109,39 @@ __device__ __forceinline__ void st_pair(const TreeView &tv, const SmemTables &sm
     if (want_m) m = st_mrca_id<M>(tv, sm, k, ft);
 }
 
+// the same with paired records (compact layout): rd[mrca] from the block table, an endpoint,
+// an endpoint's sector neighbour -- or, failing all that, one more gather
+__device__ __forceinline__ void st_pair_paired(const TreeView &tv, const SmemTables &sm, const PairQ &q,
+                                               const RecRaw &l, const RecRaw &h, double nbl, double nbh,
+                                               bool want_d, bool want_m, double &d, int32_t &m) {
+    bool ft = false;
+    const uint64_t k = q.lo == q.hi ? uint64_t(uint32_t(q.lo))
+                                    : st_rmq<1>(tv, sm, q.lo, q.hi, l.suf, h.pre, &ft);
+    if (want_d) {
+        double rm;
+        if (ft) {
+            rm = sm.brd8[st_key_id(k)];
+        } else {
+            const int32_t id = st_key_id(k);
+            // slot parity of an id: which half of its sector, hence which neighbour came along
+            const bool lo_upper = (reinterpret_cast<uintptr_t>(tv.rec16 + q.lo) & 16) != 0;
+            const bool hi_upper = (reinterpret_cast<uintptr_t>(tv.rec16 + q.hi) & 16) != 0;
+            if (id == q.hi + (hi_upper ? -1 : 1)) rm = nbh;
+            else if (id == q.lo + (lo_upper ? -1 : 1)) rm = nbl;
+            else if (id == q.lo) rm = l.rd_hi;
+            else if (id == q.hi) rm = h.rd_hi;
+            else rm = __ldg(&tv.rec16[id].rd);
+        }
+        d = st_patristic(dd{l.rd_hi, 0.0}, dd{h.rd_hi, 0.0}, dd{rm, 0.0});
+    }
+    if (want_m) m = st_mrca_id<1>(tv, sm, k, ft);
+}
+
 // P pairs per thread per iteration: 2P independent record gathers are in flight
 // before anything depends on them (the kernel is latency-bound on those gathers).
-template <typename IdxT, int P, int M, int QT, int MINB>
+// PR = 1 (compact layout only): endpoint records come with their sector neighbours
+// (st_ld_rec_paired), and rd[mrca] is taken from an endpoint or a neighbour when it is one.
+template <typename IdxT, int P, int M, int QT, int MINB, int PR>
 __global__ void __launch_bounds__(QT, MINB)
 k_pairs(const TreeView tv, const IdxT *__restrict__ pairs, int64_t n, double *__restrict__ out,
         int32_t *__restrict__ mrca_out) {
@@ -127,6 +160,7 @@ k_pairs(const TreeView tv, const IdxT *__restrict__ pairs, int64_t n, double *__
         const RawPairs<IdxT, P> cur = st_load_pairs<IdxT, P>(pairs, P * i);
         PairQ q[P];
         RecRaw l[P], h[P];
+        double nbl[P], nbh[P];  // PR: root distances of the endpoints' sector neighbours
 #pragma unroll
         for (int k = 0; k < P; ++k) {
             long long a, b;
@@ -135,8 +169,14 @@ k_pairs(const TreeView tv, const IdxT *__restrict__ pairs, int64_t n, double *__
         }
 #pragma unroll
         for (int k = 0; k < P; ++k) {
-            l[k] = st_ld_rec<M>(tv, q[k].lo);
-            h[k] = st_ld_rec<M>(tv, q[k].hi);
+            if (PR) {
+                const RecPaired pl = st_ld_rec_paired(tv, q[k].lo), ph = st_ld_rec_paired(tv, q[k].hi);
+                l[k] = pl.r; h[k] = ph.r;
+                nbl[k] = pl.nb_rd; nbh[k] = ph.nb_rd;
+            } else {
+                l[k] = st_ld_rec<M>(tv, q[k].lo);
+                h[k] = st_ld_rec<M>(tv, q[k].hi);
+            }
         }
         double d[P];
         int32_t m[P];
@@ -144,7 +184,8 @@ k_pairs(const TreeView tv, const IdxT *__restrict__ pairs, int64_t n, double *__
         for (int k = 0; k < P; ++k) {
             d[k] = 0.0;
             m[k] = 0;
-            st_pair<M>(tv, sm, q[k], l[k], h[k], want_d, want_m, d[k], m[k]);
+            if (PR) st_pair_paired(tv, sm, q[k], l[k], h[k], nbl[k], nbh[k], want_d, want_m, d[k], m[k]);
+            else st_pair<M>(tv, sm, q[k], l[k], h[k], want_d, want_m, d[k], m[k]);
             if (q[k].bad) {
                 d[k] = nan;
                 m[k] = -1;
@@ -178,7 +219,7 @@ k_pairs(const TreeView tv, const IdxT *__restrict__ pairs, int64_t n, double *__
 }
 
 // ------------------------------------------------------------------ launch --
-template <typename IdxT, int P, int M>
+template <typename IdxT, int P, int M, int PR = 0>
 static int launch_variant_m(const st_tree *t, const void *d_pairs, int64_t n, double *d_out,
                             int32_t *d_mrca, cudaStream_t stream, RangeStatus *status) {
     // 2 pairs/thread: 2 x 512 threads x 64 registers; 4 pairs/thread needs ~80 registers:
@@ -188,7 +229,7 @@ static int launch_variant_m(const st_tree *t, const void *d_pairs, int64_t n, do
 #define ST_MINB_P2 2
 #endif
     constexpr int QT = P == 4 ? 256 : ST_QT_P2, MINB = P == 4 ? 3 : ST_MINB_P2;
-    auto kern = k_pairs<IdxT, P, M, QT, MINB>;
+    auto kern = k_pairs<IdxT, P, M, QT, MINB, PR>;
     // per device, per thread: the attribute and the occupancy query are made once per
     // shared-memory size (they cost microseconds that single-pair calls would notice)
     static thread_local int configured_smem[64] = {0};
@@ -216,9 +257,16 @@ static int launch_variant_m(const st_tree *t, const void *d_pairs, int64_t n, do
     return ST_OK;
 }
 
+static int st_paired_records() {  // SUCHTREE_B200_PAIRED = 0 | 1 (read per launch: tests flip it)
+    const char *e = getenv("SUCHTREE_B200_PAIRED");
+    return e ? (atoi(e) != 0) : ST_PAIRED_DEFAULT;
+}
+
 template <typename IdxT, int P>
 static int launch_variant(const st_tree *t, const void *d_pairs, int64_t n, double *d_out,
                           int32_t *d_mrca, cudaStream_t stream, RangeStatus *status) {
+    if (t->compact && P == 2 && st_paired_records())
+        return launch_variant_m<IdxT, 2, 1, 1>(t, d_pairs, n, d_out, d_mrca, stream, status);
     if (t->compact) return launch_variant_m<IdxT, P, 1>(t, d_pairs, n, d_out, d_mrca, stream, status);
     if (t->compact_tables) return launch_variant_m<IdxT, P, 3>(t, d_pairs, n, d_out, d_mrca, stream, status);
     return launch_variant_m<IdxT, P, 0>(t, d_pairs, n, d_out, d_mrca, stream, status);

@@ -251,7 +251,7 @@ class SuchLinkedTrees:
     def _links(self):
         """Device-resident link list (st_links handle) of the current subset; rebuilt only
         when subset_a / subset_b changed the list."""
-        ver = self._subset_version
+        ver = getattr(self, "_subset_version", 0)
         cur = getattr(self, "_links_handle", None)
         if cur is None or cur[0] != ver:
             self._drop_links()

@@ -228,6 +228,21 @@ class SuchTree:
             raise InvalidNodeError(node_id, self.size)
         return node_id
 
+    def _validate_nodes(self, nodes):
+        """int64 ids of a sequence of nodes: one vectorised range check when they are all
+        integers (the per-node loop costs ~1 us per id), else node by node as the reference."""
+        if isinstance(nodes, np.ndarray) and nodes.dtype.kind in "iu" and nodes.ndim == 1:
+            ids = nodes.astype(np.int64)
+        elif isinstance(nodes, (list, tuple, range)) and all(type(v) is int for v in nodes):
+            ids = np.fromiter(nodes, dtype=np.int64, count=len(nodes))
+        else:
+            return np.array([self._validate_node(nd) for nd in nodes], dtype=np.int64)
+        if ids.size:
+            bad = (ids < 0) | (ids >= self.size)
+            if bad.any():
+                raise InvalidNodeError(int(ids[np.argmax(bad)]), self.size)  # the first offender, as the loop
+        return ids
+
     def _validate_node_pair(self, a, b):
         return self._validate_node(a), self._validate_node(b)
 
@@ -628,9 +643,11 @@ class SuchTree:
         _deprecation_warning("quartet_topologies()", "quartet_topologies_bulk()")
         return self.quartet_topologies_bulk(quartets)
 
-    def quartet_topologies_device(self, d_quartets_ptr, n, d_out_ptr, stream=None):
-        """Device-resident variant: contiguous int64 (n,4) in and out."""
-        rc = _lib.lib().st_quartet_topologies_device(self._handle, d_quartets_ptr, n, d_out_ptr, stream)
+    def quartet_topologies_device(self, d_quartets_ptr, n, d_out_ptr, stream=None, idx_bits=64):
+        """Device-resident variant: contiguous int64 (idx_bits=64) or int32 (idx_bits=32)
+        (n,4) in and out."""
+        fn = _lib.lib().st_quartet_topologies_device if idx_bits == 64 else _lib.lib().st_quartet_topologies_device32
+        rc = fn(self._handle, d_quartets_ptr, n, d_out_ptr, stream)
         _lib.check(rc, self.size)
 
     def nearest_neighbors(self, node, k=1, from_nodes=None):
@@ -672,7 +689,7 @@ class SuchTree:
                 if ids.shape[0] != n or not np.array_equal(ids, np.arange(0, 2 * n, 2)):
                     ids_ptr, n = ids, ids.shape[0]
         else:
-            ids_ptr = np.array([self._validate_node(nd) for nd in nodes], dtype=np.int64)
+            ids_ptr = self._validate_nodes(nodes)
             n = ids_ptr.shape[0]
         if n * n * 8 >= _lib.PINNED_RESULT_MIN_BYTES:
             out = _lib.pinned_empty((n, n), np.float64)  # every element is written by the kernels

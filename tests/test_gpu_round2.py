@@ -427,3 +427,86 @@ def test_nccl_moment_allreduce_two_gpus():
     assert r0 == r1 and n0 == n1 == 1_000_000
     assert abs(r0 - r_one) <= 1e-12
     assert x0 == x1 and xn0 == xn1 == 2500 * 2499 // 2 and abs(x0 - r_ex_one) <= 1e-12
+
+
+# ------------------------------------------- kernel variants (round 2) -------
+def _with_env(name, value, fn):
+    old = os.environ.get(name)
+    os.environ[name] = value
+    try:
+        return fn()
+    finally:
+        if old is None:
+            del os.environ[name]
+        else:
+            os.environ[name] = old
+
+
+@pytest.mark.parametrize("shape", ["yule", "left_comb", "right_comb", "balanced"])
+@pytest.mark.parametrize("block_shift", [0, 3])
+def test_paired_record_kernel_matches_plain_kernel_and_oracle(shape, block_shift):
+    """The paired-record pair kernel (one 32-byte load per endpoint; rd[mrca] from an endpoint
+    or its sector neighbour) against the plain kernel and the oracle: leaf pairs, any-node
+    pairs, repeated ids, MRCA ids, on both comb orientations (the record shift is voted per
+    tree) and with tiny RMQ blocks so that every route is taken."""
+    if shape == "yule":
+        ft = synth.yule_tree(3000, seed=3)
+    elif shape == "balanced":
+        ft = synth.balanced_tree(2048, seed=3)
+    else:
+        ft = synth.caterpillar_tree(1500, seed=3)
+        if shape == "right_comb":
+            n = ft.size
+            src = ft
+            ft = synth.caterpillar_tree(1500, seed=3)
+            rev = lambda a: np.where(a >= 0, n - 1 - a, -1).astype(np.int32)[::-1].copy()  # noqa: E731
+            ft.parent, ft.left, ft.right = rev(src.parent), rev(src.right), rev(src.left)
+            ft.distance = src.distance[::-1].copy()
+            ft.root = n - 1 - src.root
+    T = SuchTree.from_flat(ft, _block_shift=block_shift)
+    assert T.index_info["layout"] == 1
+    ot = O.OracleTree(ft.parent, ft.distance)
+    rng = np.random.default_rng(8)
+    p = np.concatenate([2 * rng.integers(0, ft.n_leaves, size=(300_001, 2)), rng.integers(0, ft.size, size=(300_000, 2)),
+                        np.repeat(rng.integers(0, ft.size, size=(1000, 1)), 2, axis=1)]).astype(np.int64)
+    want, wm = ot.distances_f64_climb(p, with_mrca=True)
+    for paired in ("0", "1"):
+        d = _with_env("SUCHTREE_B200_PAIRED", paired, lambda: T.distances_bulk(p))
+        m = _with_env("SUCHTREE_B200_PAIRED", paired, lambda: T.common_ancestors_bulk(p))
+        assert np.array_equal(d, want), paired
+        assert np.array_equal(m, wm), paired
+
+
+@pytest.mark.parametrize("qpt", ["1", "2"])
+def test_depth_only_quartet_kernel_variants(qpt):
+    """1 or 2 quartets per thread, int64 and int32 ids on the device, ragged counts, any nodes
+    and repeated ids: rows bit-exact against the oracle's literal restatement
+    (MuchTree.pyx:1331-1376)."""
+    import torch
+
+    ft = synth.yule_tree(5000, seed=9)
+    ot = O.OracleTree(ft.parent, ft.distance)
+    rng = np.random.default_rng(10)
+    for bs in (0, 2):
+        T = SuchTree.from_flat(ft, _block_shift=bs)
+        for n in (1, 2, 3, 255, 256, 257, 100_003):
+            q = np.concatenate([2 * rng.integers(0, ft.n_leaves, size=(n, 4)),
+                                rng.integers(0, ft.size, size=(n, 4))]).astype(np.int64)
+            q[::5, 1] = q[::5, 0]
+            q[::9, 3] = q[::9, 1]
+            q[::17] = q[::17, :1]  # all four equal
+            want = ot.quartet_topologies(q)
+            got = _with_env("SUCHTREE_B200_QPT", qpt, lambda: T.quartet_topologies_bulk(q))
+            assert np.array_equal(got, want), (bs, n)
+            dq = torch.from_numpy(q.astype(np.int32)).cuda()
+            do = torch.empty_like(dq)
+            _with_env("SUCHTREE_B200_QPT", qpt,
+                      lambda: T.quartet_topologies_device(dq.data_ptr(), q.shape[0], do.data_ptr(), idx_bits=32))
+            torch.cuda.synchronize()
+            assert np.array_equal(do.cpu().numpy().astype(np.int64), want), (bs, n, "int32")
+        bad = torch.tensor([[0, 2, 4, ft.size]], dtype=torch.int32).cuda()
+        ob = torch.empty_like(bad)
+        T.quartet_topologies_device(bad.data_ptr(), 1, ob.data_ptr(), idx_bits=32)
+        with pytest.raises(InvalidNodeError):
+            T.check_range()
+        assert ob.cpu().numpy().tolist() == [[-1, -1, -1, -1]]
