@@ -729,6 +729,8 @@ def run_other_workloads(args, rank, world, local, dev, peak):
             "index_bytes": int(T.index_info["index_bytes"]),
             "hbm_frac": 16.0 * n3 / sec / 1e9 / peak, "gather_frac": gfrac,
             "gather_peak_sectors_per_s": sps.value, "all_finite": finite,
+            "paired_record_kernel": bool(T.index_info["paired_records"]),
+            "probe_neighbour_is_mrca": float(T.index_info["probe_neighbour_hit"]),
         }
         del T
     del pairs, out

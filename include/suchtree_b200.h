@@ -63,6 +63,12 @@ typedef struct st_tree_info {
     int32_t layout;       /* 0 = wide records (32 B/node, double-double root distance) + 64-bit block tables,
                              1 = compact records (16 B/node; every root distance exact in fp64) + 32-bit tables,
                              2 = wide records + 32-bit block tables (inexact root distances) */
+    int32_t paired_records; /* 1: the pair kernel fetches each endpoint's whole 32-byte sector (its record and
+                               its slot neighbour's) -- chosen at build time when the probe below says that the
+                               neighbour is often the MRCA (ladder-like trees); compact layout only */
+    double probe_third_gather;  /* build-time probe, 16384 random leaf pairs: fraction whose MRCA is neither a
+                                   block minimum nor an endpoint (the plain kernel gathers its root distance) */
+    double probe_neighbour_hit; /* ... and fraction for which an endpoint's sector neighbour IS the MRCA */
 } st_tree_info;
 
 /* thread-local text of the last error raised on this thread ("" if none) */

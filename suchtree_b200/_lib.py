@@ -35,6 +35,9 @@ class TreeInfo(C.Structure):
         ("query_smem_bytes", C.c_int32),
         ("sm_count", C.c_int32),
         ("layout", C.c_int32),
+        ("paired_records", C.c_int32),
+        ("probe_third_gather", C.c_double),
+        ("probe_neighbour_hit", C.c_double),
     ]
 
 

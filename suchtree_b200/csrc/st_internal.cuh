@@ -109,6 +109,8 @@ struct st_tree {
     NodeRec16 *d_rec16 = nullptr;       // = d_rec16_base + rec16_shift: record of node v at slot v + shift
     NodeRec16 *d_rec16_base = nullptr;  // allocation: n_nodes + 2 slots, zero padded, 32-byte aligned
     int rec16_shift = 0;                // 0 | 1: chosen so that most leaves share a 32-byte sector with their parent
+    int paired = 0;                     // 1: the pair kernel loads whole sectors (record + neighbour), see k_probe_paired
+    double probe_third_gather = 0.0, probe_neighbour_hit = 0.0;
     uint32_t *d_stk32 = nullptr;
     double *d_brd8 = nullptr;
     int32_t *d_bid = nullptr;

@@ -122,7 +122,9 @@ __device__ __forceinline__ int quartet_pair_index(int u, int v) {
 }
 
 // P quartets per thread per iteration: 4P independent record gathers in flight
-template <int M, typename IdxT, int P, int MINB>
+// SMALL (n_nodes <= 2^29): the sort runs on packed 32-bit keys (id << 2 | input position), two
+// min/max instructions per comparator.
+template <int M, typename IdxT, int P, int MINB, bool SMALL>
 __global__ void __launch_bounds__(QQT, MINB)
 k_quartets(const TreeView tv, const IdxT *__restrict__ quartets, int64_t n, IdxT *__restrict__ out,
            int aligned) {
@@ -144,24 +146,46 @@ k_quartets(const TreeView tv, const IdxT *__restrict__ quartets, int64_t n, IdxT
             if (ok[t]) q[t] = quad_load<IdxT>(quartets + 4 * i, aligned != 0);
             else q[t].v[0] = q[t].v[1] = q[t].v[2] = q[t].v[3] = 0;
             // range check of quartet_topologies_bulk (MuchTree.pyx:1303-1310), on the device
-            long long mx = q[t].v[0], mn = q[t].v[0];
+            bool bad = false;
 #pragma unroll
-            for (int k = 1; k < 4; ++k) {
-                mx = (long long)q[t].v[k] > mx ? (long long)q[t].v[k] : mx;
-                mn = (long long)q[t].v[k] < mn ? (long long)q[t].v[k] : mn;
-            }
-            if (mn < 0 || mx >= nn) {
+            for (int k = 0; k < 4; ++k) bad |= (unsigned long long)(long long)q[t].v[k] >= (unsigned long long)nn;
+            if (bad) {
+                long long mx = q[t].v[0], mn = q[t].v[0];
+#pragma unroll
+                for (int k = 1; k < 4; ++k) {
+                    mx = (long long)q[t].v[k] > mx ? (long long)q[t].v[k] : mx;
+                    mn = (long long)q[t].v[k] < mn ? (long long)q[t].v[k] : mn;
+                }
                 if (mx >= nn) atomicMax(&tv.status->max_bad, (unsigned long long)mx);
                 if (mn < 0) atomicMin(&tv.status->min_bad, mn);
-                quad_store<IdxT>(out + 4 * i, aligned != 0, IdxT(-1), IdxT(-1), IdxT(-1), IdxT(-1));
+                if (ok[t]) quad_store<IdxT>(out + 4 * i, aligned != 0, IdxT(-1), IdxT(-1), IdxT(-1), IdxT(-1));
                 ok[t] = false;
             }
+            if (SMALL) {
+                // 5-comparator sorting network on packed keys
+                int32_t key[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                x[t][k] = ok[t] ? int32_t(q[t].v[k]) : 0;
-                pos[t][k] = k;
-            }
-            // 5-comparator sorting network on (id, position)
+                for (int k = 0; k < 4; ++k) key[k] = ok[t] ? (int32_t(q[t].v[k]) << 2) | k : k;
+#define ST_CE(a, b)                                          \
+    {                                                        \
+        const int32_t lo_ = min(key[a], key[b]);             \
+        key[b] = max(key[a], key[b]);                        \
+        key[a] = lo_;                                        \
+    }
+                ST_CE(0, 1) ST_CE(2, 3) ST_CE(0, 2) ST_CE(1, 3) ST_CE(1, 2)
+#undef ST_CE
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    x[t][k] = key[k] >> 2;
+                    pos[t][k] = key[k] & 3;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    x[t][k] = ok[t] ? int32_t(q[t].v[k]) : 0;
+                    pos[t][k] = k;
+                }
+                // 5-comparator sorting network on (id, position)
 #define ST_CE(a, b)                                          \
     {                                                        \
         const bool sw = x[t][a] > x[t][b];                   \
@@ -170,8 +194,9 @@ k_quartets(const TreeView tv, const IdxT *__restrict__ quartets, int64_t n, IdxT
         x[t][a] = sw ? xb : xa; x[t][b] = sw ? xa : xb;      \
         pos[t][a] = sw ? pb : pa; pos[t][b] = sw ? pa : pb;  \
     }
-            ST_CE(0, 1) ST_CE(2, 3) ST_CE(0, 2) ST_CE(1, 3) ST_CE(1, 2)
+                ST_CE(0, 1) ST_CE(2, 3) ST_CE(0, 2) ST_CE(1, 3) ST_CE(1, 2)
 #undef ST_CE
+            }
         }
 #pragma unroll
         for (int t = 0; t < P; ++t)
@@ -230,10 +255,10 @@ static int st_quartets_per_thread() {  // SUCHTREE_B200_QPT = 1 | 2 (read per la
     return (x == 1 || x == 2) ? x : ST_QPT_DEFAULT;
 }
 
-template <int M, typename IdxT, int P, int MINB>
+template <int M, typename IdxT, int P, int MINB, bool SMALL>
 static int launch_quartets_p(const st_tree *t, const IdxT *d_q, int64_t n, IdxT *d_out,
                              cudaStream_t stream, RangeStatus *status) {
-    auto kern = k_quartets<M, IdxT, P, MINB>;
+    auto kern = k_quartets<M, IdxT, P, MINB, SMALL>;
     const int smem = t->query_smem_bytes;
     int rc = st_raise_smem(kern, t->device, smem);
     if (rc != ST_OK) return rc;
@@ -254,8 +279,11 @@ static int launch_quartets_p(const st_tree *t, const IdxT *d_q, int64_t n, IdxT 
 template <int M, typename IdxT>
 static int launch_quartets_m(const st_tree *t, const IdxT *d_q, int64_t n, IdxT *d_out,
                              cudaStream_t stream, RangeStatus *status) {
-    if (st_quartets_per_thread() == 2) return launch_quartets_p<M, IdxT, 2, 3>(t, d_q, n, d_out, stream, status);
-    return launch_quartets_p<M, IdxT, 1, 4>(t, d_q, n, d_out, stream, status);
+    if (t->n_nodes > (int64_t(1) << 29)) return launch_quartets_p<M, IdxT, 1, 4, false>(t, d_q, n, d_out, stream, status);
+    if (st_quartets_per_thread() == 2) return launch_quartets_p<M, IdxT, 2, 3, true>(t, d_q, n, d_out, stream, status);
+    if (const char *e = getenv("SUCHTREE_B200_QMINB"))  // experiments: resident CTAs per SM asked of the compiler
+        if (atoi(e) == 5) return launch_quartets_p<M, IdxT, 1, 5, true>(t, d_q, n, d_out, stream, status);
+    return launch_quartets_p<M, IdxT, 1, 4, true>(t, d_q, n, d_out, stream, status);
 }
 
 template <typename IdxT>

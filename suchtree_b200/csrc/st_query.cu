@@ -23,9 +23,6 @@
 #endif
 
 #include "st_device.cuh"
-#ifndef ST_PAIRED_DEFAULT
-#define ST_PAIRED_DEFAULT 0
-#endif
 #include "st_hostctx.cuh"
 #include "st_hostpool.cuh"
 
@@ -257,15 +254,17 @@ static int launch_variant_m(const st_tree *t, const void *d_pairs, int64_t n, do
     return ST_OK;
 }
 
-static int st_paired_records() {  // SUCHTREE_B200_PAIRED = 0 | 1 (read per launch: tests flip it)
+// the tree's own choice (build-time probe, st_tree_create) unless SUCHTREE_B200_PAIRED = 0 | 1
+// forces it (read per launch: tests and experiments flip it)
+static int st_paired_records(const st_tree *t) {
     const char *e = getenv("SUCHTREE_B200_PAIRED");
-    return e ? (atoi(e) != 0) : ST_PAIRED_DEFAULT;
+    return e && e[0] ? (atoi(e) != 0) : t->paired;
 }
 
 template <typename IdxT, int P>
 static int launch_variant(const st_tree *t, const void *d_pairs, int64_t n, double *d_out,
                           int32_t *d_mrca, cudaStream_t stream, RangeStatus *status) {
-    if (t->compact && P == 2 && st_paired_records())
+    if (t->compact && P == 2 && st_paired_records(t))
         return launch_variant_m<IdxT, 2, 1, 1>(t, d_pairs, n, d_out, d_mrca, stream, status);
     if (t->compact) return launch_variant_m<IdxT, P, 1>(t, d_pairs, n, d_out, d_mrca, stream, status);
     if (t->compact_tables) return launch_variant_m<IdxT, P, 3>(t, d_pairs, n, d_out, d_mrca, stream, status);
