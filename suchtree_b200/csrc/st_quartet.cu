@@ -15,7 +15,7 @@
 
 static const int QQT = 256;
 #ifndef ST_QPT_DEFAULT
-#define ST_QPT_DEFAULT 2
+#define ST_QPT_DEFAULT 1
 #endif
 
 // The reference's rule needs only the EQUALITY PATTERN of the six pair MRCAs, and that
