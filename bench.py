@@ -300,14 +300,21 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture."""
+def ncu_traffic(build_id, n_pairs):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the
+    committed `ncu --set full` capture (profiles/traffic.json) -- only if that capture was
+    taken from THIS binary (same st_build_id) and launch size; otherwise null, with the reason."""
     p = os.path.join(REPO, "profiles", "traffic.json")
     try:
         with open(p) as f:
-            return json.load(f).get("k_pairs_dram_bytes_per_launch")
+            t = json.load(f)
     except Exception:
-        return None
+        return None, "no profiles/traffic.json"
+    if t.get("build_id") != build_id:
+        return None, "stale: captured from build %s, this is %s (%s)" % (t.get("build_id"), build_id, t.get("capture"))
+    if int(t.get("pairs_per_launch", 0)) != int(n_pairs):
+        return None, "captured at %s pairs per launch" % t.get("pairs_per_launch")
+    return t.get("k_pairs_dram_bytes_per_launch"), "ncu capture %s (build %s)" % (t.get("capture"), build_id)
 
 
 def run_ours(args):
@@ -491,6 +498,7 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     per_launch_s = ms * 1e-3 / args.steps
     achieved = 16.0 * n_pairs / per_launch_s / 1e9
+    traffic, traffic_src = ncu_traffic(_lib.lib().st_build_id().decode(), n_pairs)
     gather = None
     if rank == 0:
         sps = C.c_double(0)
@@ -529,7 +537,8 @@ def run_ours(args):
         },
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "k_pairs<int32,VEC>",
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+            "kernel": "k_pairs<int32, 2 pairs/thread, compact layout, 512 threads x 2 CTAs/SM>",
             "algorithmic_bytes_per_pair": 16,
             "note": "the kernel is bound by the per-SM L1TEX rate of random sector gathers (2 per pair), see gather_roofline",
         },

@@ -115,6 +115,28 @@ BENCH_SIGNATURES = {
 _bench_lib = None
 
 
+class _build_lock:
+    """Inter-process lock (flock) around the stale-library check and rebuild."""
+
+    def __enter__(self):
+        import fcntl
+
+        try:
+            self.f = open(os.path.join(_build.HERE, ".build.lock"), "w")
+            fcntl.flock(self.f, fcntl.LOCK_EX)
+        except OSError:  # read-only install: nothing to build into anyway
+            self.f = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.f is not None:
+            import fcntl
+
+            fcntl.flock(self.f, fcntl.LOCK_UN)
+            self.f.close()
+        return False
+
+
 def _bind(L, signatures):
     for name, (res, args) in signatures.items():
         fn = getattr(L, name)  # AttributeError if the .so lacks a declared symbol
@@ -132,8 +154,9 @@ def lib():
         with _lock:
             if _lib is None:
                 path = _build.LIB
-                if _build.needs_build("product"):
-                    _build.build(which=("product",))
+                with _build_lock():  # one process per GPU: only one of them (re)builds, the rest wait
+                    if _build.needs_build("product"):
+                        _build.build(which=("product",))
                 L = _bind(C.CDLL(path), SIGNATURES)
                 if _build.sources("product") and L.st_build_id().decode() != _build.source_id("product"):
                     raise SuchTreeError(
@@ -149,8 +172,9 @@ def bench_lib():
     if _bench_lib is None:
         with _lock:
             if _bench_lib is None:
-                if _build.needs_build("bench"):
-                    _build.build(which=("bench",))
+                with _build_lock():
+                    if _build.needs_build("bench"):
+                        _build.build(which=("bench",))
                 _bench_lib = _bind(C.CDLL(_build.BENCH_LIB), BENCH_SIGNATURES)
     return _bench_lib
 

@@ -124,7 +124,8 @@ __device__ __forceinline__ int quartet_pair_index(int u, int v) {
 // P quartets per thread per iteration: 4P independent record gathers in flight
 // SMALL (n_nodes <= 2^29): the sort runs on packed 32-bit keys (id << 2 | input position), two
 // min/max instructions per comparator.
-template <int M, typename IdxT, int P, int MINB, bool SMALL>
+// PF: the ids of the thread's NEXT iteration are fetched before the current one is worked on.
+template <int M, typename IdxT, int P, int MINB, bool SMALL, bool PF = false>
 __global__ void __launch_bounds__(QQT, MINB)
 k_quartets(const TreeView tv, const IdxT *__restrict__ quartets, int64_t n, IdxT *__restrict__ out,
            int aligned) {
@@ -133,18 +134,34 @@ k_quartets(const TreeView tv, const IdxT *__restrict__ quartets, int64_t n, IdxT
     const SmemTables sm = st_load_tables<M>(tv, smem_raw, &tables_bar);
     const long long nn = tv.n_nodes;
     const int64_t groups = (n + P - 1) / P;
-    for (int64_t g = int64_t(blockIdx.x) * QQT + threadIdx.x; g < groups; g += int64_t(gridDim.x) * QQT) {
+    const int64_t stride = int64_t(gridDim.x) * QQT;
+    auto fetch = [&](int64_t g, QuadT<IdxT>(&dst)[P]) {
+#pragma unroll
+        for (int t = 0; t < P; ++t) {
+            const int64_t i = g * P + t;
+            if (g < groups && i < n) dst[t] = quad_load<IdxT>(quartets + 4 * i, aligned != 0);
+            else dst[t].v[0] = dst[t].v[1] = dst[t].v[2] = dst[t].v[3] = 0;
+        }
+    };
+    QuadT<IdxT> nxt[P];
+    if (PF) fetch(int64_t(blockIdx.x) * QQT + threadIdx.x, nxt);
+    for (int64_t g = int64_t(blockIdx.x) * QQT + threadIdx.x; g < groups; g += stride) {
         QuadT<IdxT> q[P];
         int32_t x[P][4];  // ids sorted ascending
         int pos[P][4];    // pos[r] = position in the input quartet of the id of rank r
         bool ok[P];
         RecKeys rk[P][4];
+        if (PF) {
+#pragma unroll
+            for (int t = 0; t < P; ++t) q[t] = nxt[t];
+            fetch(g + stride, nxt);
+        } else {
+            fetch(g, q);
+        }
 #pragma unroll
         for (int t = 0; t < P; ++t) {
             const int64_t i = g * P + t;
             ok[t] = i < n;
-            if (ok[t]) q[t] = quad_load<IdxT>(quartets + 4 * i, aligned != 0);
-            else q[t].v[0] = q[t].v[1] = q[t].v[2] = q[t].v[3] = 0;
             // range check of quartet_topologies_bulk (MuchTree.pyx:1303-1310), on the device
             bool bad = false;
 #pragma unroll
@@ -255,10 +272,10 @@ static int st_quartets_per_thread() {  // SUCHTREE_B200_QPT = 1 | 2 (read per la
     return (x == 1 || x == 2) ? x : ST_QPT_DEFAULT;
 }
 
-template <int M, typename IdxT, int P, int MINB, bool SMALL>
+template <int M, typename IdxT, int P, int MINB, bool SMALL, bool PF = false>
 static int launch_quartets_p(const st_tree *t, const IdxT *d_q, int64_t n, IdxT *d_out,
                              cudaStream_t stream, RangeStatus *status) {
-    auto kern = k_quartets<M, IdxT, P, MINB, SMALL>;
+    auto kern = k_quartets<M, IdxT, P, MINB, SMALL, PF>;
     const int smem = t->query_smem_bytes;
     int rc = st_raise_smem(kern, t->device, smem);
     if (rc != ST_OK) return rc;
@@ -283,6 +300,8 @@ static int launch_quartets_m(const st_tree *t, const IdxT *d_q, int64_t n, IdxT 
     if (st_quartets_per_thread() == 2) return launch_quartets_p<M, IdxT, 2, 3, true>(t, d_q, n, d_out, stream, status);
     if (const char *e = getenv("SUCHTREE_B200_QMINB"))  // experiments: resident CTAs per SM asked of the compiler
         if (atoi(e) == 5) return launch_quartets_p<M, IdxT, 1, 5, true>(t, d_q, n, d_out, stream, status);
+    if (const char *e = getenv("SUCHTREE_B200_QPF"))  // experiments: prefetch the next iteration's ids
+        if (atoi(e) == 1) return launch_quartets_p<M, IdxT, 1, 4, true, true>(t, d_q, n, d_out, stream, status);
     return launch_quartets_p<M, IdxT, 1, 4, true>(t, d_q, n, d_out, stream, status);
 }
 
