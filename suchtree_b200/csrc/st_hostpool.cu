@@ -1,6 +1,13 @@
 // Host thread pool (see st_hostpool.cuh).  Plain C++: no device code here.
 #include "st_hostpool.cuh"
 
+#include <cstring>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
+#include "st_internal.cuh"
+
 #include <algorithm>
 #include <condition_variable>
 #include <cstdlib>
@@ -97,3 +104,85 @@ Pool &pool() {
 
 void st_parallel_for(int n_parts, const std::function<void(int, int)> &fn) { pool().parallel_for(n_parts, fn); }
 int st_host_threads() { return pool().n_threads; }
+
+// ------------------------------------------------- host passes over id arrays --
+// int64 ids -> int32, OR of everything seen (bit 31 and above set <=> some id is
+// negative or >= 2^31: the rare error path then finds the exact id)
+static uint64_t pack_ids_contig(const int64_t *__restrict__ src, int32_t *__restrict__ dst, int64_t count) {
+    uint64_t acc = 0;
+    int64_t i = 0;
+#if defined(__SSE2__)
+    // 4 ids per step; streaming stores: the staging buffer is read next by the DMA
+    // engine, not by this core, so skip the read-for-ownership of its lines
+    while (i < count && (reinterpret_cast<uintptr_t>(dst + i) & 15)) {
+        const int64_t v = src[i];
+        acc |= uint64_t(v);
+        dst[i++] = int32_t(v);
+    }
+    __m128i vacc = _mm_setzero_si128();
+    for (; i + 8 <= count; i += 8) {
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i));
+        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 2));
+        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 4));
+        const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 6));
+        vacc = _mm_or_si128(vacc, _mm_or_si128(_mm_or_si128(a, b), _mm_or_si128(c, d)));
+        const __m128 lo = _mm_shuffle_ps(_mm_castsi128_ps(a), _mm_castsi128_ps(b), _MM_SHUFFLE(2, 0, 2, 0));
+        const __m128 hi = _mm_shuffle_ps(_mm_castsi128_ps(c), _mm_castsi128_ps(d), _MM_SHUFFLE(2, 0, 2, 0));
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i), _mm_castps_si128(lo));
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 4), _mm_castps_si128(hi));
+    }
+    alignas(16) uint64_t lanes[2];
+    _mm_store_si128(reinterpret_cast<__m128i *>(lanes), vacc);
+    acc |= lanes[0] | lanes[1];
+    _mm_sfence();
+#endif
+    for (; i < count; ++i) {
+        const int64_t v = src[i];
+        acc |= uint64_t(v);
+        dst[i] = int32_t(v);
+    }
+    return acc;
+}
+uint64_t st_pack_ids(const int64_t *src, int64_t s0, int64_t s1, int64_t m, int32_t *dst, int width) {
+    const bool contiguous = (s1 == 1 && s0 == width);
+    const int parts = int(std::min<int64_t>(st_host_threads(), m / 32768 + 1));
+    std::vector<uint64_t> accs(size_t(parts), 0);
+    st_parallel_for(parts, [&](int p, int np) {
+        const int64_t b = m * p / np, e = m * (p + 1) / np;
+        uint64_t acc = 0;
+        if (contiguous) {
+            acc = pack_ids_contig(src + b * width, dst + b * width, (e - b) * width);
+        } else {
+            for (int64_t i = b; i < e; ++i)
+                for (int k = 0; k < width; ++k) {
+                    const int64_t v = src[i * s0 + k * s1];
+                    acc |= uint64_t(v);
+                    dst[i * width + k] = int32_t(v);
+                }
+        }
+        accs[size_t(p)] = acc;
+    });
+    uint64_t acc = 0;
+    for (uint64_t a : accs) acc |= a;
+    return acc;
+}
+void st_parallel_copy(void *dst, const void *src, size_t bytes) {
+    const int parts = int(std::min<size_t>(size_t(st_host_threads()), bytes / (size_t(1) << 20) + 1));
+    st_parallel_for(parts, [&](int p, int np) {
+        const size_t b = bytes * size_t(p) / size_t(np), e = bytes * size_t(p + 1) / size_t(np);
+        memcpy(static_cast<char *>(dst) + b, static_cast<const char *>(src) + b, e - b);
+    });
+}
+// the reference's report for an out-of-range array: max id if it is >= size, else min id
+void st_report_range(const int64_t *src, int64_t s0, int64_t s1, int64_t n, int width, int64_t n_nodes) {
+    int64_t mx = INT64_MIN, mn = INT64_MAX;
+    for (int64_t i = 0; i < n; ++i)
+        for (int k = 0; k < width; ++k) {
+            const int64_t v = src[i * s0 + k * s1];
+            mx = v > mx ? v : mx;
+            mn = v < mn ? v : mn;
+        }
+    st_set_bad_node(mx >= n_nodes ? mx : mn);
+    st_set_error("node id %lld out of bounds (tree size %lld)", (long long)st_bad_node(), (long long)n_nodes);
+}
+

@@ -9,9 +9,11 @@
 // (:1319-1320); no such j -> row 5 -- with MRCA equality decided from depths (below).
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "st_device.cuh"
 #include "st_hostctx.cuh"
+#include "st_hostpool.cuh"
 
 static const int QQT = 256;
 #ifndef ST_QPT_DEFAULT
@@ -125,9 +127,11 @@ __device__ __forceinline__ int quartet_pair_index(int u, int v) {
 // SMALL (n_nodes <= 2^29): the sort runs on packed 32-bit keys (id << 2 | input position), two
 // min/max instructions per comparator.
 // PF: the ids of the thread's NEXT iteration are fetched before the current one is worked on.
-template <int M, typename IdxT, int P, int MINB, bool SMALL, bool PF = false>
+// IdxT: type of the ids read, OutT: type of the ids written (the host path ships int32 ids
+// over PCIe and gets the drop-in's int64 rows back).
+template <int M, typename IdxT, int P, int MINB, bool SMALL, bool PF = false, typename OutT = IdxT>
 __global__ void __launch_bounds__(QQT, MINB)
-k_quartets(const TreeView tv, const IdxT *__restrict__ quartets, int64_t n, IdxT *__restrict__ out,
+k_quartets(const TreeView tv, const IdxT *__restrict__ quartets, int64_t n, OutT *__restrict__ out,
            int aligned) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t tables_bar;
@@ -175,7 +179,7 @@ k_quartets(const TreeView tv, const IdxT *__restrict__ quartets, int64_t n, IdxT
                 }
                 if (mx >= nn) atomicMax(&tv.status->max_bad, (unsigned long long)mx);
                 if (mn < 0) atomicMin(&tv.status->min_bad, mn);
-                if (ok[t]) quad_store<IdxT>(out + 4 * i, aligned != 0, IdxT(-1), IdxT(-1), IdxT(-1), IdxT(-1));
+                if (ok[t]) quad_store<OutT>(out + 4 * i, aligned != 0, OutT(-1), OutT(-1), OutT(-1), OutT(-1));
                 ok[t] = false;
             }
             if (SMALL) {
@@ -251,8 +255,8 @@ k_quartets(const TreeView tv, const IdxT *__restrict__ quartets, int64_t n, IdxT
             j = min(j, c13 == 1 ? quartet_pair_index(pos[t][1], pos[t][3]) : 5);
             j = min(j, c23 == 1 ? quartet_pair_index(pos[t][2], pos[t][3]) : 5);
             // rows of I: {0,1,2,3} {0,2,1,3} {0,3,1,2} {1,2,0,3} {1,3,0,2} {2,3,0,1}
-            const IdxT a = q[t].v[0], b = q[t].v[1], c = q[t].v[2], d = q[t].v[3];
-            IdxT o0, o1, o2, o3;
+            const OutT a = OutT(q[t].v[0]), b = OutT(q[t].v[1]), c = OutT(q[t].v[2]), d = OutT(q[t].v[3]);
+            OutT o0, o1, o2, o3;
             switch (j) {
                 case 0: o0 = a; o1 = b; o2 = c; o3 = d; break;
                 case 1: o0 = a; o1 = c; o2 = b; o3 = d; break;
@@ -261,7 +265,7 @@ k_quartets(const TreeView tv, const IdxT *__restrict__ quartets, int64_t n, IdxT
                 case 4: o0 = b; o1 = d; o2 = a; o3 = c; break;
                 default: o0 = c; o1 = d; o2 = a; o3 = b; break;
             }
-            quad_store<IdxT>(out + 4 * (g * P + t), aligned != 0, o0, o1, o2, o3);
+            quad_store<OutT>(out + 4 * (g * P + t), aligned != 0, o0, o1, o2, o3);
         }
     }
 }
@@ -272,10 +276,10 @@ static int st_quartets_per_thread() {  // SUCHTREE_B200_QPT = 1 | 2 (read per la
     return (x == 1 || x == 2) ? x : ST_QPT_DEFAULT;
 }
 
-template <int M, typename IdxT, int P, int MINB, bool SMALL, bool PF = false>
-static int launch_quartets_p(const st_tree *t, const IdxT *d_q, int64_t n, IdxT *d_out,
+template <int M, typename IdxT, int P, int MINB, bool SMALL, bool PF = false, typename OutT = IdxT>
+static int launch_quartets_p(const st_tree *t, const IdxT *d_q, int64_t n, OutT *d_out,
                              cudaStream_t stream, RangeStatus *status) {
-    auto kern = k_quartets<M, IdxT, P, MINB, SMALL, PF>;
+    auto kern = k_quartets<M, IdxT, P, MINB, SMALL, PF, OutT>;
     const int smem = t->query_smem_bytes;
     int rc = st_raise_smem(kern, t->device, smem);
     if (rc != ST_OK) return rc;
@@ -284,8 +288,8 @@ static int launch_quartets_p(const st_tree *t, const IdxT *d_q, int64_t n, IdxT 
     if (per_sm < 1) per_sm = 1;
     const int64_t groups = (n + P - 1) / P;
     const int grid = int(std::min<int64_t>((groups + QQT - 1) / QQT, int64_t(t->sm_count) * per_sm));
-    const uintptr_t al = 4 * sizeof(IdxT);
-    const int aligned = (reinterpret_cast<uintptr_t>(d_q) % al == 0) && (reinterpret_cast<uintptr_t>(d_out) % al == 0);
+    const int aligned = (reinterpret_cast<uintptr_t>(d_q) % (4 * sizeof(IdxT)) == 0) &&
+                        (reinterpret_cast<uintptr_t>(d_out) % (4 * sizeof(OutT)) == 0);
     TreeView view = t->view;
     if (status) view.status = status;
     kern<<<grid, QQT, smem, stream>>>(view, d_q, n, d_out, aligned);
@@ -298,10 +302,8 @@ static int launch_quartets_m(const st_tree *t, const IdxT *d_q, int64_t n, IdxT 
                              cudaStream_t stream, RangeStatus *status) {
     if (t->n_nodes > (int64_t(1) << 29)) return launch_quartets_p<M, IdxT, 1, 4, false>(t, d_q, n, d_out, stream, status);
     if (st_quartets_per_thread() == 2) return launch_quartets_p<M, IdxT, 2, 3, true>(t, d_q, n, d_out, stream, status);
-    if (const char *e = getenv("SUCHTREE_B200_QMINB"))  // experiments: resident CTAs per SM asked of the compiler
-        if (atoi(e) == 5) return launch_quartets_p<M, IdxT, 1, 5, true>(t, d_q, n, d_out, stream, status);
-    if (const char *e = getenv("SUCHTREE_B200_QPF"))  // experiments: prefetch the next iteration's ids
-        if (atoi(e) == 1) return launch_quartets_p<M, IdxT, 1, 4, true, true>(t, d_q, n, d_out, stream, status);
+    // (measured and not kept, profiles/r02_summary.md: 5 resident CTAs per SM -- 48 registers, spills,
+    //  0.59x; prefetching the next iteration's ids, PF = true, 0.94x; two quartets per thread 0.91x)
     return launch_quartets_p<M, IdxT, 1, 4, true>(t, d_q, n, d_out, stream, status);
 }
 
@@ -312,6 +314,20 @@ static int launch_quartets(const st_tree *t, const IdxT *d_q, int64_t n, IdxT *d
     if (t->compact) return launch_quartets_m<1, IdxT>(t, d_q, n, d_out, stream, status);
     if (t->compact_tables) return launch_quartets_m<3, IdxT>(t, d_q, n, d_out, stream, status);
     return launch_quartets_m<0, IdxT>(t, d_q, n, d_out, stream, status);
+}
+
+// int32 ids in, int64 rows out (host path)
+static int launch_quartets_mixed(const st_tree *t, const int32_t *d_q, int64_t n, int64_t *d_out,
+                                 cudaStream_t stream, RangeStatus *status) {
+    if (n == 0) return ST_OK;
+    if (t->n_nodes > (int64_t(1) << 29)) {
+        if (t->compact) return launch_quartets_p<1, int32_t, 1, 4, false, false, int64_t>(t, d_q, n, d_out, stream, status);
+        if (t->compact_tables) return launch_quartets_p<3, int32_t, 1, 4, false, false, int64_t>(t, d_q, n, d_out, stream, status);
+        return launch_quartets_p<0, int32_t, 1, 4, false, false, int64_t>(t, d_q, n, d_out, stream, status);
+    }
+    if (t->compact) return launch_quartets_p<1, int32_t, 1, 4, true, false, int64_t>(t, d_q, n, d_out, stream, status);
+    if (t->compact_tables) return launch_quartets_p<3, int32_t, 1, 4, true, false, int64_t>(t, d_q, n, d_out, stream, status);
+    return launch_quartets_p<0, int32_t, 1, 4, true, false, int64_t>(t, d_q, n, d_out, stream, status);
 }
 
 extern "C" int st_quartet_topologies_device(const st_tree *t, const int64_t *d_quartets, int64_t n,
@@ -334,8 +350,11 @@ extern "C" int st_quartet_topologies_device32(const st_tree *t, const int32_t *d
     return launch_quartets<int32_t>(t, d_quartets, n, d_out, static_cast<cudaStream_t>(stream));
 }
 
-// host buffers: chunks through stream-ordered device scratch, H2D | kernel | D2H
-// overlapped across two streams
+// host buffers: the same 3-slot pipeline as st_distances on a lane of the device's host
+// context -- pack(chunk c+1: int64 ids -> int32 in pinned staging, host pool) | H2D (16 B per
+// quartet) + kernel + D2H (int64 rows, 32 B per quartet) of chunk c | copy-out(chunk c-2).
+// Rows land straight in a page-locked `out` (the shim's result arrays), else in pinned staging
+// first.  Small calls: one kernel over the pinned mappings (zero-copy), one synchronisation.
 extern "C" int st_quartet_topologies(const st_tree *t, const int64_t *quartets, int64_t s0, int64_t s1,
                                      int64_t n, int64_t *out) {
     if (!t || n < 0 || (n > 0 && (!quartets || !out))) {
@@ -347,73 +366,83 @@ extern "C" int st_quartet_topologies(const st_tree *t, const int64_t *quartets, 
     LaneGuard lg(t->device);
     HostLane *lane = lg.lane;
     if (!lane) return ST_ERR_CUDA;
-    const bool contiguous = (s0 == 4 && s1 == 1);
-    const int64_t C = std::min<int64_t>(n, int64_t(1) << 21);
-    int64_t *d_in[2] = {nullptr, nullptr}, *d_o[2] = {nullptr, nullptr};
-    int64_t *h_pack = nullptr;
-    auto cleanup = [&]() {
-        for (int i = 0; i < 2; ++i) {
-            if (d_in[i]) cudaFreeAsync(d_in[i], lane->streams[i]);
-            if (d_o[i]) cudaFreeAsync(d_o[i], lane->streams[i]);
-        }
-        if (h_pack) cudaFreeHost(h_pack);
-    };
-    for (int i = 0; i < 2; ++i) {
-        if (cudaMallocAsync(reinterpret_cast<void **>(&d_in[i]), size_t(C) * 32, lane->streams[i]) != cudaSuccess ||
-            cudaMallocAsync(reinterpret_cast<void **>(&d_o[i]), size_t(C) * 32, lane->streams[i]) != cudaSuccess) {
-            cleanup();
-            st_set_error("st_quartet_topologies: device allocation failed");
-            return ST_ERR_NOMEM;
-        }
-    }
-    if (!contiguous && cudaMallocHost(&h_pack, size_t(C) * 32 * 2) != cudaSuccess) {
-        cleanup();
-        st_set_error("st_quartet_topologies: pinned allocation failed");
-        return ST_ERR_NOMEM;
-    }
-    int rc = ST_OK;
-    int c = 0;
-    for (int64_t done = 0; done < n && rc == ST_OK; ++c) {
-        const int b = c & 1;
-        cudaStream_t st = lane->streams[b];
-        const int64_t m = std::min(C, n - done);
-        const int64_t *src = quartets + done * s0;
-        if (!contiguous) {
-            if (c >= 2) cudaStreamSynchronize(st);  // the pack buffer of this slot is free again
-            int64_t *hp = h_pack + size_t(b) * C * 4;
-            for (int64_t i = 0; i < m; ++i)
-                for (int k = 0; k < 4; ++k) hp[4 * i + k] = src[i * s0 + k * s1];
-            src = hp;
-        }
-        if (cudaMemcpyAsync(d_in[b], src, size_t(m) * 32, cudaMemcpyHostToDevice, st) != cudaSuccess) {
-            st_set_error("st_quartet_topologies: H2D copy failed");
-            rc = ST_ERR_CUDA;
-            break;
-        }
-        rc = launch_quartets<int64_t>(t, d_in[b], m, d_o[b], st, lane->d_status);
-        if (rc != ST_OK) break;
-        if (cudaMemcpyAsync(out + done * 4, d_o[b], size_t(m) * 32, cudaMemcpyDeviceToHost, st) != cudaSuccess) {
-            st_set_error("st_quartet_topologies: D2H copy failed");
-            rc = ST_ERR_CUDA;
-        }
-        done += m;
-    }
-    cudaError_t e0 = cudaStreamSynchronize(lane->streams[0]), e1 = cudaStreamSynchronize(lane->streams[1]);
-    cleanup();
-    if (rc == ST_OK && (e0 != cudaSuccess || e1 != cudaSuccess)) {
-        st_set_error("st_quartet_topologies: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
-        rc = ST_ERR_CUDA;
-    }
-    unsigned long long mxb = 0;
-    long long mnb = 0;
-    const int rc2 = st_lane_read_status(lane, lane->streams[0], &mxb, &mnb);  // also clears the word for the next call
-    if (rc != ST_OK) return rc;
-    if (rc2 != ST_OK) return rc2;
-    if (mxb != 0 || mnb != 0) {
+    auto range_error = [&](unsigned long long mxb, long long mnb) {
         // the reference reports max_id when it is >= size, else min_id (MuchTree.pyx:1303-1310)
         st_set_bad_node(mxb != 0 ? (int64_t)mxb : (int64_t)mnb);
         st_set_error("node id %lld out of bounds (tree size %lld)", (long long)st_bad_node(), (long long)t->n_nodes);
         return ST_ERR_NODE_RANGE;
+    };
+    unsigned long long mxb = 0;
+    long long mnb = 0;
+    int rc = ST_OK;
+    if (n <= ST_MEDIUM_CALL / 4) {  // h_small_in / h_small_out hold ST_MEDIUM_CALL pairs = 1/4 as many int64 rows
+        int32_t *hp = static_cast<int32_t *>(lane->h_small_in);
+        if (st_pack_ids(quartets, s0, s1, n, hp, 4) >> 31) {
+            st_report_range(quartets, s0, s1, n, 4, t->n_nodes);
+            return ST_ERR_NODE_RANGE;
+        }
+        int64_t *ho = static_cast<int64_t *>(lane->h_small_out);
+        cudaStream_t st = lane->streams[0];
+        rc = launch_quartets_mixed(t, hp, n, ho, st, lane->d_status);
+        if (rc != ST_OK) return rc;
+        rc = st_lane_read_status(lane, st, &mxb, &mnb);  // synchronises
+        if (rc != ST_OK) return rc;
+        if (mxb != 0 || mnb != 0) return range_error(mxb, mnb);
+        memcpy(out, ho, size_t(n) * 32);
+        return ST_OK;
     }
+    const bool out_pinned = st_is_pinned(out) && st_is_pinned(out + 4 * n - 1);
+    rc = st_lane_ensure_stage(lane, 4 * n, true, !out_pinned);
+    if (rc != ST_OK) return rc;
+    const int64_t C = lane->stage_pairs / 4;  // rows per chunk: d_out / h_out hold 8 B per staged pair
+    int64_t chunk_begin[ST_LANE_SLOTS] = {0, 0, 0}, chunk_len[ST_LANE_SLOTS] = {0, 0, 0};
+    auto copy_out = [&](int s) {
+        if (!out_pinned && chunk_len[s] > 0)
+            st_parallel_copy(out + 4 * chunk_begin[s], lane->h_out[s], size_t(chunk_len[s]) * 32);
+        chunk_len[s] = 0;
+    };
+    auto quiesce = [&]() {
+        for (int k = 0; k < ST_LANE_SLOTS; ++k) cudaStreamSynchronize(lane->streams[k]);
+        st_lane_read_status(lane, lane->streams[0], &mxb, &mnb);
+    };
+    int64_t done = 0;
+    int c = 0;
+    for (; done < n; ++c) {
+        const int s = c % ST_LANE_SLOTS;
+        const int64_t m = std::min(C, n - done);
+        cudaStream_t st = lane->streams[s];
+        if (c >= ST_LANE_SLOTS) {
+            ST_CUDA(cudaEventSynchronize(lane->ev[s]));
+            copy_out(s);
+        }
+        int32_t *hp = static_cast<int32_t *>(lane->h_in[s]);
+        if (st_pack_ids(quartets + done * s0, s0, s1, m, hp, 4) >> 31) {
+            quiesce();
+            st_report_range(quartets, s0, s1, n, 4, t->n_nodes);
+            return ST_ERR_NODE_RANGE;
+        }
+        int32_t *d_in = static_cast<int32_t *>(lane->d_in[s]);
+        int64_t *d_o = static_cast<int64_t *>(lane->d_out[s]);
+        ST_CUDA(cudaMemcpyAsync(d_in, hp, size_t(m) * 16, cudaMemcpyHostToDevice, st));
+        rc = launch_quartets_mixed(t, d_in, m, d_o, st, lane->d_status);
+        if (rc != ST_OK) {
+            quiesce();
+            return rc;
+        }
+        void *dst = out_pinned ? static_cast<void *>(out + 4 * done) : lane->h_out[s];
+        ST_CUDA(cudaMemcpyAsync(dst, d_o, size_t(m) * 32, cudaMemcpyDeviceToHost, st));
+        ST_CUDA(cudaEventRecord(lane->ev[s], st));
+        chunk_begin[s] = done;
+        chunk_len[s] = m;
+        done += m;
+    }
+    for (int k = 0; k < ST_LANE_SLOTS && k < c; ++k) {
+        const int s = (c - std::min(c, ST_LANE_SLOTS) + k) % ST_LANE_SLOTS;
+        ST_CUDA(cudaStreamSynchronize(lane->streams[s]));
+        copy_out(s);
+    }
+    rc = st_lane_read_status(lane, lane->streams[0], &mxb, &mnb);
+    if (rc != ST_OK) return rc;
+    if (mxb != 0 || mnb != 0) return range_error(mxb, mnb);
     return ST_OK;
 }

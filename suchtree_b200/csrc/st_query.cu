@@ -18,10 +18,6 @@
 #include <cmath>
 #include <cstring>
 #include <vector>
-#if defined(__SSE2__)
-#include <emmintrin.h>
-#endif
-
 #include "st_device.cuh"
 #include "st_hostctx.cuh"
 #include "st_hostpool.cuh"
@@ -400,86 +396,6 @@ extern "C" int st_random_leaf_pairs_device(const st_tree *t, uint64_t seed, int6
 // Every call owns its lane's range-status word: concurrent callers on one tree neither
 // queue on a mutex nor see each other's out-of-range flags.
 
-// int64 ids -> int32, OR of everything seen (bit 31 and above set <=> some id is
-// negative or >= 2^31: the rare error path then finds the exact id)
-static uint64_t pack_ids_contig(const int64_t *__restrict__ src, int32_t *__restrict__ dst, int64_t count) {
-    uint64_t acc = 0;
-    int64_t i = 0;
-#if defined(__SSE2__)
-    // 4 ids per step; streaming stores: the staging buffer is read next by the DMA
-    // engine, not by this core, so skip the read-for-ownership of its lines
-    while (i < count && (reinterpret_cast<uintptr_t>(dst + i) & 15)) {
-        const int64_t v = src[i];
-        acc |= uint64_t(v);
-        dst[i++] = int32_t(v);
-    }
-    __m128i vacc = _mm_setzero_si128();
-    for (; i + 8 <= count; i += 8) {
-        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i));
-        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 2));
-        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 4));
-        const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 6));
-        vacc = _mm_or_si128(vacc, _mm_or_si128(_mm_or_si128(a, b), _mm_or_si128(c, d)));
-        const __m128 lo = _mm_shuffle_ps(_mm_castsi128_ps(a), _mm_castsi128_ps(b), _MM_SHUFFLE(2, 0, 2, 0));
-        const __m128 hi = _mm_shuffle_ps(_mm_castsi128_ps(c), _mm_castsi128_ps(d), _MM_SHUFFLE(2, 0, 2, 0));
-        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i), _mm_castps_si128(lo));
-        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 4), _mm_castps_si128(hi));
-    }
-    alignas(16) uint64_t lanes[2];
-    _mm_store_si128(reinterpret_cast<__m128i *>(lanes), vacc);
-    acc |= lanes[0] | lanes[1];
-    _mm_sfence();
-#endif
-    for (; i < count; ++i) {
-        const int64_t v = src[i];
-        acc |= uint64_t(v);
-        dst[i] = int32_t(v);
-    }
-    return acc;
-}
-static uint64_t pack_pairs(const int64_t *src, int64_t s0, int64_t s1, int64_t m, int32_t *dst, int width) {
-    const bool contiguous = (s1 == 1 && s0 == width);
-    const int parts = int(std::min<int64_t>(st_host_threads(), m / 32768 + 1));
-    std::vector<uint64_t> accs(size_t(parts), 0);
-    st_parallel_for(parts, [&](int p, int np) {
-        const int64_t b = m * p / np, e = m * (p + 1) / np;
-        uint64_t acc = 0;
-        if (contiguous) {
-            acc = pack_ids_contig(src + b * width, dst + b * width, (e - b) * width);
-        } else {
-            for (int64_t i = b; i < e; ++i)
-                for (int k = 0; k < width; ++k) {
-                    const int64_t v = src[i * s0 + k * s1];
-                    acc |= uint64_t(v);
-                    dst[i * width + k] = int32_t(v);
-                }
-        }
-        accs[size_t(p)] = acc;
-    });
-    uint64_t acc = 0;
-    for (uint64_t a : accs) acc |= a;
-    return acc;
-}
-static void parallel_copy(void *dst, const void *src, size_t bytes) {
-    const int parts = int(std::min<size_t>(size_t(st_host_threads()), bytes / (size_t(1) << 20) + 1));
-    st_parallel_for(parts, [&](int p, int np) {
-        const size_t b = bytes * size_t(p) / size_t(np), e = bytes * size_t(p + 1) / size_t(np);
-        memcpy(static_cast<char *>(dst) + b, static_cast<const char *>(src) + b, e - b);
-    });
-}
-// the reference's report for an out-of-range array: max id if it is >= size, else min id
-static void report_range(const int64_t *src, int64_t s0, int64_t s1, int64_t n, int width, int64_t n_nodes) {
-    int64_t mx = INT64_MIN, mn = INT64_MAX;
-    for (int64_t i = 0; i < n; ++i)
-        for (int k = 0; k < width; ++k) {
-            const int64_t v = src[i * s0 + k * s1];
-            mx = v > mx ? v : mx;
-            mn = v < mn ? v : mn;
-        }
-    st_set_bad_node(mx >= n_nodes ? mx : mn);
-    st_set_error("node id %lld out of bounds (tree size %lld)", (long long)st_bad_node(), (long long)n_nodes);
-}
-
 // Latency path for small and medium calls (distance(a,b), common_ancestor(a,b), lists up to
 // 2^18 pairs): the ids are packed on the host into pinned staging, ONE kernel reads them and
 // writes the results through the pinned mappings (zero-copy over PCIe), one synchronisation.
@@ -503,8 +419,8 @@ static int host_pairs_small(const st_tree *t, HostLane *lane, const int64_t *pai
                          (long long)t->n_nodes);
             return ST_ERR_NODE_RANGE;
         }
-    } else if (pack_pairs(pairs, s0, s1, n, hp, 2) >> 31) {  // negative or beyond int32
-        report_range(pairs, s0, s1, n, 2, t->n_nodes);
+    } else if (st_pack_ids(pairs, s0, s1, n, hp, 2) >> 31) {  // negative or beyond int32
+        st_report_range(pairs, s0, s1, n, 2, t->n_nodes);
         return ST_ERR_NODE_RANGE;
     }
     void *ho = lane->h_small_out;
@@ -521,14 +437,14 @@ static int host_pairs_small(const st_tree *t, HostLane *lane, const int64_t *pai
         rc = st_lane_read_status(lane, st, &mxb, &mnb);
         if (rc != ST_OK) return rc;
         if (mxb != 0 || mnb != 0) {
-            report_range(pairs, s0, s1, n, 2, t->n_nodes);
+            st_report_range(pairs, s0, s1, n, 2, t->n_nodes);
             return ST_ERR_NODE_RANGE;
         }
     }
     const size_t bytes = size_t(n) * (out_d ? 8 : 4);
     void *dst = out_d ? static_cast<void *>(out_d) : static_cast<void *>(out_m);
     if (tiny) memcpy(dst, ho, bytes);
-    else parallel_copy(dst, ho, bytes);
+    else st_parallel_copy(dst, ho, bytes);
     return ST_OK;
 }
 
@@ -571,7 +487,7 @@ static int host_pairs_run(const st_tree *t, const int64_t *pairs, int64_t s0, in
     int64_t chunk_begin[ST_LANE_SLOTS] = {0, 0, 0}, chunk_len[ST_LANE_SLOTS] = {0, 0, 0};
     auto copy_out = [&](int s) {  // results of the chunk last issued on slot s -> caller's buffer
         if (!out_pinned && chunk_len[s] > 0)
-            parallel_copy(user_out + size_t(chunk_begin[s]) * out_elem, lane->h_out[s],
+            st_parallel_copy(user_out + size_t(chunk_begin[s]) * out_elem, lane->h_out[s],
                           size_t(chunk_len[s]) * out_elem);
         chunk_len[s] = 0;
     };
@@ -603,10 +519,10 @@ static int host_pairs_run(const st_tree *t, const int64_t *pairs, int64_t s0, in
                                     cudaMemcpyHostToDevice, st));
         if (mp > 0) {
             int32_t *hp = static_cast<int32_t *>(lane->h_in[s]);
-            const uint64_t acc = pack_pairs(src, s0, s1, mp, hp, 2);
+            const uint64_t acc = st_pack_ids(src, s0, s1, mp, hp, 2);
             if (acc >> 31) {  // a negative id, or one beyond int32: cannot be a node of any tree
                 quiesce();
-                report_range(pairs, s0, s1, n, 2, t->n_nodes);
+                st_report_range(pairs, s0, s1, n, 2, t->n_nodes);
                 return ST_ERR_NODE_RANGE;
             }
             ST_CUDA(cudaMemcpyAsync(d_in, hp, size_t(mp) * 8, cudaMemcpyHostToDevice, st));
@@ -662,14 +578,14 @@ extern "C" int st_bench_pack(int64_t n_pairs, int iters, double *pairs_per_s) {
         return ST_ERR_NOMEM;
     }
     for (int64_t i = 0; i < 2 * n_pairs; ++i) src[i] = i & 0xffff;
-    uint64_t acc = pack_pairs(src, 2, 1, n_pairs, dst, 2);  // warm (page touch)
+    uint64_t acc = st_pack_ids(src, 2, 1, n_pairs, dst, 2);  // warm (page touch)
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     cudaEventRecord(e0);
     cudaEventSynchronize(e0);
     auto t0 = std::chrono::steady_clock::now();
-    for (int it = 0; it < iters; ++it) acc |= pack_pairs(src, 2, 1, n_pairs, dst, 2);
+    for (int it = 0; it < iters; ++it) acc |= st_pack_ids(src, 2, 1, n_pairs, dst, 2);
     const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);

@@ -590,7 +590,10 @@ class SuchTree:
         if any(s % 8 for s in quartets.strides):
             quartets = np.ascontiguousarray(quartets)
         n = quartets.shape[0]
-        out = np.zeros((n, 4), dtype=np.int64)
+        if n * 32 >= _lib.PINNED_RESULT_MIN_BYTES:
+            out = _lib.pinned_empty((n, 4), np.int64)  # every row is written by the kernel
+        else:
+            out = np.zeros((n, 4), dtype=np.int64)
         s0, s1 = quartets.strides[0] // 8, quartets.strides[1] // 8
         rc = _lib.lib().st_quartet_topologies(self._handle, quartets.ctypes.data, s0, s1, n, out.ctypes.data)
         _lib.check(rc, self.size)
