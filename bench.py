@@ -303,18 +303,19 @@ def measured_peak():
 def ncu_traffic(build_id, n_pairs):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the
     committed `ncu --set full` capture (profiles/traffic.json) -- only if that capture was
-    taken from THIS binary (same st_build_id) and launch size; otherwise null, with the reason."""
+    taken from THIS pair kernel (same st_pairs_kernel_id: hash of its sources and compiler
+    flags) and launch size; otherwise null, with the reason."""
     p = os.path.join(REPO, "profiles", "traffic.json")
     try:
         with open(p) as f:
             t = json.load(f)
     except Exception:
         return None, "no profiles/traffic.json"
-    if t.get("build_id") != build_id:
-        return None, "stale: captured from build %s, this is %s (%s)" % (t.get("build_id"), build_id, t.get("capture"))
+    if t.get("pairs_kernel_id") != build_id:
+        return None, "stale: captured from kernel %s, this is %s (%s)" % (t.get("pairs_kernel_id"), build_id, t.get("capture"))
     if int(t.get("pairs_per_launch", 0)) != int(n_pairs):
         return None, "captured at %s pairs per launch" % t.get("pairs_per_launch")
-    return t.get("k_pairs_dram_bytes_per_launch"), "ncu capture %s (build %s)" % (t.get("capture"), build_id)
+    return t.get("k_pairs_dram_bytes_per_launch"), "ncu capture %s (pair kernel %s)" % (t.get("capture"), build_id)
 
 
 def run_ours(args):
@@ -498,7 +499,7 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     per_launch_s = ms * 1e-3 / args.steps
     achieved = 16.0 * n_pairs / per_launch_s / 1e9
-    traffic, traffic_src = ncu_traffic(_lib.lib().st_build_id().decode(), n_pairs)
+    traffic, traffic_src = ncu_traffic(_lib.lib().st_pairs_kernel_id().decode(), n_pairs)
     gather = None
     if rank == 0:
         sps = C.c_double(0)

@@ -77,6 +77,9 @@ ST_API int st_version(void);
 /* hash of the CUDA sources this binary was compiled from (suchtree_b200/build.py); the
  * Python loader compares it with the sources on disk and rebuilds a stale library */
 ST_API const char *st_build_id(void);
+/* hash of the sources of the pair kernel alone (st_query.cu, st_device.cuh, st_internal.cuh):
+ * the stamp on profiles/traffic.json, so that an ncu figure is never quoted for another kernel */
+ST_API const char *st_pairs_kernel_id(void);
 ST_API int st_device_count(int *count);
 
 /* ---- tree: replaces `cdef struct Node` + SuchTree.__init__'s fill/depth passes

@@ -54,6 +54,7 @@ SIGNATURES = {
     "st_last_error": (C.c_char_p, []),
     "st_version": (_int, []),
     "st_build_id": (C.c_char_p, []),
+    "st_pairs_kernel_id": (C.c_char_p, []),
     "st_device_count": (_int, [C.POINTER(_int)]),
     "st_tree_create": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _int, _int, C.POINTER(_vp)]),
     "st_tree_create_ex": (_int, [_int, _i64, _vp, _vp, _vp, _vp, _int, _int, _int, C.POINTER(_vp)]),

@@ -66,6 +66,18 @@ def source_id(which="product"):
     return h.hexdigest()[:16]
 
 
+def pairs_kernel_id():
+    """sha1 over the sources the pair kernel (k_pairs, the kernel bench.py's roofline is about)
+    is compiled from: profiles/traffic.json is stamped with it, so the ncu DRAM-traffic figure
+    is only reported for the kernel it was captured from."""
+    h = hashlib.sha1()
+    for name in ("st_query.cu", "st_device.cuh", "st_internal.cuh"):
+        with open(os.path.join(CSRC, name), "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()[:16]
+
+
 def _id_file(lib):
     return lib + ".id"
 
@@ -116,6 +128,8 @@ def _build_one(which, force, verbose, extra):
         carries_id = base in ("st_index", "st_bench_gather")
         if carries_id:  # the TU that answers st_build_id(): recompiled whenever anything changed
             f = flags + ['-DST_BUILD_ID="%s"' % sid]
+        if base == "st_query":
+            f = flags + ['-DST_PAIRS_KERNEL_ID="%s"' % pairs_kernel_id()]
         stale = not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_t)
         if force or extra or stale or (carries_id and built_id(lib) != sid):
             jobs.append((src, obj, f, verbose))

@@ -316,6 +316,11 @@ int st_read_range_status(const st_tree *t, cudaStream_t stream, bool *bad) {
     return ST_OK;
 }
 
+#ifndef ST_PAIRS_KERNEL_ID
+#define ST_PAIRS_KERNEL_ID "unknown"
+#endif
+extern "C" const char *st_pairs_kernel_id(void) { return ST_PAIRS_KERNEL_ID; }
+
 // ------------------------------------------------------------ device API ----
 extern "C" int st_distances_device(const st_tree *t, const void *d_pairs, int idx_bits, int64_t n,
                                    double *d_out, int32_t *d_mrca, void *stream) {
