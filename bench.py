@@ -957,8 +957,8 @@ def run_other_workloads(args, rank, world, local, dev, peak):
                             "100k-leaf Yule trees, 100k random links (cfg4's), one GPU" % int(scan["node_ids"].shape[0]),
                 "clades_computed": int(done.sum()), "link_pairs": int(scan["n_pairs"].sum()),
                 "link_pairs_per_s": float(scan["n_pairs"].sum()) / dt, "s_per_scan": dt,
-                "timing": "host wall clock around the Python call (link sort + work-item plan on the host, "
-                          "3 kernels, moments read back)",
+                "timing": "host wall clock around the Python call (plan, shift, moments and fold kernels on the "
+                          "device; sorted links and prefix counts kept in the st_links handle; moments read back)",
             }
             del SLT3, A3, B3
         except Exception as e:  # diagnostics only

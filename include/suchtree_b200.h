@@ -307,6 +307,13 @@ ST_API int st_links_sample_moments(const st_links *links, uint64_t seed, int64_t
 ST_API int st_links_linked_moments(const st_links *links, int64_t first_pair, int64_t n_pairs, double x0,
                             double y0, void *nccl_comm, st_moments *out);
 
+/* = st_clade_moments on the handle: the links sorted by the scanned side's id and their
+ * prefix counts are built once per handle and side and kept on the device; the per-call plan
+ * (runs, eligible clades, work items) is made by kernels, not on the host. */
+ST_API int st_links_clade_moments(const st_links *links, int side, const int64_t *clade_lo,
+                           const int64_t *clade_hi, int64_t n_clades, int64_t min_links,
+                           int64_t max_links, st_moments *out, int64_t *n_links_out);
+
 /* ---- NCCL plumbing for the moment all-reduce (libnccl.so.2 is dlopen'ed on first use; a
  *      single-GPU process never loads it).  id128: 128 bytes (ncclUniqueId) produced on one
  * rank by st_nccl_unique_id and handed to the others by whatever rendezvous the host has

@@ -102,6 +102,7 @@ SIGNATURES = {
         _int, [_vp, _u64, _i64, _i64, C.c_double, C.c_double, _vp, C.POINTER(Moments)]),
     "st_links_linked_moments": (
         _int, [_vp, _i64, _i64, C.c_double, C.c_double, _vp, C.POINTER(Moments)]),
+    "st_links_clade_moments": (_int, [_vp, _int, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "st_nccl_version": (_int, [C.POINTER(_int)]),
     "st_nccl_unique_id": (_int, [_vp]),
     "st_nccl_comm_create": (_int, [_int, _int, _int, _vp, C.POINTER(_vp)]),

@@ -7,7 +7,9 @@
 // (size,2) int64 id arrays the reference materialises are only written when the
 // caller asks for them.
 #include <algorithm>
+#include <climits>
 #include <cmath>
+#include <mutex>
 #include <vector>
 
 #include <new>
@@ -103,6 +105,13 @@ struct st_links {
     int64_t L = 0;
     int32_t *col_a = nullptr, *col_b = nullptr;  // linklist[:,1] (TreeA ids), linklist[:,0] (TreeB ids)
     int2 *rows = nullptr;                        // (b, a) per link, for the samplers
+    // per-clade scans (st_links_clade_moments), built on first use per side (0: TreeB, 1: TreeA):
+    // the links sorted (stably) by their id on that side, and first[v] = number of links with
+    // side id < v -- a clade (an id interval) is then the run [first[lo], first[hi + 1])
+    std::vector<int2> h_rows;
+    mutable std::mutex scan_mu;
+    mutable int2 *rows_sorted[2] = {nullptr, nullptr};
+    mutable int32_t *first[2] = {nullptr, nullptr};
 };
 
 static int check_pair_of_trees(const st_tree *ta, const st_tree *tb, const int64_t *linklist, int64_t L) {
@@ -123,6 +132,10 @@ extern "C" void st_links_destroy(st_links *k) {
     cudaFree(k->col_a);
     cudaFree(k->col_b);
     cudaFree(k->rows);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(k->rows_sorted[i]);
+        cudaFree(k->first[i]);
+    }
     delete k;
 }
 
@@ -161,6 +174,7 @@ extern "C" int st_links_create(const st_tree *ta, const st_tree *tb, const int64
     k->tb = tb;
     k->device = ta->device;
     k->L = L;
+    k->h_rows = rows;
     const size_t n = size_t(std::max<int64_t>(L, 1));
     if (cudaMalloc(reinterpret_cast<void **>(&k->col_a), n * 4) != cudaSuccess ||
         cudaMalloc(reinterpret_cast<void **>(&k->col_b), n * 4) != cudaSuccess ||
@@ -722,18 +736,139 @@ extern "C" int st_linked_moments(const st_tree *ta, const st_tree *tb, const int
 // assignment gives the same result: each item owns its partial, folded per clade in item order).
 struct CladeItem {
     int64_t first;  // first pair of the item in the clade's own (i, j<i) enumeration
-    int32_t clade;  // slot among the eligible clades
+    int32_t clade;  // index of the clade in the caller's arrays
     int32_t len;    // pairs in the item
 };
 static_assert(sizeof(CladeItem) == 16, "CladeItem is one 16-byte load");
 
-// x0, y0 of every clade: the distances of its first link pair (conditioning shift, as in
-// SuchLinkedTrees.linked_pearson)
-__global__ void k_clade_shift(const TreeView ta, const TreeView tb, const int2 *__restrict__ links,
-                              const int64_t *__restrict__ run_begin, int32_t n_clades,
-                              double2 *__restrict__ shift) {
+// The PLAN runs on the device too (round 1 built it on the host: a counting sort of the links,
+// run bounds, the eligible clades and the item list, per call): the sorted links and the prefix
+// counts belong to the st_links handle (built once per side), and per call
+//   k_clade_runs   clade -> run of links, eligibility, pair count; total pair count
+//   k_clade_chunk  item size from the total (at most ~2^20 items, at least 4096 pairs each)
+//   k_clade_count  items per clade  -> exclusive scan -> first item of every clade
+//   k_clade_items  one warp per clade writes its items
+// One 16-byte read-back (item count) sizes the partials; then shift | moments | fold as before.
+struct CladeMeta {
+    unsigned long long total_pairs;
+    long long chunk;
+    int32_t n_items, overflow;
+};
+
+__global__ void k_clade_runs(const int32_t *__restrict__ first, int64_t n_side, const int64_t *__restrict__ lo,
+                             const int64_t *__restrict__ hi, int32_t n_clades, int64_t min_links,
+                             int64_t max_links, int32_t *__restrict__ run_begin, int32_t *__restrict__ run_len,
+                             int64_t *__restrict__ pairs, CladeMeta *meta) {
+    const int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long mine = 0;
+    if (c < n_clades) {
+        // links with lo <= id <= hi (bounds clamped to the tree)
+        const int64_t l = lo[c] > 0 ? lo[c] : 0, h = hi[c] < n_side - 1 ? hi[c] : n_side - 1;
+        const int32_t s = l <= h ? first[l] : 0;
+        const int64_t n = l <= h ? int64_t(first[h + 1]) - s : 0;
+        run_begin[c] = s;
+        run_len[c] = int32_t(n);
+        const bool elig = n >= min_links && n <= max_links;
+        const int64_t p = elig ? n * (n - 1) / 2 : 0;
+        pairs[c] = p;
+        mine = (unsigned long long)p;
+    }
+    // integer sum: exact, order-independent
+    for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&meta->total_pairs, mine);
+}
+
+__global__ void k_clade_chunk(CladeMeta *meta) {
+    // items of at most `chunk` pairs (a multiple of 32), about 2^20 of them at most
+    long long chunk = ((long long)(meta->total_pairs >> 20) + 31) & ~31ll;
+    chunk = chunk < 4096 ? 4096 : (chunk > (1ll << 30) ? (1ll << 30) : chunk);
+    meta->chunk = chunk;
+}
+
+__global__ void k_clade_count(const int64_t *__restrict__ pairs, int32_t n_clades, const CladeMeta *meta,
+                              int32_t *__restrict__ items) {
     const int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_clades) return;
+    const long long chunk = meta->chunk;
+    items[c] = int32_t((pairs[c] + chunk - 1) / chunk);
+}
+
+// ---- exclusive scan of int32 (1024 elements per CTA, recursive over the CTA sums) ----
+__global__ void __launch_bounds__(1024)
+k_scan_block(const int32_t *__restrict__ in, int32_t n, int32_t *__restrict__ out, int32_t *__restrict__ sums) {
+    __shared__ int32_t warp_tot[32];
+    const int32_t i = blockIdx.x * 1024 + threadIdx.x;
+    const int32_t v = i < n ? in[i] : 0;
+    int32_t x = v;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        int32_t t = warp_tot[lane];
+        for (int o = 1; o < 32; o <<= 1) {
+            const int32_t y = __shfl_up_sync(0xffffffffu, t, o);
+            if (lane >= o) t += y;
+        }
+        warp_tot[lane] = t;  // inclusive over warps
+    }
+    __syncthreads();
+    const int32_t before = w ? warp_tot[w - 1] : 0;
+    if (i < n) out[i] = before + x - v;  // exclusive
+    if (threadIdx.x == 1023 && sums) sums[blockIdx.x] = before + x;
+}
+__global__ void k_scan_add(int32_t *__restrict__ out, int32_t n, const int32_t *__restrict__ offs) {
+    const int32_t i = blockIdx.x * 1024 + threadIdx.x;
+    if (i < n) out[i] += offs[blockIdx.x];
+}
+// scratch: room for ceil(n/1024) + ceil(n/1024^2) + ... + 1 ints (<= n/1000 + 8)
+static void exclusive_scan_i32(const int32_t *in, int32_t n, int32_t *out, int32_t *scratch, cudaStream_t s) {
+    const int32_t nb = (n + 1023) / 1024;
+    k_scan_block<<<nb, 1024, 0, s>>>(in, n, out, nb > 1 ? scratch : nullptr);
+    if (nb > 1) {
+        exclusive_scan_i32(scratch, nb, scratch, scratch + nb, s);  // in place: every CTA reads before it writes
+        k_scan_add<<<nb, 1024, 0, s>>>(out, n, scratch);
+    }
+}
+
+// total item count (last exclusive prefix + last count); more than 2^31 items cannot be indexed
+__global__ void k_clade_total(const int32_t *__restrict__ item_begin, const int32_t *__restrict__ items,
+                              int32_t n_clades, CladeMeta *meta) {
+    const long long t = (long long)item_begin[n_clades - 1] + items[n_clades - 1];
+    meta->n_items = int32_t(t);
+    meta->overflow = t > 0x7fffffffll || t < 0;
+}
+
+__global__ void k_clade_items(const int64_t *__restrict__ pairs, const int32_t *__restrict__ item_begin,
+                              const int32_t *__restrict__ n_items_of, int32_t n_clades, const CladeMeta *meta,
+                              CladeItem *__restrict__ items) {
+    const int32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= n_clades) return;
+    const int32_t cnt = n_items_of[c];
+    if (cnt == 0) return;
+    const long long chunk = meta->chunk;
+    const int64_t p = pairs[c];
+    CladeItem *dst = items + item_begin[c];
+    for (int32_t k = lane; k < cnt; k += 32) {
+        const int64_t f = int64_t(k) * chunk;
+        dst[k] = CladeItem{f, c, int32_t(p - f < chunk ? p - f : chunk)};
+    }
+}
+
+// x0, y0 of every computed clade: the distances of its first link pair (conditioning shift, as in
+// SuchLinkedTrees.linked_pearson)
+__global__ void k_clade_shift(const TreeView ta, const TreeView tb, const int2 *__restrict__ links,
+                              const int32_t *__restrict__ run_begin, const int32_t *__restrict__ n_items_of,
+                              int32_t n_clades, double2 *__restrict__ shift) {
+    const int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_clades) return;
+    if (n_items_of[c] == 0) {
+        shift[c] = make_double2(0.0, 0.0);
+        return;
+    }
     const int2 l1 = __ldg(links + run_begin[c]), l2 = __ldg(links + run_begin[c] + 1);
     shift[c] = make_double2(linked_query<2>(ta, st_global_tables(ta), l1.y, l2.y),
                             linked_query<2>(tb, st_global_tables(tb), l1.x, l2.x));
@@ -742,7 +877,7 @@ __global__ void k_clade_shift(const TreeView ta, const TreeView tb, const int2 *
 template <int MA, int MB>
 __global__ void __launch_bounds__(MLT)
 k_clade_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ links,
-                const int64_t *__restrict__ run_begin, const double2 *__restrict__ shift,
+                const int32_t *__restrict__ run_begin, const double2 *__restrict__ shift,
                 const CladeItem *__restrict__ items, int32_t n_items, int32_t *__restrict__ next_item,
                 double *__restrict__ partials /* [n_items][5] */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -793,181 +928,201 @@ k_clade_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ l
     }
 }
 
-// one warp per clade folds the partials of its items in a fixed order
+// one warp per clade folds the partials of its items in a fixed order and writes the clade's
+// st_moments row {n, x0, y0, sx, sy, sxx, syy, sxy} (all zero when the clade was not computed)
 __global__ void k_clade_fold(const double *__restrict__ partials, const int32_t *__restrict__ item_begin,
-                             int32_t n_clades, double *__restrict__ out /* [n_clades][5] */) {
+                             const int32_t *__restrict__ n_items_of, const int64_t *__restrict__ pairs,
+                             const double2 *__restrict__ shift, const int32_t *__restrict__ run_len,
+                             int32_t n_clades, double *__restrict__ out /* [n_clades][8] */,
+                             int64_t *__restrict__ n_links_out) {
     const int32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= n_clades) return;
-    const int32_t b = item_begin[c], e = item_begin[c + 1];
+    const int32_t b = item_begin[c], e = b + n_items_of[c];
     double v[5] = {0, 0, 0, 0, 0};
     for (int32_t it = b + lane; it < e; it += 32)
 #pragma unroll
         for (int k = 0; k < 5; ++k) v[k] += partials[size_t(it) * 5 + k];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        const double s = warp_sum(v[k]);
-        if (lane == 0) out[size_t(c) * 5 + k] = s;
+    for (int k = 0; k < 5; ++k) v[k] = warp_sum(v[k]);
+    if (lane == 0) {
+        double *o = out + size_t(c) * 8;
+        const bool done = e > b;
+        o[0] = done ? double(pairs[c]) : 0.0;
+        o[1] = done ? shift[c].x : 0.0;
+        o[2] = done ? shift[c].y : 0.0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) o[3 + k] = done ? v[k] : 0.0;
+        if (n_links_out) n_links_out[c] = run_len[c];
     }
 }
 
-extern "C" int st_clade_moments(const st_tree *ta, const st_tree *tb, const int64_t *linklist, int64_t L,
-                                int side, const int64_t *clade_lo, const int64_t *clade_hi,
-                                int64_t n_clades, int64_t min_links, int64_t max_links, st_moments *out,
-                                int64_t *n_links_out) {
-    int rc = check_pair_of_trees(ta, tb, linklist, L);
-    if (rc != ST_OK) return rc;
-    if ((side != 0 && side != 1) || n_clades < 0 || (n_clades > 0 && (!clade_lo || !clade_hi || !out)) ||
-        L >= (int64_t(1) << 31)) {
+// links sorted by the id on `side` + prefix counts, on the device, once per handle and side
+static int ensure_scan_index(const st_links *k, int side) {
+    std::lock_guard<std::mutex> lock(k->scan_mu);
+    if (k->rows_sorted[side]) return ST_OK;
+    const int64_t L = k->L;
+    const int64_t n_side = side == 0 ? k->tb->n_nodes : k->ta->n_nodes;
+    // counting sort over the node ids (stable), O(links + nodes)
+    std::vector<int32_t> first(static_cast<size_t>(n_side) + 1, 0);
+    auto key = [&](int64_t i) { return side == 0 ? k->h_rows[size_t(i)].x : k->h_rows[size_t(i)].y; };
+    for (int64_t i = 0; i < L; ++i) ++first[size_t(key(i)) + 1];
+    for (int64_t v = 0; v < n_side; ++v) first[size_t(v) + 1] += first[size_t(v)];
+    std::vector<int2> rows(static_cast<size_t>(std::max<int64_t>(L, 1)));
+    {
+        std::vector<int32_t> next(first.begin(), first.end() - 1);
+        for (int64_t i = 0; i < L; ++i) rows[size_t(next[size_t(key(i))]++)] = k->h_rows[size_t(i)];
+    }
+    int2 *d_rows = nullptr;
+    int32_t *d_first = nullptr;
+    if (cudaMalloc(reinterpret_cast<void **>(&d_rows), rows.size() * 8) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void **>(&d_first), first.size() * 4) != cudaSuccess ||
+        cudaMemcpy(d_rows, rows.data(), rows.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(d_first, first.data(), first.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+        st_set_error("st_clade_moments: building the scan index failed: %s", cudaGetErrorString(cudaGetLastError()));
+        cudaFree(d_rows);
+        cudaFree(d_first);
+        return ST_ERR_CUDA;
+    }
+    k->first[side] = d_first;
+    k->rows_sorted[side] = d_rows;
+    return ST_OK;
+}
+
+extern "C" int st_links_clade_moments(const st_links *k, int side, const int64_t *clade_lo,
+                                      const int64_t *clade_hi, int64_t n_clades, int64_t min_links,
+                                      int64_t max_links, st_moments *out, int64_t *n_links_out) {
+    if (!k || (side != 0 && side != 1) || n_clades < 0 || (n_clades > 0 && (!clade_lo || !clade_hi || !out)) ||
+        n_clades >= (int64_t(1) << 31)) {
         st_set_error("st_clade_moments: bad arguments (side must be 0 or 1, clade arrays and out non-NULL)");
         return ST_ERR_INVALID_ARG;
     }
+    if (n_clades == 0) return ST_OK;
     if (min_links < 2) min_links = 2;  // a pair needs two links
     if (max_links < 0) max_links = INT64_MAX;
-    for (int64_t i = 0; i < L; ++i) {
-        const int64_t vb = linklist[2 * i], va = linklist[2 * i + 1];
-        if (va < 0 || va >= ta->n_nodes || vb < 0 || vb >= tb->n_nodes) {
-            const bool a_bad = va < 0 || va >= ta->n_nodes;
-            st_set_bad_node(a_bad ? va : vb);
-            st_set_error("linklist row %lld: %s id %lld out of bounds", (long long)i, a_bad ? "TreeA" : "TreeB",
-                         (long long)(a_bad ? va : vb));
-            return ST_ERR_NODE_RANGE;
-        }
-    }
-    // links sorted (stably) by the id on the scanned side -- a counting sort over the node ids,
-    // O(links + nodes) -- so that every clade is a run: first[v] = number of links with id < v
-    const int64_t n_side = side == 0 ? tb->n_nodes : ta->n_nodes;
-    std::vector<int32_t> first(static_cast<size_t>(n_side) + 1, 0);
-    for (int64_t i = 0; i < L; ++i) ++first[size_t(linklist[2 * i + side]) + 1];
-    for (int64_t v = 0; v < n_side; ++v) first[size_t(v) + 1] += first[size_t(v)];
-    std::vector<int2> rows(static_cast<size_t>(L));
-    {
-        std::vector<int32_t> next(first.begin(), first.end() - 1);
-        for (int64_t i = 0; i < L; ++i)
-            rows[size_t(next[size_t(linklist[2 * i + side])]++)] =
-                make_int2(int32_t(linklist[2 * i]), int32_t(linklist[2 * i + 1]));
-    }
-    // runs, eligible clades, work items
-    std::vector<int64_t> run_begin;   // per eligible clade
-    std::vector<int64_t> slot_clade;  // eligible slot -> caller's clade index
-    std::vector<int64_t> run_len;
-    double total_pairs = 0.0;
-    for (int64_t c = 0; c < n_clades; ++c) {
-        // links with clade_lo <= id <= clade_hi (bounds clamped to the tree)
-        const int64_t lo = std::max<int64_t>(clade_lo[c], 0), hi = std::min<int64_t>(clade_hi[c], n_side - 1);
-        const int64_t s = lo <= hi ? first[size_t(lo)] : 0;
-        const int64_t n = lo <= hi ? first[size_t(hi) + 1] - s : 0;
-        if (n_links_out) n_links_out[c] = n;
-        out[c].n = 0.0;
-        out[c].x0 = out[c].y0 = out[c].sx = out[c].sy = out[c].sxx = out[c].syy = out[c].sxy = 0.0;
-        if (n < min_links || n > max_links) continue;
-        run_begin.push_back(s);
-        run_len.push_back(n);
-        slot_clade.push_back(c);
-        total_pairs += double(n) * double(n - 1) * 0.5;
-    }
-    const int64_t n_elig = int64_t(run_begin.size());
-    if (n_elig == 0) return ST_OK;
-    if (n_elig >= (int64_t(1) << 31) || total_pairs >= 9.0e18) {
-        st_set_error("st_clade_moments: too much work for one call (%lld clades, %.3g pairs)", (long long)n_elig,
-                     total_pairs);
-        return ST_ERR_INVALID_ARG;
-    }
-    // items of at most `chunk` pairs (a multiple of 32), about 2^20 of them at most
-    int64_t chunk = (int64_t(total_pairs / double(int64_t(1) << 20)) + 31) & ~int64_t(31);
-    chunk = std::min<int64_t>(std::max<int64_t>(chunk, 4096), int64_t(1) << 30);
-    std::vector<CladeItem> items;
-    std::vector<int32_t> item_begin(size_t(n_elig) + 1, 0);
-    for (int64_t c = 0; c < n_elig; ++c) {
-        const int64_t pairs = run_len[size_t(c)] * (run_len[size_t(c)] - 1) / 2;
-        for (int64_t p = 0; p < pairs; p += chunk)
-            items.push_back(CladeItem{p, int32_t(c), int32_t(std::min(chunk, pairs - p))});
-        if (items.size() >= (size_t(1) << 31)) {
-            st_set_error("st_clade_moments: too many work items");
-            return ST_ERR_INVALID_ARG;
-        }
-        item_begin[size_t(c) + 1] = int32_t(items.size());
-    }
-    const int32_t n_items = int32_t(items.size());
-
+    const st_tree *ta = k->ta, *tb = k->tb;
     DeviceGuard g(ta->device);
+    int rc = ensure_scan_index(k, side);
+    if (rc != ST_OK) return rc;
     LaneGuard lg(ta->device);
     HostLane *lane = lg.lane;
     if (!lane) return ST_ERR_CUDA;
     cudaStream_t s = lane->streams[0];
-    // one stream-ordered scratch block: rows | run_begin | items | item_begin | shift | partials | out5 | counter
+    const int64_t n_side = side == 0 ? tb->n_nodes : ta->n_nodes;
+    const int32_t nc = int32_t(n_clades);
+
+    // one stream-ordered scratch block for the plan
     auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
-    const size_t o_rows = 0, o_run = o_rows + al(size_t(L) * 8), o_items = o_run + al(size_t(n_elig) * 8),
-                 o_ibeg = o_items + al(size_t(n_items) * 16), o_shift = o_ibeg + al((size_t(n_elig) + 1) * 4),
-                 o_part = o_shift + al(size_t(n_elig) * 16), o_out = o_part + al(size_t(n_items) * 40),
-                 o_cnt = o_out + al(size_t(n_elig) * 40), bytes = o_cnt + 256;
+    const size_t scan_ints = size_t(nc) / 1000 + 64;
+    const size_t o_lo = 0, o_hi = o_lo + al(size_t(nc) * 8), o_pairs = o_hi + al(size_t(nc) * 8),
+                 o_run = o_pairs + al(size_t(nc) * 8), o_len = o_run + al(size_t(nc) * 4),
+                 o_cnt = o_len + al(size_t(nc) * 4), o_ibeg = o_cnt + al(size_t(nc) * 4),
+                 o_scan = o_ibeg + al(size_t(nc) * 4), o_shift = o_scan + al(scan_ints * 4),
+                 o_out = o_shift + al(size_t(nc) * 16), o_nl = o_out + al(size_t(nc) * 64),
+                 o_meta = o_nl + al(size_t(nc) * 8), o_next = o_meta + 256, bytes = o_next + 256;
     unsigned char *d = nullptr;
     if (cudaMallocAsync(reinterpret_cast<void **>(&d), bytes, s) != cudaSuccess) {
         cudaGetLastError();
         st_set_error("st_clade_moments: device allocation of %zu bytes failed", bytes);
         return ST_ERR_NOMEM;
     }
-    int2 *d_rows = reinterpret_cast<int2 *>(d + o_rows);
-    int64_t *d_run = reinterpret_cast<int64_t *>(d + o_run);
-    CladeItem *d_items = reinterpret_cast<CladeItem *>(d + o_items);
-    int32_t *d_ibeg = reinterpret_cast<int32_t *>(d + o_ibeg);
+    int64_t *d_lo = reinterpret_cast<int64_t *>(d + o_lo), *d_hi = reinterpret_cast<int64_t *>(d + o_hi);
+    int64_t *d_pairs = reinterpret_cast<int64_t *>(d + o_pairs);
+    int32_t *d_run = reinterpret_cast<int32_t *>(d + o_run), *d_len = reinterpret_cast<int32_t *>(d + o_len);
+    int32_t *d_cnt = reinterpret_cast<int32_t *>(d + o_cnt), *d_ibeg = reinterpret_cast<int32_t *>(d + o_ibeg);
+    int32_t *d_scan = reinterpret_cast<int32_t *>(d + o_scan);
     double2 *d_shift = reinterpret_cast<double2 *>(d + o_shift);
-    double *d_part = reinterpret_cast<double *>(d + o_part);
     double *d_out = reinterpret_cast<double *>(d + o_out);
-    int32_t *d_cnt = reinterpret_cast<int32_t *>(d + o_cnt);
-    std::vector<double> h_out(size_t(n_elig) * 5);
-    std::vector<double2> h_shift(static_cast<size_t>(n_elig));
+    int64_t *d_nl = reinterpret_cast<int64_t *>(d + o_nl);
+    CladeMeta *d_meta = reinterpret_cast<CladeMeta *>(d + o_meta);
+    int32_t *d_next = reinterpret_cast<int32_t *>(d + o_next);
+    unsigned char *d2 = nullptr;  // items + partials, sized after the plan
     cudaError_t e = cudaSuccess;
     auto step = [&](cudaError_t r) {
         if (e == cudaSuccess) e = r;
     };
-    step(cudaMemcpyAsync(d_rows, rows.data(), size_t(L) * 8, cudaMemcpyHostToDevice, s));
-    step(cudaMemcpyAsync(d_run, run_begin.data(), size_t(n_elig) * 8, cudaMemcpyHostToDevice, s));
-    step(cudaMemcpyAsync(d_items, items.data(), size_t(n_items) * 16, cudaMemcpyHostToDevice, s));
-    step(cudaMemcpyAsync(d_ibeg, item_begin.data(), (size_t(n_elig) + 1) * 4, cudaMemcpyHostToDevice, s));
-    step(cudaMemsetAsync(d_cnt, 0, 4, s));
-    const int smem = ((ta->query_smem_bytes + 15) & ~15) + tb->query_smem_bytes;
-    const int grid = int(std::min<int64_t>((int64_t(n_items) + MLT / 32 - 1) / (MLT / 32), int64_t(ta->sm_count)));
-    if (e == cudaSuccess) {
-        k_clade_shift<<<int((n_elig + 255) / 256), 256, 0, s>>>(ta->view, tb->view, d_rows, d_run,
-                                                                 int32_t(n_elig), d_shift);
+    auto fail = [&](int code) {
+        if (d2) cudaFreeAsync(d2, s);
+        cudaFreeAsync(d, s);
+        cudaStreamSynchronize(s);
+        return code;
+    };
+    step(cudaMemcpyAsync(d_lo, clade_lo, size_t(nc) * 8, cudaMemcpyHostToDevice, s));
+    step(cudaMemcpyAsync(d_hi, clade_hi, size_t(nc) * 8, cudaMemcpyHostToDevice, s));
+    step(cudaMemsetAsync(d_meta, 0, sizeof(CladeMeta), s));
+    step(cudaMemsetAsync(d_next, 0, 4, s));
+    const int T = 256, gb = (nc + T - 1) / T;
+    k_clade_runs<<<gb, T, 0, s>>>(k->first[side], n_side, d_lo, d_hi, nc, min_links, max_links, d_run, d_len,
+                                  d_pairs, d_meta);
+    k_clade_chunk<<<1, 1, 0, s>>>(d_meta);
+    k_clade_count<<<gb, T, 0, s>>>(d_pairs, nc, d_meta, d_cnt);
+    exclusive_scan_i32(d_cnt, nc, d_ibeg, d_scan, s);
+    k_clade_total<<<1, 1, 0, s>>>(d_ibeg, d_cnt, nc, d_meta);
+    CladeMeta *h_meta = reinterpret_cast<CladeMeta *>(lane->h_scratch);  // pinned, 64 doubles
+    step(cudaMemcpyAsync(h_meta, d_meta, sizeof(CladeMeta), cudaMemcpyDeviceToHost, s));
+    step(cudaStreamSynchronize(s));
+    step(cudaGetLastError());
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        st_set_error("st_clade_moments: %s", cudaGetErrorString(e));
+        return fail(ST_ERR_CUDA);
+    }
+    if (h_meta->overflow || double(h_meta->total_pairs) >= 9.0e18) {
+        st_set_error("st_clade_moments: too much work for one call (%.3g link pairs)", double(h_meta->total_pairs));
+        return fail(ST_ERR_INVALID_ARG);
+    }
+    const int32_t n_items = h_meta->n_items;
+    CladeItem *d_items = nullptr;
+    double *d_part = nullptr;
+    if (n_items > 0) {
+        const size_t b_items = al(size_t(n_items) * 16);
+        if (cudaMallocAsync(reinterpret_cast<void **>(&d2), b_items + size_t(n_items) * 40, s) != cudaSuccess) {
+            cudaGetLastError();
+            st_set_error("st_clade_moments: device allocation for %d work items failed", n_items);
+            return fail(ST_ERR_NOMEM);
+        }
+        d_items = reinterpret_cast<CladeItem *>(d2);
+        d_part = reinterpret_cast<double *>(d2 + b_items);
+        const int2 *rows = k->rows_sorted[side];
+        k_clade_items<<<int((int64_t(nc) * 32 + T - 1) / T), T, 0, s>>>(d_pairs, d_ibeg, d_cnt, nc, d_meta, d_items);
+        k_clade_shift<<<gb, T, 0, s>>>(ta->view, tb->view, rows, d_run, d_cnt, nc, d_shift);
+        const int smem = ((ta->query_smem_bytes + 15) & ~15) + tb->query_smem_bytes;
+        const int grid = int(std::min<int64_t>((int64_t(n_items) + MLT / 32 - 1) / (MLT / 32), int64_t(ta->sm_count)));
         int rc2 = ST_OK;
 #define ST_LAUNCH_CLADE(MA, MB)                                                                          \
-    rc2 = st_raise_smem(k_clade_moments<MA, MB>, ta->device, smem);                                                     \
+    rc2 = st_raise_smem(k_clade_moments<MA, MB>, ta->device, smem);                                      \
     if (rc2 == ST_OK)                                                                                    \
-        k_clade_moments<MA, MB><<<grid, MLT, smem, s>>>(ta->view, tb->view, d_rows, d_run, d_shift,      \
-                                                        d_items, n_items, d_cnt, d_part)
+        k_clade_moments<MA, MB><<<grid, MLT, smem, s>>>(ta->view, tb->view, rows, d_run, d_shift, d_items, \
+                                                        n_items, d_next, d_part)
         ST_DISPATCH_MODES(tree_mode(ta), tree_mode(tb), ST_LAUNCH_CLADE);
 #undef ST_LAUNCH_CLADE
-        if (rc2 != ST_OK) {
-            cudaFreeAsync(d, s);
-            cudaStreamSynchronize(s);
-            return rc2;
-        }
-        k_clade_fold<<<int((n_elig * 32 + 255) / 256), 256, 0, s>>>(d_part, d_ibeg, int32_t(n_elig), d_out);
-        step(cudaGetLastError());
-        step(cudaMemcpyAsync(h_out.data(), d_out, h_out.size() * 8, cudaMemcpyDeviceToHost, s));
-        step(cudaMemcpyAsync(h_shift.data(), d_shift, h_shift.size() * 16, cudaMemcpyDeviceToHost, s));
+        if (rc2 != ST_OK) return fail(rc2);
     }
+    k_clade_fold<<<int((int64_t(nc) * 32 + T - 1) / T), T, 0, s>>>(d_part, d_ibeg, d_cnt, d_pairs, d_shift, d_len, nc,
+                                                                 d_out, n_links_out ? d_nl : nullptr);
+    step(cudaGetLastError());
+    // rows are laid out as st_moments: straight into the caller's arrays
+    static_assert(sizeof(st_moments) == 64, "st_moments is 8 doubles");
+    step(cudaMemcpyAsync(out, d_out, size_t(nc) * 64, cudaMemcpyDeviceToHost, s));
+    if (n_links_out) step(cudaMemcpyAsync(n_links_out, d_nl, size_t(nc) * 8, cudaMemcpyDeviceToHost, s));
+    if (d2) cudaFreeAsync(d2, s);
     cudaFreeAsync(d, s);
-    step(cudaStreamSynchronize(s));  // also keeps the host vectors alive until the copies have left them
+    step(cudaStreamSynchronize(s));
     if (e != cudaSuccess) {
         cudaGetLastError();
         st_set_error("st_clade_moments: %s", cudaGetErrorString(e));
         return ST_ERR_CUDA;
     }
-    for (int64_t c = 0; c < n_elig; ++c) {
-        st_moments &m = out[slot_clade[size_t(c)]];
-        const int64_t n = run_len[size_t(c)];
-        m.n = double(n) * double(n - 1) * 0.5;
-        m.x0 = h_shift[size_t(c)].x;
-        m.y0 = h_shift[size_t(c)].y;
-        m.sx = h_out[size_t(c) * 5 + 0];
-        m.sy = h_out[size_t(c) * 5 + 1];
-        m.sxx = h_out[size_t(c) * 5 + 2];
-        m.syy = h_out[size_t(c) * 5 + 3];
-        m.sxy = h_out[size_t(c) * 5 + 4];
-    }
     return ST_OK;
+}
+
+extern "C" int st_clade_moments(const st_tree *ta, const st_tree *tb, const int64_t *linklist, int64_t L,
+                                int side, const int64_t *clade_lo, const int64_t *clade_hi,
+                                int64_t n_clades, int64_t min_links, int64_t max_links, st_moments *out,
+                                int64_t *n_links_out) {
+    TempLinks tl;
+    int rc = st_links_create(ta, tb, linklist, L, &tl.k);
+    if (rc != ST_OK) return rc;
+    return st_links_clade_moments(tl.k, side, clade_lo, clade_hi, n_clades, min_links, max_links, out, n_links_out);
 }
 
 extern "C" double st_moments_pearson(const st_moments *m) {

@@ -273,6 +273,7 @@ class SuchLinkedTrees:
 
     def __del__(self):
         self._drop_links()
+        self._drop_scan_handle()
 
     # ---- linked_distances (:2900-2934) ---------------------------------------
     def linked_distances(self):
@@ -425,14 +426,13 @@ class SuchLinkedTrees:
         lo_all, hi_all = T._clade_intervals()
         lo = np.ascontiguousarray(lo_all[nodes], dtype=np.int64)
         hi = np.ascontiguousarray(hi_all[nodes], dtype=np.int64)
-        ll = self._links_for_scan(side)
+        links = self._scan_handle(side)
         n = int(nodes.shape[0])
         moments = np.zeros((n, 8), dtype=np.float64)  # rows laid out as st_moments
         n_links = np.zeros(n, dtype=np.int64)
         if n:
-            rc = _lib.lib().st_clade_moments(
-                self._TreeA._handle, self._TreeB._handle, ll.ctypes.data, int(ll.shape[0]),
-                0 if side == "b" else 1, lo.ctypes.data, hi.ctypes.data, n, int(min_links),
+            rc = _lib.lib().st_links_clade_moments(
+                links, 0 if side == "b" else 1, lo.ctypes.data, hi.ctypes.data, n, int(min_links),
                 -1 if max_links is None else int(max_links), moments.ctypes.data, n_links.ctypes.data)
             _lib.check(rc)
         return nodes, (hi - lo) // 2 + 1, n_links, moments
@@ -456,6 +456,29 @@ class SuchLinkedTrees:
             ll[:, 1] = self._link_a[keep]
             self._scan_links = (key, ll)
         return self._scan_links[1]
+
+    def _scan_handle(self, side):
+        """st_links handle of _links_for_scan(side): the sorted links and prefix counts the scan
+        needs stay on the device until a subset changes."""
+        ll = self._links_for_scan(side)
+        key = self._scan_links[0]
+        cur = getattr(self, "_scan_links_handle", None)
+        if cur is None or cur[0] != key:
+            self._drop_scan_handle()
+            h = C.c_void_p()
+            _lib.check(_lib.lib().st_links_create(self._TreeA._handle, self._TreeB._handle, ll.ctypes.data,
+                                                  int(ll.shape[0]), C.byref(h)))
+            self._scan_links_handle = (key, h)
+        return self._scan_links_handle[1]
+
+    def _drop_scan_handle(self):
+        cur = getattr(self, "_scan_links_handle", None)
+        if cur is not None and cur[1].value:
+            try:
+                _lib.lib().st_links_destroy(cur[1])
+            except Exception:
+                pass
+        self._scan_links_handle = None
 
     def clade_pearson(self, nodes=None, side="b", min_links=2, max_links=None, rank=None, world=None):
         """Pearson r of (TreeA distance, TreeB distance) over all link pairs of every

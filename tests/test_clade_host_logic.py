@@ -36,8 +36,27 @@ class _StandIn:
     def __getattr__(self, name):
         return getattr(self.real, name)
 
+    # the link-list handle (st_links_create / st_links_destroy): the stand-in keeps the list itself
+    def st_links_create(self, ha, hb, ll_p, n_links, h_ref):
+        ll = np.ctypeslib.as_array(C.cast(ll_p, C.POINTER(C.c_int64)), (n_links, 2)).copy() if n_links else np.empty((0, 2), np.int64)
+        self.handles = getattr(self, "handles", {})
+        hid = 1000 + len(self.handles)
+        self.handles[hid] = ll
+        h_ref._obj.value = hid
+        return 0
+
+    def st_links_destroy(self, h):
+        self.handles.pop(h.value, None)
+
+    def st_links_clade_moments(self, h, side, lo_p, hi_p, n, min_links, max_links, out_p, nl_p):
+        ll = self.handles[h.value]
+        return self._clade_moments(ll, side, lo_p, hi_p, n, min_links, max_links, out_p, nl_p)
+
     def st_clade_moments(self, ha, hb, ll_p, n_links, side, lo_p, hi_p, n, min_links, max_links, out_p, nl_p):
         ll = np.ctypeslib.as_array(C.cast(ll_p, C.POINTER(C.c_int64)), (n_links, 2)) if n_links else np.empty((0, 2), np.int64)
+        return self._clade_moments(ll, side, lo_p, hi_p, n, min_links, max_links, out_p, nl_p)
+
+    def _clade_moments(self, ll, side, lo_p, hi_p, n, min_links, max_links, out_p, nl_p):
         lo = np.ctypeslib.as_array(C.cast(lo_p, C.POINTER(C.c_int64)), (n,))
         hi = np.ctypeslib.as_array(C.cast(hi_p, C.POINTER(C.c_int64)), (n,))
         out = C.cast(out_p, C.POINTER(_lib.Moments))
