@@ -210,9 +210,11 @@ def run_reference_arm(args):
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "tree_leaves": TREE_LEAVES, "pairs_per_step": per_step,
-                   "note": "the full step of our arm at N=1 (the CPU arm does not grow with --gpus); pool "
-                           "start-up outside the rate; results written to shared memory by the workers"},
+        "config": {"workload": WORKLOAD, "tree_leaves": TREE_LEAVES, "tree_nodes": int(ft.size),
+                   "pairs_per_step_per_gpu": per_step, "pair_dtype": "int64x2", "result_dtype": "f64",
+                   "note": "the same step as our arm: all 1e8 pairs of rank 0's Philox stream, every step (the "
+                           "CPU arm does not grow with --gpus); pool start-up outside the rate; results written "
+                           "to shared memory by the workers"},
         "cpu_baseline": {
             "value": value, "unit": UNIT, "cores": cores, "kind": ref.kind, "cpu_model": cpu_model(),
             "sample": "%d pairs/step x %d steps of the cfg2 pair stream (the whole step), fork Pool(%d) over "

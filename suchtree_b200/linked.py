@@ -424,12 +424,15 @@ class SuchLinkedTrees:
         if nodes.size and (nodes.min() < 0 or nodes.max() >= T.size):
             raise Exception("Node ID out of bounds.", int(nodes.max() if nodes.max() >= T.size else nodes.min()))
         lo_all, hi_all = T._clade_intervals()
-        lo = np.ascontiguousarray(lo_all[nodes], dtype=np.int64)
-        hi = np.ascontiguousarray(hi_all[nodes], dtype=np.int64)
-        links = self._scan_handle(side)
         n = int(nodes.shape[0])
-        moments = np.zeros((n, 8), dtype=np.float64)  # rows laid out as st_moments
-        n_links = np.zeros(n, dtype=np.int64)
+        big = n * 64 >= _lib.PINNED_RESULT_MIN_BYTES  # page-locked arrays: the copies are plain DMA
+        new = _lib.pinned_empty if big else np.empty
+        lo, hi = new((n,), np.int64), new((n,), np.int64)
+        np.take(lo_all, nodes, out=lo)
+        np.take(hi_all, nodes, out=hi)
+        links = self._scan_handle(side)
+        moments = new((n, 8), np.float64)  # rows laid out as st_moments; every row is written
+        n_links = new((n,), np.int64)
         if n:
             rc = _lib.lib().st_links_clade_moments(
                 links, 0 if side == "b" else 1, lo.ctypes.data, hi.ctypes.data, n, int(min_links),
