@@ -51,6 +51,38 @@ def test_our_arm_line_has_the_contract_keys(name, n):
     assert per_gpu > 5e10
 
 
+@pytest.mark.parametrize("name,n", [("r02_bench_n1.json", 1), ("r02_bench_n2.json", 2), ("r02_bench_n8.json", 8)])
+def test_round2_line_reports_the_reference_signature_and_its_roofline(name, n):
+    """Round 2: e2e is the reference's own call (pageable numpy in, fresh array out, no out=
+    kwarg, no pinned buffers handed in), measured over `steps` calls, with a copy roofline
+    measured in the same run; at N > 1 the cfg4 collective is inside the timed call and the
+    all-reduced r is checked."""
+    d = _load(name)
+    e = d["e2e"]
+    assert "out=" not in e["call"] and "pinned" not in e["call"] and "fresh" in e["call"]
+    assert e["steps"] == d["steps"] and e["matches_device_path"] is True
+    r = e["roofline"]
+    assert r["unit"] == "GB/s" and r["frac"] == pytest.approx(e["value"] / r["peak_pairs_per_s"])
+    assert r["frac"] >= 0.85 and ("%d rank" % n) in r["what"]
+    assert e["value"] >= 3e9
+    c4 = d["other_workloads"]["cfg4_pearson_sampler"]
+    if n > 1:
+        assert "ncclAllReduce" in c4["workload"] and c4["allreduce_check"]["ok_1e-12"] is True
+        assert c4["samples_in_r"] == n * 125_000_000
+    else:
+        assert d["other_workloads"]["cfg5_matrix"]["parity_vs_oracle"]["bit_exact"] is True
+        assert d["other_workloads"]["cfg5_matrix"]["parity_vs_oracle"]["sampled_elements"] >= 1_000_000
+
+
+def test_round2_reference_arm_runs_the_full_step():
+    d = _load("r02_bench_reference_arm.json")
+    ours = _load("r02_bench_n1.json")
+    assert d["impl"] == "reference" and d["config"]["workload"] == ours["config"]["workload"]
+    per_step = d["config"].get("pairs_per_step_per_gpu", d["config"].get("pairs_per_step"))
+    assert per_step == ours["config"]["pairs_per_step_per_gpu"] == 100_000_000
+    assert d["cpu_baseline"]["kind"] == "reference"
+
+
 def test_reference_arm_line():
     d = _load("r01_bench_reference_arm.json")
     assert d["impl"] == "reference" and d["metric"] == "patristic_distance_pairs_per_sec"
