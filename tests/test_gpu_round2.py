@@ -510,3 +510,37 @@ def test_depth_only_quartet_kernel_variants(qpt):
         with pytest.raises(InvalidNodeError):
             T.check_range()
         assert ob.cpu().numpy().tolist() == [[-1, -1, -1, -1]]
+
+
+def test_more_callers_than_lanes_wait_their_turn(tree):
+    """Twelve threads, four lanes per device: the extra callers block until a lane is free;
+    every call returns its own correct result (distances, MRCA ids, quartets mixed)."""
+    T, ot, ft = tree
+    out, errs = {}, []
+
+    def run(k):
+        try:
+            rng = np.random.default_rng(100 + k)
+            for rep in range(4):
+                n = int(rng.integers(1, 400_000))
+                p = rng.integers(0, ft.size, size=(n, 2)).astype(np.int64)
+                if k % 3 == 0:
+                    got, want = T.distances_bulk(p), ot.distances_f64_climb(p)
+                elif k % 3 == 1:
+                    got, want = T.common_ancestors_bulk(p), ot.distances_f64_climb(p, with_mrca=True)[1]
+                else:
+                    q = rng.integers(0, ft.size, size=(n // 4 + 1, 4)).astype(np.int64)
+                    got, want = T.quartet_topologies_bulk(q), ot.quartet_topologies(q)
+                if not np.array_equal(got, want):
+                    errs.append((k, rep, "mismatch"))
+            out[k] = True
+        except Exception as e:  # noqa: BLE001
+            errs.append((k, repr(e)))
+
+    th = [threading.Thread(target=run, args=(k,)) for k in range(12)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=300)
+    assert not errs, errs
+    assert len(out) == 12
