@@ -32,9 +32,8 @@ q32 = q64.to(torch.int32)
 o32 = torch.empty_like(q32)
 want = ot.quartet_topologies(q64[:300000].cpu().numpy())
 res = {}
-for name, env in (('default_qpt1_minb4', {}), ('minb5', {'SUCHTREE_B200_QMINB': '5'}), ('prefetch', {'SUCHTREE_B200_QPF': '1'}),
-                  ('qpt2', {'SUCHTREE_B200_QPT': '2'})):
-    for k in ('SUCHTREE_B200_QMINB', 'SUCHTREE_B200_QPF', 'SUCHTREE_B200_QPT'):
+for name, env in (('default_qpt1_256x4', {}), ('qpt1_384x3', {'SUCHTREE_B200_QT': '384'}), ('qpt2', {'SUCHTREE_B200_QPT': '2'})):
+    for k in ('SUCHTREE_B200_QT', 'SUCHTREE_B200_QPT'):
         os.environ.pop(k, None)
     os.environ.update(env)
     s64 = timed(lambda: T.quartet_topologies_device(q64.data_ptr(), nq, o64.data_ptr(), stream=sptr))

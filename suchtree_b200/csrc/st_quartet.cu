@@ -15,7 +15,6 @@
 #include "st_hostctx.cuh"
 #include "st_hostpool.cuh"
 
-static const int QQT = 256;
 #ifndef ST_QPT_DEFAULT
 #define ST_QPT_DEFAULT 1
 #endif
@@ -129,7 +128,7 @@ __device__ __forceinline__ int quartet_pair_index(int u, int v) {
 // PF: the ids of the thread's NEXT iteration are fetched before the current one is worked on.
 // IdxT: type of the ids read, OutT: type of the ids written (the host path ships int32 ids
 // over PCIe and gets the drop-in's int64 rows back).
-template <int M, typename IdxT, int P, int MINB, bool SMALL, bool PF = false, typename OutT = IdxT>
+template <int M, typename IdxT, int P, int MINB, bool SMALL, bool PF = false, typename OutT = IdxT, int QQT = 256>
 __global__ void __launch_bounds__(QQT, MINB)
 k_quartets(const TreeView tv, const IdxT *__restrict__ quartets, int64_t n, OutT *__restrict__ out,
            int aligned) {
@@ -276,10 +275,10 @@ static int st_quartets_per_thread() {  // SUCHTREE_B200_QPT = 1 | 2 (read per la
     return (x == 1 || x == 2) ? x : ST_QPT_DEFAULT;
 }
 
-template <int M, typename IdxT, int P, int MINB, bool SMALL, bool PF = false, typename OutT = IdxT>
+template <int M, typename IdxT, int P, int MINB, bool SMALL, bool PF = false, typename OutT = IdxT, int QQT = 256>
 static int launch_quartets_p(const st_tree *t, const IdxT *d_q, int64_t n, OutT *d_out,
                              cudaStream_t stream, RangeStatus *status) {
-    auto kern = k_quartets<M, IdxT, P, MINB, SMALL, PF, OutT>;
+    auto kern = k_quartets<M, IdxT, P, MINB, SMALL, PF, OutT, QQT>;
     const int smem = t->query_smem_bytes;
     int rc = st_raise_smem(kern, t->device, smem);
     if (rc != ST_OK) return rc;
@@ -302,6 +301,8 @@ static int launch_quartets_m(const st_tree *t, const IdxT *d_q, int64_t n, IdxT 
                              cudaStream_t stream, RangeStatus *status) {
     if (t->n_nodes > (int64_t(1) << 29)) return launch_quartets_p<M, IdxT, 1, 4, false>(t, d_q, n, d_out, stream, status);
     if (st_quartets_per_thread() == 2) return launch_quartets_p<M, IdxT, 2, 3, true>(t, d_q, n, d_out, stream, status);
+    if (const char *e = getenv("SUCHTREE_B200_QT"))  // experiment: 3 CTAs of 384 threads (56 registers)
+        if (atoi(e) == 384) return launch_quartets_p<M, IdxT, 1, 3, true, false, IdxT, 384>(t, d_q, n, d_out, stream, status);
     // (measured and not kept, profiles/r02_summary.md: 5 resident CTAs per SM -- 48 registers, spills,
     //  0.59x; prefetching the next iteration's ids, PF = true, 0.94x; two quartets per thread 0.91x)
     return launch_quartets_p<M, IdxT, 1, 4, true>(t, d_q, n, d_out, stream, status);
