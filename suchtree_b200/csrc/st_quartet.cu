@@ -301,8 +301,9 @@ static int launch_quartets_m(const st_tree *t, const IdxT *d_q, int64_t n, IdxT 
                              cudaStream_t stream, RangeStatus *status) {
     if (t->n_nodes > (int64_t(1) << 29)) return launch_quartets_p<M, IdxT, 1, 4, false>(t, d_q, n, d_out, stream, status);
     if (st_quartets_per_thread() == 2) return launch_quartets_p<M, IdxT, 2, 3, true>(t, d_q, n, d_out, stream, status);
-    if (const char *e = getenv("SUCHTREE_B200_QT"))  // experiment: 3 CTAs of 384 threads (56 registers)
-        if (atoi(e) == 384) return launch_quartets_p<M, IdxT, 1, 3, true, false, IdxT, 384>(t, d_q, n, d_out, stream, status);
+    // int64 ids (the drop-in layout): 3 CTAs of 384 threads at 56 registers, 1152 threads per SM,
+    // measured 4.26e10 vs 4.15e10 quartets/s for 4 x 256 at 64; int32 ids: 4 x 256 is the faster (4.61e10 vs 4.52e10)
+    if (sizeof(IdxT) == 8) return launch_quartets_p<M, IdxT, 1, 3, true, false, IdxT, 384>(t, d_q, n, d_out, stream, status);
     // (measured and not kept, profiles/r02_summary.md: 5 resident CTAs per SM -- 48 registers, spills,
     //  0.59x; prefetching the next iteration's ids, PF = true, 0.94x; two quartets per thread 0.91x)
     return launch_quartets_p<M, IdxT, 1, 4, true>(t, d_q, n, d_out, stream, status);
