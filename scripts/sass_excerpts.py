@@ -14,8 +14,8 @@ import sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(REPO, "suchtree_b200", "libsuchtree_b200.so")
 WANT = [r"k_pairsIiLi2ELi1ELi512ELi2ELi0E", r"k_pairsIiLi2ELi1ELi512ELi2ELi1E", r"k_pairsIlLi2ELi1ELi512ELi2ELi0E",
-        r"k_pairsIiLi2ELi0ELi512ELi2ELi0E", r"k_matrix_ordered", r"k_matrix_diag", r"k_quartetsILi1ElLi1ELi4ELb1E",
-        r"k_quartetsILi1EiLi1ELi4ELb1E", r"k_sample_momentsILi1ELi1E", r"k_linked_momentsILi1ELi1E",
+        r"k_pairsIiLi2ELi0ELi512ELi2ELi0E", r"k_matrix_ordered", r"k_matrix_diag", r"k_quartetsILi1ElLi1ELi3ELb1ELb0ElLi384E",
+        r"k_quartetsILi1EiLi1ELi4ELb1ELb0EiLi256E", r"k_sample_momentsILi1ELi1E", r"k_linked_momentsILi1ELi1E",
         r"k_clade_momentsILi1ELi1E", r"k_sample_xs", r"k_bucket_sums"]
 PAT = re.compile(r"\b(UBLKCP|UTMALDG|SYNCS|LDG\.E[\w.]*|STG\.E[\w.]*|LDS[\w.]*|ATOMG[\w.]*|RED[\w.]*|LDGSTS[\w.]*)")
 
