@@ -949,8 +949,7 @@ def run_other_workloads(args, rank, world, local, dev, peak):
             r = st_pearson(np.asarray(D1), np.asarray(D2), device=local)
             res["published_benchmark_by_name"] = {
                 "workload": "docs/benchmarks.md: 1e6 random leaf-name pairs, distances_by_name() on ml.tree and "
-                            "nj.tree (54,327 leaves, 108,653 nodes each; wide layout: zero-length edges carry "
-                            "the reference's 2.2e-16 epsilon), names -> ids included",
+                            "nj.tree (54,327 leaves, 108,653 nodes each), names -> ids included",
                 "s_both_calls": dt, "pairs_per_s": 2 * npairs / dt, "load_two_trees_s": load_s,
                 "published_s": 10.1, "published_pairs_per_s": 1.98e5, "published_hardware": "Intel i7-3770S, 1 thread",
                 "pearson_r": r, "published_pearson_r": 0.969,

@@ -46,6 +46,8 @@ def test_fresh_result_comes_from_the_pinned_pool_and_is_recycled(tree):
     T, ot, ft = tree
     n = 3_000_000
     p = _pairs(ft, n, 1)
+    gc.collect()
+    _lib.lib().st_host_trim(0)  # blocks cached by earlier tests would be handed out first
     r = T.distances_bulk(p)
     assert type(r) is np.ndarray and r.dtype == np.float64 and r.shape == (n,) and r.flags.c_contiguous
     assert r.flags.writeable and _pinned(r)
@@ -487,9 +489,10 @@ def test_depth_only_quartet_kernel_variants(qpt):
     ft = synth.yule_tree(5000, seed=9)
     ot = O.OracleTree(ft.parent, ft.distance)
     rng = np.random.default_rng(10)
-    for bs in (0, 2):
-        T = SuchTree.from_flat(ft, _block_shift=bs)
-        for n in (1, 2, 3, 255, 256, 257, 100_003):
+    for bs in (0, 2, "wide"):
+        T = SuchTree.from_flat(ft, _wide=True) if bs == "wide" else SuchTree.from_flat(ft, _block_shift=bs)
+        assert T.index_info["layout"] == (0 if bs == "wide" else 1)
+        for n in (1, 2, 3, 255, 256, 257, 383, 384, 385, 100_003):
             q = np.concatenate([2 * rng.integers(0, ft.n_leaves, size=(n, 4)),
                                 rng.integers(0, ft.size, size=(n, 4))]).astype(np.int64)
             q[::5, 1] = q[::5, 0]
