@@ -19,6 +19,9 @@
 #include <cstring>
 #include <vector>
 #include "st_device.cuh"
+#ifndef ST_LEAN_DEFAULT
+#define ST_LEAN_DEFAULT 1
+#endif
 #include "st_hostctx.cuh"
 #include "st_hostpool.cuh"
 
@@ -102,6 +105,59 @@ __device__ __forceinline__ void st_pair(const TreeView &tv, const SmemTables &sm
     if (want_m) m = st_mrca_id<M>(tv, sm, k, ft);
 }
 
+// Lean form for the compact layout (PR = 2): per endpoint only what the pair needs -- its root
+// distance and ONE 32-bit key (suffix key of lo, prefix key of hi) -- 3 registers per record
+// instead of 8, 32-bit depth compares instead of widened 64-bit keys.  Same results bit for bit.
+struct RecC {
+    double rd;
+    uint32_t key;
+};
+__device__ __forceinline__ RecC st_ld_rec_c(const TreeView &tv, int32_t id, bool hi_side) {
+    uint64_t a, b;
+    asm volatile("ld.global.nc.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(tv.rec16 + id));
+    return RecC{__longlong_as_double((long long)a), hi_side ? uint32_t(b >> 32) : uint32_t(b)};
+}
+__device__ __forceinline__ void st_pair_c(const TreeView &tv, const SmemTables &sm, const PairQ &q,
+                                          const RecC &l, const RecC &h, bool want_d, bool want_m, double &d,
+                                          int32_t &m) {
+    const int bs = tv.block_shift;
+    double rm;
+    int32_t id;
+    if (q.lo == q.hi) {  // MRCA(a,a) = a
+        rm = l.rd;
+        id = q.lo;
+    } else {
+        const int32_t blo = q.lo >> bs, bhi = q.hi >> bs;
+        bool ft = false;
+        uint32_t mid = 0;
+        if (blo == bhi) {
+            id = st_key_id(st_rmq_inblock(tv.depth, tv.mst, tv.n_micro, tv.micro_shift, q.lo, q.hi));
+        } else {
+            const uint32_t ds = l.key >> bs, dp = h.key >> bs;
+            const int32_t span = bhi - blo - 1;
+            if (span > 0) {
+                const int k = 31 - __clz(span);
+                const uint32_t *lvl = sm.stk32 + k * tv.n_blocks;
+                mid = min(lvl[blo + 1], lvl[bhi - (1 << k)]);
+                // candidates are distinct nodes and the minimum depth is unique: no ties
+                ft = (mid >> tv.table_shift) < min(ds, dp);
+            }
+            const uint32_t mask = (1u << bs) - 1u;
+            id = ds < dp ? int32_t((uint32_t(q.lo) & ~mask) + (l.key & mask))
+                         : int32_t((uint32_t(q.hi) & ~mask) + (h.key & mask));
+        }
+        if (ft) {  // a block minimum: root distance (and id) from the shared-memory tables
+            const uint32_t blk = mid & ((1u << tv.table_shift) - 1u);
+            rm = sm.brd8[blk];
+            id = want_m ? sm.bid[blk] : 0;
+        } else {
+            rm = id == q.lo ? l.rd : (id == q.hi ? h.rd : __ldg(&tv.rec16[id].rd));
+        }
+    }
+    if (want_d) d = st_patristic(dd{l.rd, 0.0}, dd{h.rd, 0.0}, dd{rm, 0.0});
+    if (want_m) m = id;
+}
+
 // the same with paired records (compact layout): rd[mrca] from the block table, an endpoint,
 // an endpoint's sector neighbour -- or, failing all that, one more gather
 __device__ __forceinline__ void st_pair_paired(const TreeView &tv, const SmemTables &sm, const PairQ &q,
@@ -152,14 +208,45 @@ k_pairs(const TreeView tv, const IdxT *__restrict__ pairs, int64_t n, double *__
     for (; i < groups; i += stride) {
         const RawPairs<IdxT, P> cur = st_load_pairs<IdxT, P>(pairs, P * i);
         PairQ q[P];
-        RecRaw l[P], h[P];
-        double nbl[P], nbh[P];  // PR: root distances of the endpoints' sector neighbours
 #pragma unroll
         for (int k = 0; k < P; ++k) {
             long long a, b;
             st_decode_pair<IdxT, P>(cur, k, a, b);
             q[k] = st_make_query(tv, a, b);
         }
+        if (PR == 2) {  // lean compact path
+            RecC lc[P], hc[P];
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                lc[k] = st_ld_rec_c(tv, q[k].lo, false);
+                hc[k] = st_ld_rec_c(tv, q[k].hi, true);
+            }
+            double dc[P];
+            int32_t mc[P];
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                dc[k] = 0.0;
+                mc[k] = 0;
+                st_pair_c(tv, sm, q[k], lc[k], hc[k], want_d, want_m, dc[k], mc[k]);
+                if (q[k].bad) {
+                    dc[k] = nan;
+                    mc[k] = -1;
+                }
+            }
+            if (want_d) {
+                if (P == 4) st_st_stream_f64x4(out + P * i, dc[0], dc[1], dc[2], dc[3]);
+                else if (P == 2) st_st_stream_f64x2(out + P * i, dc[0], dc[1]);
+                else st_st_stream_f64(out + i, dc[0]);
+            }
+            if (want_m) {
+                if (P == 4) st_st_stream_i32x4(mrca_out + P * i, mc[0], mc[1], mc[2], mc[3]);
+                else if (P == 2) st_st_stream_i32x2(mrca_out + P * i, mc[0], mc[1]);
+                else st_st_stream_i32(mrca_out + i, mc[0]);
+            }
+            continue;
+        }
+        RecRaw l[P], h[P];
+        double nbl[P], nbh[P];  // PR: root distances of the endpoints' sector neighbours
 #pragma unroll
         for (int k = 0; k < P; ++k) {
             if (PR) {
@@ -212,7 +299,7 @@ k_pairs(const TreeView tv, const IdxT *__restrict__ pairs, int64_t n, double *__
 }
 
 // ------------------------------------------------------------------ launch --
-template <typename IdxT, int P, int M, int PR = 0>
+template <typename IdxT, int P, int M, int PR = 0, int QT_ = 0, int MINB_ = 0>
 static int launch_variant_m(const st_tree *t, const void *d_pairs, int64_t n, double *d_out,
                             int32_t *d_mrca, cudaStream_t stream, RangeStatus *status) {
     // 2 pairs/thread: 2 x 512 threads x 64 registers; 4 pairs/thread needs ~80 registers:
@@ -221,7 +308,7 @@ static int launch_variant_m(const st_tree *t, const void *d_pairs, int64_t n, do
 #define ST_QT_P2 512
 #define ST_MINB_P2 2
 #endif
-    constexpr int QT = P == 4 ? 256 : ST_QT_P2, MINB = P == 4 ? 3 : ST_MINB_P2;
+    constexpr int QT = QT_ ? QT_ : (P == 4 ? 256 : ST_QT_P2), MINB = MINB_ ? MINB_ : (P == 4 ? 3 : ST_MINB_P2);
     auto kern = k_pairs<IdxT, P, M, QT, MINB, PR>;
     // per device, per thread: the attribute and the occupancy query are made once per
     // shared-memory size (they cost microseconds that single-pair calls would notice)
@@ -262,18 +349,30 @@ static int launch_variant(const st_tree *t, const void *d_pairs, int64_t n, doub
                           int32_t *d_mrca, cudaStream_t stream, RangeStatus *status) {
     if (t->compact && P == 2 && st_paired_records(t))
         return launch_variant_m<IdxT, 2, 1, 1>(t, d_pairs, n, d_out, d_mrca, stream, status);
-    if (t->compact) return launch_variant_m<IdxT, P, 1>(t, d_pairs, n, d_out, d_mrca, stream, status);
+    if (t->compact) {
+        // lean compact path (3 registers per record); SUCHTREE_B200_LEAN = 0 keeps the generic one,
+        // 42 / 43 = four pairs per thread as 512 x 2 / 256 x 3 (experiments)
+        const char *e = getenv("SUCHTREE_B200_LEAN");
+        const int lean = e && e[0] ? atoi(e) : ST_LEAN_DEFAULT;
+        if (lean == 0) return launch_variant_m<IdxT, P, 1>(t, d_pairs, n, d_out, d_mrca, stream, status);
+        if constexpr (P == 4) {
+            if (lean == 42) return launch_variant_m<IdxT, 4, 1, 2, 512, 2>(t, d_pairs, n, d_out, d_mrca, stream, status);
+            return launch_variant_m<IdxT, 4, 1, 2, 256, 3>(t, d_pairs, n, d_out, d_mrca, stream, status);
+        } else if constexpr (P == 2) {
+            if (lean == 23) return launch_variant_m<IdxT, 2, 1, 2, 512, 3>(t, d_pairs, n, d_out, d_mrca, stream, status);
+            if (lean == 25) return launch_variant_m<IdxT, 2, 1, 2, 256, 5>(t, d_pairs, n, d_out, d_mrca, stream, status);
+            if (lean == 33) return launch_variant_m<IdxT, 2, 1, 2, 384, 3>(t, d_pairs, n, d_out, d_mrca, stream, status);
+        }
+        return launch_variant_m<IdxT, P, 1, 2>(t, d_pairs, n, d_out, d_mrca, stream, status);
+    }
     if (t->compact_tables) return launch_variant_m<IdxT, P, 3>(t, d_pairs, n, d_out, d_mrca, stream, status);
     return launch_variant_m<IdxT, P, 0>(t, d_pairs, n, d_out, d_mrca, stream, status);
 }
 
-static int st_pairs_per_thread() {  // SUCHTREE_B200_PPT = 1 | 2 | 4 (experiments)
-    static const int v = [] {
-        const char *e = getenv("SUCHTREE_B200_PPT");
-        const int x = e ? atoi(e) : 2;
-        return (x == 1 || x == 2 || x == 4) ? x : 2;
-    }();
-    return v;
+static int st_pairs_per_thread() {  // SUCHTREE_B200_PPT = 1 | 2 | 4 (read per launch: experiments)
+    const char *e = getenv("SUCHTREE_B200_PPT");
+    const int x = e && e[0] ? atoi(e) : 2;
+    return (x == 1 || x == 2 || x == 4) ? x : 2;
 }
 
 int st_launch_pairs(const st_tree *t, const void *d_pairs, int idx_bits, int64_t n, double *d_out,
