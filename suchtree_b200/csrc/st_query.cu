@@ -350,19 +350,14 @@ static int launch_variant(const st_tree *t, const void *d_pairs, int64_t n, doub
     if (t->compact && P == 2 && st_paired_records(t))
         return launch_variant_m<IdxT, 2, 1, 1>(t, d_pairs, n, d_out, d_mrca, stream, status);
     if (t->compact) {
-        // lean compact path (3 registers per record); SUCHTREE_B200_LEAN = 0 keeps the generic one,
-        // 42 / 43 = four pairs per thread as 512 x 2 / 256 x 3 (experiments)
+        // lean compact path (3 registers per record, 32-bit keys): +1 % over the generic one on
+        // every tree shape, bit-identical; SUCHTREE_B200_LEAN = 0 keeps the generic path (tests).
+        // Measured and not kept (profiles/r02_lean_variants.json): 384 x 3 (equal), 256 x 5 and
+        // 512 x 3 (spills: 0.55x / 0.77x), four pairs per thread at 256 x 3 (0.94x) or 512 x 2 (0.79x).
         const char *e = getenv("SUCHTREE_B200_LEAN");
         const int lean = e && e[0] ? atoi(e) : ST_LEAN_DEFAULT;
         if (lean == 0) return launch_variant_m<IdxT, P, 1>(t, d_pairs, n, d_out, d_mrca, stream, status);
-        if constexpr (P == 4) {
-            if (lean == 42) return launch_variant_m<IdxT, 4, 1, 2, 512, 2>(t, d_pairs, n, d_out, d_mrca, stream, status);
-            return launch_variant_m<IdxT, 4, 1, 2, 256, 3>(t, d_pairs, n, d_out, d_mrca, stream, status);
-        } else if constexpr (P == 2) {
-            if (lean == 23) return launch_variant_m<IdxT, 2, 1, 2, 512, 3>(t, d_pairs, n, d_out, d_mrca, stream, status);
-            if (lean == 25) return launch_variant_m<IdxT, 2, 1, 2, 256, 5>(t, d_pairs, n, d_out, d_mrca, stream, status);
-            if (lean == 33) return launch_variant_m<IdxT, 2, 1, 2, 384, 3>(t, d_pairs, n, d_out, d_mrca, stream, status);
-        }
+        if constexpr (P == 4) return launch_variant_m<IdxT, 4, 1, 2, 256, 3>(t, d_pairs, n, d_out, d_mrca, stream, status);
         return launch_variant_m<IdxT, P, 1, 2>(t, d_pairs, n, d_out, d_mrca, stream, status);
     }
     if (t->compact_tables) return launch_variant_m<IdxT, P, 3>(t, d_pairs, n, d_out, d_mrca, stream, status);

@@ -472,11 +472,13 @@ def test_paired_record_kernel_matches_plain_kernel_and_oracle(shape, block_shift
     p = np.concatenate([2 * rng.integers(0, ft.n_leaves, size=(300_001, 2)), rng.integers(0, ft.size, size=(300_000, 2)),
                         np.repeat(rng.integers(0, ft.size, size=(1000, 1)), 2, axis=1)]).astype(np.int64)
     want, wm = ot.distances_f64_climb(p, with_mrca=True)
-    for paired in ("0", "1"):
-        d = _with_env("SUCHTREE_B200_PAIRED", paired, lambda: T.distances_bulk(p))
-        m = _with_env("SUCHTREE_B200_PAIRED", paired, lambda: T.common_ancestors_bulk(p))
-        assert np.array_equal(d, want), paired
-        assert np.array_equal(m, wm), paired
+    # the three compact pair kernels: paired records, lean (32-bit keys), generic
+    for paired, lean in (("1", "1"), ("0", "1"), ("0", "0")):
+        def both():
+            return _with_env("SUCHTREE_B200_LEAN", lean, lambda: (T.distances_bulk(p), T.common_ancestors_bulk(p)))
+        d, m = _with_env("SUCHTREE_B200_PAIRED", paired, both)
+        assert np.array_equal(d, want), (paired, lean)
+        assert np.array_equal(m, wm), (paired, lean)
 
 
 @pytest.mark.parametrize("qpt", ["1", "2"])
