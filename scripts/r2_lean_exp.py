@@ -35,11 +35,10 @@ for name, ft in (('yule100k', synth.yule_tree(100000, seed=1)), ('balanced1M', s
     os.environ['SUCHTREE_B200_PAIRED'] = '0'
     entry = {}
     for label, env in (('generic_p2_512x2', {'SUCHTREE_B200_LEAN': '0'}), ('lean_p2_512x2', {'SUCHTREE_B200_LEAN': '1'}),
-                       ('lean_p2_384x3', {'SUCHTREE_B200_LEAN': '33'}), ('lean_p2_256x5', {'SUCHTREE_B200_LEAN': '25'}),
-                       ('lean_p2_512x3', {'SUCHTREE_B200_LEAN': '23'}),
-                       ('lean_p4_256x3', {'SUCHTREE_B200_LEAN': '1', 'SUCHTREE_B200_PPT': '4'}),
-                       ('lean_p4_512x2', {'SUCHTREE_B200_LEAN': '42', 'SUCHTREE_B200_PPT': '4'}),
-                       ('generic_p4_256x3', {'SUCHTREE_B200_LEAN': '0', 'SUCHTREE_B200_PPT': '4'})):
+                       ('paired_generic', {'SUCHTREE_B200_LEAN': '0', 'SUCHTREE_B200_PAIRED': '1'}),
+                       ('paired_lean', {'SUCHTREE_B200_LEAN': '1', 'SUCHTREE_B200_PAIRED': '1'}),
+                       ('lean_p4_256x3', {'SUCHTREE_B200_LEAN': '1', 'SUCHTREE_B200_PPT': '4'})):
+        os.environ['SUCHTREE_B200_PAIRED'] = '0'
         for k in ('SUCHTREE_B200_LEAN', 'SUCHTREE_B200_PPT'):
             os.environ.pop(k, None)
         os.environ.update(env)

@@ -111,12 +111,28 @@ __device__ __forceinline__ void st_pair(const TreeView &tv, const SmemTables &sm
 struct RecC {
     double rd;
     uint32_t key;
+    double nb_rd;  // NB only: root distance of the node in the other half of the 32-byte sector
 };
+// NB = true: ONE 256-bit load of the whole sector (the record and its slot neighbour's, see
+// st_ld_rec_paired); NB = false: the 16-byte record alone
+template <bool NB>
 __device__ __forceinline__ RecC st_ld_rec_c(const TreeView &tv, int32_t id, bool hi_side) {
+    if (NB) {
+        const char *p = reinterpret_cast<const char *>(tv.rec16 + id);
+        const bool upper = (reinterpret_cast<uintptr_t>(p) & 16) != 0;
+        uint64_t w0, w1, w2, w3;
+        asm volatile("ld.global.nc.L2::evict_last.v4.b64 {%0,%1,%2,%3}, [%4];"
+                     : "=l"(w0), "=l"(w1), "=l"(w2), "=l"(w3)
+                     : "l"(p - (upper ? 16 : 0)));
+        const uint64_t keys = upper ? w3 : w1;
+        return RecC{__longlong_as_double((long long)(upper ? w2 : w0)), hi_side ? uint32_t(keys >> 32) : uint32_t(keys),
+                    __longlong_as_double((long long)(upper ? w0 : w2))};
+    }
     uint64_t a, b;
     asm volatile("ld.global.nc.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(tv.rec16 + id));
-    return RecC{__longlong_as_double((long long)a), hi_side ? uint32_t(b >> 32) : uint32_t(b)};
+    return RecC{__longlong_as_double((long long)a), hi_side ? uint32_t(b >> 32) : uint32_t(b), 0.0};
 }
+template <bool NB>
 __device__ __forceinline__ void st_pair_c(const TreeView &tv, const SmemTables &sm, const PairQ &q,
                                           const RecC &l, const RecC &h, bool want_d, bool want_m, double &d,
                                           int32_t &m) {
@@ -150,6 +166,15 @@ __device__ __forceinline__ void st_pair_c(const TreeView &tv, const SmemTables &
             const uint32_t blk = mid & ((1u << tv.table_shift) - 1u);
             rm = sm.brd8[blk];
             id = want_m ? sm.bid[blk] : 0;
+        } else if (NB) {
+            // slot parity of an id: which half of its sector, hence which neighbour came along
+            const int32_t lo_nb = q.lo + ((reinterpret_cast<uintptr_t>(tv.rec16 + q.lo) & 16) ? -1 : 1);
+            const int32_t hi_nb = q.hi + ((reinterpret_cast<uintptr_t>(tv.rec16 + q.hi) & 16) ? -1 : 1);
+            if (id == hi_nb) rm = h.nb_rd;
+            else if (id == lo_nb) rm = l.nb_rd;
+            else if (id == q.lo) rm = l.rd;
+            else if (id == q.hi) rm = h.rd;
+            else rm = __ldg(&tv.rec16[id].rd);
         } else {
             rm = id == q.lo ? l.rd : (id == q.hi ? h.rd : __ldg(&tv.rec16[id].rd));
         }
@@ -214,12 +239,13 @@ k_pairs(const TreeView tv, const IdxT *__restrict__ pairs, int64_t n, double *__
             st_decode_pair<IdxT, P>(cur, k, a, b);
             q[k] = st_make_query(tv, a, b);
         }
-        if (PR == 2) {  // lean compact path
+        if (PR >= 2) {  // lean compact path (PR = 3: with the sector neighbours)
+            constexpr bool NB = PR == 3;
             RecC lc[P], hc[P];
 #pragma unroll
             for (int k = 0; k < P; ++k) {
-                lc[k] = st_ld_rec_c(tv, q[k].lo, false);
-                hc[k] = st_ld_rec_c(tv, q[k].hi, true);
+                lc[k] = st_ld_rec_c<NB>(tv, q[k].lo, false);
+                hc[k] = st_ld_rec_c<NB>(tv, q[k].hi, true);
             }
             double dc[P];
             int32_t mc[P];
@@ -227,7 +253,7 @@ k_pairs(const TreeView tv, const IdxT *__restrict__ pairs, int64_t n, double *__
             for (int k = 0; k < P; ++k) {
                 dc[k] = 0.0;
                 mc[k] = 0;
-                st_pair_c(tv, sm, q[k], lc[k], hc[k], want_d, want_m, dc[k], mc[k]);
+                st_pair_c<NB>(tv, sm, q[k], lc[k], hc[k], want_d, want_m, dc[k], mc[k]);
                 if (q[k].bad) {
                     dc[k] = nan;
                     mc[k] = -1;
@@ -347,8 +373,11 @@ static int st_paired_records(const st_tree *t) {
 template <typename IdxT, int P>
 static int launch_variant(const st_tree *t, const void *d_pairs, int64_t n, double *d_out,
                           int32_t *d_mrca, cudaStream_t stream, RangeStatus *status) {
-    if (t->compact && P == 2 && st_paired_records(t))
-        return launch_variant_m<IdxT, 2, 1, 1>(t, d_pairs, n, d_out, d_mrca, stream, status);
+    if (t->compact && P == 2 && st_paired_records(t)) {
+        const char *e = getenv("SUCHTREE_B200_LEAN");
+        if (e && e[0] == '0') return launch_variant_m<IdxT, 2, 1, 1>(t, d_pairs, n, d_out, d_mrca, stream, status);
+        return launch_variant_m<IdxT, 2, 1, 3>(t, d_pairs, n, d_out, d_mrca, stream, status);
+    }
     if (t->compact) {
         // lean compact path (3 registers per record, 32-bit keys): +1 % over the generic one on
         // every tree shape, bit-identical; SUCHTREE_B200_LEAN = 0 keeps the generic path (tests).
