@@ -25,6 +25,13 @@ __device__ __forceinline__ double linked_query(const TreeView &tv, const SmemTab
                                                int32_t b) {
     int32_t lo = min(a, b), hi = max(a, b);
     if (lo == hi) return 0.0;
+    if (M == 1) {  // compact layout: the lean form (3 registers per record, 32-bit keys), same bits
+        const RecC lc = st_ld_rec_c<false>(tv, lo, false), hc = st_ld_rec_c<false>(tv, hi, true);
+        double d = 0.0;
+        int32_t m = 0;
+        st_pair_c<false>(tv, sm, PairQ{lo, hi, false}, lc, hc, true, false, d, m);
+        return d;
+    }
     RecRaw l = st_ld_rec<M>(tv, lo), h = st_ld_rec<M>(tv, hi);
     bool ft;
     uint64_t key = st_rmq<M>(tv, sm, lo, hi, l.suf, h.pre, &ft);

@@ -69,11 +69,6 @@ __device__ __forceinline__ void st_decode_pair(const RawPairs<IdxT, P> &r, int k
     }
 }
 
-struct PairQ {
-    int32_t lo, hi;
-    bool bad;
-};
-
 // range check as SuchTree.distances_bulk does before the kernel (MuchTree.pyx:897-903),
 // moved onto the device so the host never makes a pass over the pair array.
 __device__ __forceinline__ PairQ st_make_query(const TreeView &tv, long long a, long long b) {
@@ -103,84 +98,6 @@ __device__ __forceinline__ void st_pair(const TreeView &tv, const SmemTables &sm
                                     : st_rmq<M>(tv, sm, q.lo, q.hi, l.suf, h.pre, &ft);
     if (want_d) d = st_patristic(dd{l.rd_hi, l.rd_lo}, dd{h.rd_hi, h.rd_lo}, st_mrca_rd<M>(tv, sm, k, ft));
     if (want_m) m = st_mrca_id<M>(tv, sm, k, ft);
-}
-
-// Lean form for the compact layout (PR = 2): per endpoint only what the pair needs -- its root
-// distance and ONE 32-bit key (suffix key of lo, prefix key of hi) -- 3 registers per record
-// instead of 8, 32-bit depth compares instead of widened 64-bit keys.  Same results bit for bit.
-struct RecC {
-    double rd;
-    uint32_t key;
-    double nb_rd;  // NB only: root distance of the node in the other half of the 32-byte sector
-};
-// NB = true: ONE 256-bit load of the whole sector (the record and its slot neighbour's, see
-// st_ld_rec_paired); NB = false: the 16-byte record alone
-template <bool NB>
-__device__ __forceinline__ RecC st_ld_rec_c(const TreeView &tv, int32_t id, bool hi_side) {
-    if (NB) {
-        const char *p = reinterpret_cast<const char *>(tv.rec16 + id);
-        const bool upper = (reinterpret_cast<uintptr_t>(p) & 16) != 0;
-        uint64_t w0, w1, w2, w3;
-        asm volatile("ld.global.nc.L2::evict_last.v4.b64 {%0,%1,%2,%3}, [%4];"
-                     : "=l"(w0), "=l"(w1), "=l"(w2), "=l"(w3)
-                     : "l"(p - (upper ? 16 : 0)));
-        const uint64_t keys = upper ? w3 : w1;
-        return RecC{__longlong_as_double((long long)(upper ? w2 : w0)), hi_side ? uint32_t(keys >> 32) : uint32_t(keys),
-                    __longlong_as_double((long long)(upper ? w0 : w2))};
-    }
-    uint64_t a, b;
-    asm volatile("ld.global.nc.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(tv.rec16 + id));
-    return RecC{__longlong_as_double((long long)a), hi_side ? uint32_t(b >> 32) : uint32_t(b), 0.0};
-}
-template <bool NB>
-__device__ __forceinline__ void st_pair_c(const TreeView &tv, const SmemTables &sm, const PairQ &q,
-                                          const RecC &l, const RecC &h, bool want_d, bool want_m, double &d,
-                                          int32_t &m) {
-    const int bs = tv.block_shift;
-    double rm;
-    int32_t id;
-    if (q.lo == q.hi) {  // MRCA(a,a) = a
-        rm = l.rd;
-        id = q.lo;
-    } else {
-        const int32_t blo = q.lo >> bs, bhi = q.hi >> bs;
-        bool ft = false;
-        uint32_t mid = 0;
-        if (blo == bhi) {
-            id = st_key_id(st_rmq_inblock(tv.depth, tv.mst, tv.n_micro, tv.micro_shift, q.lo, q.hi));
-        } else {
-            const uint32_t ds = l.key >> bs, dp = h.key >> bs;
-            const int32_t span = bhi - blo - 1;
-            if (span > 0) {
-                const int k = 31 - __clz(span);
-                const uint32_t *lvl = sm.stk32 + k * tv.n_blocks;
-                mid = min(lvl[blo + 1], lvl[bhi - (1 << k)]);
-                // candidates are distinct nodes and the minimum depth is unique: no ties
-                ft = (mid >> tv.table_shift) < min(ds, dp);
-            }
-            const uint32_t mask = (1u << bs) - 1u;
-            id = ds < dp ? int32_t((uint32_t(q.lo) & ~mask) + (l.key & mask))
-                         : int32_t((uint32_t(q.hi) & ~mask) + (h.key & mask));
-        }
-        if (ft) {  // a block minimum: root distance (and id) from the shared-memory tables
-            const uint32_t blk = mid & ((1u << tv.table_shift) - 1u);
-            rm = sm.brd8[blk];
-            id = want_m ? sm.bid[blk] : 0;
-        } else if (NB) {
-            // slot parity of an id: which half of its sector, hence which neighbour came along
-            const int32_t lo_nb = q.lo + ((reinterpret_cast<uintptr_t>(tv.rec16 + q.lo) & 16) ? -1 : 1);
-            const int32_t hi_nb = q.hi + ((reinterpret_cast<uintptr_t>(tv.rec16 + q.hi) & 16) ? -1 : 1);
-            if (id == hi_nb) rm = h.nb_rd;
-            else if (id == lo_nb) rm = l.nb_rd;
-            else if (id == q.lo) rm = l.rd;
-            else if (id == q.hi) rm = h.rd;
-            else rm = __ldg(&tv.rec16[id].rd);
-        } else {
-            rm = id == q.lo ? l.rd : (id == q.hi ? h.rd : __ldg(&tv.rec16[id].rd));
-        }
-    }
-    if (want_d) d = st_patristic(dd{l.rd, 0.0}, dd{h.rd, 0.0}, dd{rm, 0.0});
-    if (want_m) m = id;
 }
 
 // the same with paired records (compact layout): rd[mrca] from the block table, an endpoint,
