@@ -233,6 +233,20 @@ class _PinnedBlock:
             self.ptr = None
 
 
+def result_empty(shape, dtype, zero_small=False):
+    """The fresh result array of a drop-in call: page-locked (pool) when it is large, an ordinary
+    np.empty / np.zeros otherwise.  SUCHTREE_B200_PINNED_RESULTS=0 keeps every result pageable
+    (slower D2H, but no page-locked memory is held by arrays the caller keeps around)."""
+    import numpy as np
+
+    if not isinstance(shape, tuple):
+        shape = (int(shape),)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+    if nbytes >= PINNED_RESULT_MIN_BYTES and os.environ.get("SUCHTREE_B200_PINNED_RESULTS", "1") != "0":
+        return pinned_empty(shape, dtype)
+    return np.zeros(shape, dtype=dtype) if zero_small else np.empty(shape, dtype=dtype)
+
+
 def pinned_empty(shape, dtype):
     """np.empty() in page-locked memory from the library's pool: an ordinary ndarray
     (its .base keeps the block alive) that D2H copies can land in directly."""
@@ -247,7 +261,9 @@ PINNED_RESULT_MIN_BYTES = 4 << 20    # smaller results: plain np.empty (the smal
 REGISTER_MIN_BYTES = 64 << 20        # inputs at least this large are candidates for registration
 
 _registered = {}   # id(owner) -> [ptr, nbytes, sightings, registered, finalizer]
-_reg_lock = threading.Lock()
+# re-entrant: a finaliser (_unregister) can fire from a garbage collection that an allocation
+# inside maybe_register() triggers while this thread already holds the lock
+_reg_lock = threading.RLock()
 
 
 def _register_policy():

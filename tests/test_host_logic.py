@@ -352,3 +352,43 @@ def test_three_loaders_agree_on_random_newick():
                 assert np.array_equal(getattr(ft, k), a[k]), (k, text)
             assert np.asarray(ft.distance, np.float32).tobytes() == np.asarray(a["distance"], np.float32).tobytes(), text
         assert np.array_equal(newick.flatten(text).support, newick.flatten_py(text).support, equal_nan=True), text
+
+
+def test_input_registration_bookkeeping_without_a_device(monkeypatch):
+    """maybe_register(): thresholds, the policy variable, owners it cannot track, and the
+    weakref finaliser that forgets an array when it dies (no device here: the registration
+    call itself fails and is not retried on every call)."""
+    import gc
+
+    monkeypatch.setattr(_lib, "REGISTER_MIN_BYTES", 1 << 16)
+    calls = []
+
+    class Fake:
+        def st_host_register(self, p, n):
+            calls.append(("reg", p, n))
+            return 0
+
+        def st_host_unregister(self, p):
+            calls.append(("unreg", p))
+            return 0
+
+    monkeypatch.setattr(_lib, "lib", lambda: Fake())
+    small = np.zeros((100, 2), np.int64)
+    assert _lib.maybe_register(small) is False and not calls
+    big = np.zeros((1 << 13, 2), np.int64)  # 128 KiB
+    monkeypatch.setenv("SUCHTREE_B200_REGISTER", "0")
+    assert _lib.maybe_register(big) is False and not calls
+    monkeypatch.setenv("SUCHTREE_B200_REGISTER", "2")
+    assert _lib.maybe_register(big) is False and not calls  # first sighting
+    assert _lib.maybe_register(big[: 1 << 12]) is True  # second sighting (through a view): the OWNER is registered
+    assert calls == [("reg", big.ctypes.data, big.nbytes)]
+    assert _lib.maybe_register(big) is True and len(calls) == 1
+    # memory owned by something that is not an ndarray is left alone
+    raw = bytearray(1 << 18)
+    foreign = np.frombuffer(raw, dtype=np.int64).reshape(-1, 2)
+    assert _lib.maybe_register(foreign) is False and _lib.maybe_register(foreign) is False and len(calls) == 1
+    key, ptr = id(big), big.ctypes.data
+    assert key in _lib._registered
+    del big
+    gc.collect()
+    assert key not in _lib._registered and calls[-1] == ("unreg", ptr)
