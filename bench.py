@@ -432,15 +432,11 @@ def run_ours(args):
     np_pairs = pairs[:n_e2e].cpu().numpy().astype(np.int64)  # pageable host memory, C-contiguous
     assert np_pairs.flags.owndata and not _lib.lib().st_host_is_pinned(np_pairs.ctypes.data)
     t0 = time.perf_counter()
-    r = T.distances_bulk(np_pairs)  # cold call: served from pageable memory while the pool block is page-locked
+    r = T.distances_bulk(np_pairs)  # cold call: result pool and (maybe) staging are allocated here
     e2e_first_s = time.perf_counter() - t0
     e2e_ok = bool(torch.equal(torch.from_numpy(r).to(dev), out[:n_e2e]))
-    # warm-up to the steady state of a loop over the same array: two pool blocks alternate as
-    # results, the input gets page-locked in place (both happen on helper threads)
-    for _ in range(max(args.warmup, 3) + 2):
+    for _ in range(max(args.warmup, 3) - 1):
         r = T.distances_bulk(np_pairs)
-        _lib.wait_for_pool()
-        _lib.wait_for_registrations()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -448,7 +444,6 @@ def run_ours(args):
     dt = time.perf_counter() - t0
     e2e_ok = e2e_ok and bool(torch.equal(torch.from_numpy(r).to(dev), out[:n_e2e]))
     in_registered = bool(_lib.lib().st_host_is_pinned(np_pairs.ctypes.data))
-    result_pinned = bool(_lib.lib().st_host_is_pinned(r.ctypes.data))
 
     def all_max(x):
         t_ = torch.tensor([x], dtype=torch.float64, device=dev)
@@ -464,9 +459,7 @@ def run_ours(args):
     reps = max(3, min(args.steps, 5))
     os.environ["SUCHTREE_B200_REGISTER"] = "0"
     np_pairs2 = np_pairs.copy()
-    for _ in range(3):
-        r = T.distances_bulk(np_pairs2)
-        _lib.wait_for_pool()
+    r = T.distances_bulk(np_pairs2)
     barrier()
     t0 = time.perf_counter()
     for _ in range(reps):
@@ -561,7 +554,6 @@ def run_ours(args):
                     "array every step), r = fresh numpy float64 (n,) -- the reference's signature, "
                     "MuchTree.pyx:872-909",
             "input_registered_in_place": in_registered,
-            "result_page_locked": result_pinned,
             "first_call_s": e2e_first_s,
             "roofline": e2e_roofline,
             "variants_pairs_per_s": variants,
@@ -695,9 +687,7 @@ def run_other_workloads(args, rank, world, local, dev, peak):
         d_o1 = torch.empty(p1.shape[0], dtype=torch.float64, device=dev)
         sec = _timed(stream, lambda: G.distances_device(d_p1.data_ptr(), p1.shape[0], d_o1.data_ptr(), idx_bits=64,
                                                         stream=sptr), steps=20)
-        for _ in range(4):  # warm: the result size gets its pool blocks (helper thread)
-            G.distances_bulk(p1)
-            _lib.wait_for_pool()
+        G.distances_bulk(p1)
         t0 = time.perf_counter()
         for _ in range(5):
             got = G.distances_bulk(p1)
@@ -793,10 +783,9 @@ def run_other_workloads(args, rank, world, local, dev, peak):
     if rank == 0:
         nodes = list(range(0, 40_000, 2))
         t0 = time.perf_counter()
-        D = T.pairwise_distances(nodes)  # cold: pageable result while the pool block is page-locked
+        D = T.pairwise_distances(nodes)  # cold: the pinned result block is allocated here
         cold = time.perf_counter() - t0
         del D
-        _lib.wait_for_pool()
         t0 = time.perf_counter()
         D = T.pairwise_distances(nodes)
         warm = time.perf_counter() - t0

@@ -276,11 +276,6 @@ ST_API int st_bench_copy(int device, int64_t h2d_bytes, int64_t d2h_bytes, int64
 ST_API int st_host_alloc(int64_t bytes, void **out);
 ST_API int st_host_free(void *p);
 ST_API int st_host_trim(int64_t keep_bytes); /* drop cached blocks down to keep_bytes */
-/* 1 when a cached block of this size class is ready; st_host_reserve allocates one into the cache
- * (the shim calls it on a helper thread the first time a result size is seen, and serves that
- * first call from pageable memory instead of making it wait for the page-locking) */
-ST_API int st_host_cached(int64_t bytes);
-ST_API int st_host_reserve(int device, int64_t bytes);
 /* page-lock / unlock a caller-owned array in place (cudaHostRegister): the host pipeline
  * then DMAs straight out of it.  The shim registers large inputs it sees repeatedly and
  * unregisters them when the array is garbage-collected. */

@@ -91,8 +91,6 @@ SIGNATURES = {
     "st_host_alloc": (_int, [_i64, C.POINTER(_vp)]),
     "st_host_free": (_int, [_vp]),
     "st_host_trim": (_int, [_i64]),
-    "st_host_cached": (_int, [_i64]),
-    "st_host_reserve": (_int, [_int, _i64]),
     "st_host_register": (_int, [_vp, _i64]),
     "st_host_unregister": (_int, [_vp]),
     "st_host_is_pinned": (_int, [_vp]),
@@ -235,43 +233,17 @@ class _PinnedBlock:
             self.ptr = None
 
 
-_reserving = {}  # size in bytes -> helper thread page-locking a pool block of that size class
-
-
-def _reserve_async(device, nbytes):
-    with _reg_lock:
-        th = _reserving.get(nbytes)
-        if th is not None and th.is_alive():
-            return
-        th = threading.Thread(target=lambda: lib().st_host_reserve(int(device), int(nbytes)),
-                              name="suchtree-b200-pool")  # not a daemon: joined at interpreter exit
-        _reserving[nbytes] = th
-        th.start()
-
-
-def wait_for_pool():
-    """Block until every pool block being prepared in the background is ready (tests, benchmarks)."""
-    for th in list(_reserving.values()):
-        th.join()
-
-
-def result_empty(shape, dtype, zero_small=False, device=0):
+def result_empty(shape, dtype, zero_small=False):
     """The fresh result array of a drop-in call: page-locked (pool) when it is large, an ordinary
-    np.empty / np.zeros otherwise.  Page-locking costs ~0.3 s per GB, so a size that is seen for
-    the first time is served from pageable memory at once (as the reference would) while a
-    helper thread prepares a pool block of that size class for the calls that follow.
-    SUCHTREE_B200_PINNED_RESULTS=0 keeps every result pageable (slower D2H, but no page-locked
-    memory is held by arrays the caller keeps around); =2 waits for the block instead."""
+    np.empty / np.zeros otherwise.  SUCHTREE_B200_PINNED_RESULTS=0 keeps every result pageable
+    (slower D2H, but no page-locked memory is held by arrays the caller keeps around)."""
     import numpy as np
 
     if not isinstance(shape, tuple):
         shape = (int(shape),)
     nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
-    mode = os.environ.get("SUCHTREE_B200_PINNED_RESULTS", "1")
-    if nbytes >= PINNED_RESULT_MIN_BYTES and mode != "0":
-        if mode == "2" or lib().st_host_cached(nbytes):
-            return pinned_empty(shape, dtype)
-        _reserve_async(device, nbytes)
+    if nbytes >= PINNED_RESULT_MIN_BYTES and os.environ.get("SUCHTREE_B200_PINNED_RESULTS", "1") != "0":
+        return pinned_empty(shape, dtype)
     return np.zeros(shape, dtype=dtype) if zero_small else np.empty(shape, dtype=dtype)
 
 
@@ -288,30 +260,10 @@ def pinned_empty(shape, dtype):
 PINNED_RESULT_MIN_BYTES = 4 << 20    # smaller results: plain np.empty (the small-call path copies anyway)
 REGISTER_MIN_BYTES = 64 << 20        # inputs at least this large are candidates for registration
 
-_registered = {}   # id(owner) -> _Reg
+_registered = {}   # id(owner) -> [ptr, nbytes, sightings, registered, finalizer]
 # re-entrant: a finaliser (_unregister) can fire from a garbage collection that an allocation
 # inside maybe_register() triggers while this thread already holds the lock
 _reg_lock = threading.RLock()
-
-
-class _Reg:
-    """One caller-owned array known to the registration table."""
-
-    __slots__ = ("ptr", "nbytes", "seen", "locked", "tried", "thread", "fin")
-
-    def __init__(self, ptr, nbytes, fin):
-        self.ptr, self.nbytes, self.fin = ptr, nbytes, fin
-        self.seen, self.locked, self.tried, self.thread = 0, False, False, None
-
-    def lock_pages(self):
-        self.tried = True  # a failure (locked-memory limit ...) is not retried on every call
-        if lib().st_host_register(self.ptr, self.nbytes) == ST_OK:
-            self.locked = True
-
-    def settle(self):
-        th = self.thread
-        if th is not None and th is not threading.current_thread():
-            th.join()
 
 
 def _register_policy():
@@ -327,23 +279,18 @@ def _register_policy():
 def _unregister(key, ptr):
     with _reg_lock:
         ent = _registered.pop(key, None)
-    if ent is not None:
-        ent.settle()  # a registration still in flight must land before it is undone
-        if ent.locked:
-            try:
-                lib().st_host_unregister(ptr)
-            except Exception:
-                pass
+    if ent is not None and ent[3]:
+        try:
+            lib().st_host_unregister(ptr)
+        except Exception:
+            pass
 
 
 def maybe_register(arr):
     """Called with a large C-contiguous input array: page-lock the buffer of the ndarray
-    that owns the memory once the policy says so -- on a helper thread (~0.25 s per GB): the
-    calls made meanwhile keep packing from pageable memory, and the library DMAs straight from
-    the array as soon as it finds it page-locked (SUCHTREE_B200_REGISTER_SYNC=1: in the calling
-    thread).  The registration lives exactly as long as the owner (weakref finaliser), so a
-    freed-and-reused address is never mistaken for a registered one.  Returns True when the
-    array is page-locked already."""
+    that owns the memory once the policy says so.  The registration lives exactly as long
+    as the owner (weakref finaliser), so a freed-and-reused address is never mistaken
+    for a registered one.  Returns True when the array is (now) page-locked."""
     import weakref
 
     import numpy as np
@@ -359,35 +306,24 @@ def maybe_register(arr):
     ptr, nbytes, key = owner.ctypes.data, owner.nbytes, id(owner)
     with _reg_lock:
         ent = _registered.get(key)
-        if ent is not None and (ent.ptr != ptr or ent.nbytes != nbytes):
-            # the owner was resized in place: forget the old range
-            _registered.pop(key)
-            ent.fin.detach()
-            ent.settle()
-            if ent.locked:
-                lib().st_host_unregister(ent.ptr)
-            ent = None
+        if ent is not None and (ent[0] != ptr or ent[1] != nbytes):
+            ent = None  # the owner was resized in place: forget the old range
+            stale = _registered.pop(key)
+            if stale[3]:
+                lib().st_host_unregister(stale[0])
+            stale[4].detach()
         if ent is None:
             try:
                 fin = weakref.finalize(owner, _unregister, key, ptr)
             except TypeError:
                 return False
-            ent = _registered[key] = _Reg(ptr, nbytes, fin)
-        ent.seen += 1
-        if ent.locked:
+            ent = _registered[key] = [ptr, nbytes, 0, False, fin]
+        ent[2] += 1
+        if ent[3]:
             return True
-        if ent.seen >= policy and not ent.tried and ent.thread is None:
-            if os.environ.get("SUCHTREE_B200_REGISTER_SYNC", "0") == "1":
-                ent.lock_pages()
-                return ent.locked
-            ent.thread = threading.Thread(target=ent.lock_pages, name="suchtree-b200-register")
-            ent.thread.start()
+        if ent[2] >= policy:
+            if lib().st_host_register(ptr, nbytes) == ST_OK:
+                ent[3] = True
+                return True
+            ent[2] = -(1 << 60)  # registration failed (locked-memory limit ...): do not retry every call
     return False
-
-
-def wait_for_registrations():
-    """Block until every page-locking in flight has landed (tests, benchmarks)."""
-    with _reg_lock:
-        ents = list(_registered.values())
-    for e in ents:
-        e.settle()

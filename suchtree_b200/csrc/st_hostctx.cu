@@ -145,9 +145,9 @@ void st_hostctx_prewarm(int device) {
     c.prewarm_thread = std::thread([device, &c] {
         HostLane *l = nullptr;
         if (cudaSetDevice(device) == cudaSuccess && lane_create(device, &l) == ST_OK) {
-            // full-size device staging, pinned input staging and pinned result staging (the
-            // first large calls return pageable results while their pool block is being locked)
-            if (st_lane_ensure_stage(l, ST_STAGE_PAIRS_MAX, true, true) != ST_OK) cudaGetLastError();
+            // full-size device staging and pinned input staging; pinned result staging is
+            // only needed by C callers that hand in pageable result buffers (lazy)
+            if (st_lane_ensure_stage(l, ST_STAGE_PAIRS_MAX, true, false) != ST_OK) cudaGetLastError();
         }
         {
             std::lock_guard<std::mutex> lk2(c.mu);
@@ -270,30 +270,6 @@ extern "C" int st_host_free(void *p) {
     }
     if (!keep && cudaFreeHost(p) != cudaSuccess) cudaGetLastError();  // (at interpreter exit the runtime may be gone)
     return ST_OK;
-}
-
-// 1 when a cached block of the size class of `bytes` is waiting in the pool
-extern "C" int st_host_cached(int64_t bytes) {
-    if (bytes < 0) return 0;
-    const size_t cls = size_class(size_t(std::max<int64_t>(bytes, 1)));
-    std::lock_guard<std::mutex> l(g_pool.mu);
-    return g_pool.free_blocks.find(cls) != g_pool.free_blocks.end() ? 1 : 0;
-}
-
-// Allocate a block of the size class of `bytes` and leave it in the cache: what the shim runs
-// on a helper thread the first time it sees a result size, so that the FIRST call is served at
-// once from pageable memory (as the reference would) instead of waiting ~0.3 s per GB for the
-// page-locking, and the next ones find the block ready.
-extern "C" int st_host_reserve(int device, int64_t bytes) {
-    DeviceGuard g(device);
-    if (!g.ok) {
-        st_set_error("st_host_reserve: cudaSetDevice(%d) failed", device);
-        return ST_ERR_CUDA;
-    }
-    void *p = nullptr;
-    int rc = st_host_alloc(bytes, &p);
-    if (rc != ST_OK) return rc;
-    return st_host_free(p);
 }
 
 extern "C" int st_host_trim(int64_t keep_bytes) {

@@ -484,7 +484,7 @@ class SuchTree:
         if out is None:
             # a fresh array, as the reference returns (MuchTree.pyx:907); large ones come from
             # the library's page-locked pool so that the D2H copies land in them directly
-            result = _lib.result_empty((n,), np.float64, device=self.device)
+            result = _lib.result_empty((n,), np.float64)
             if pairs.flags.c_contiguous:
                 _lib.maybe_register(pairs)  # large inputs seen repeatedly are page-locked in place
         else:  # extension: caller-provided (e.g. pinned) float64 result buffer
@@ -587,7 +587,7 @@ class SuchTree:
         if any(s % 8 for s in quartets.strides):
             quartets = np.ascontiguousarray(quartets)
         n = quartets.shape[0]
-        out = _lib.result_empty((n, 4), np.int64, zero_small=True, device=self.device)  # every row is written by the kernel
+        out = _lib.result_empty((n, 4), np.int64, zero_small=True)  # every row is written by the kernel
         s0, s1 = quartets.strides[0] // 8, quartets.strides[1] // 8
         rc = _lib.lib().st_quartet_topologies(self._handle, quartets.ctypes.data, s0, s1, n, out.ctypes.data)
         _lib.check(rc, self.size)
@@ -688,7 +688,7 @@ class SuchTree:
         else:
             ids_ptr = self._validate_nodes(nodes)
             n = ids_ptr.shape[0]
-        out = _lib.result_empty((n, n), np.float64, zero_small=True, device=self.device)  # every element is written by the kernels
+        out = _lib.result_empty((n, n), np.float64, zero_small=True)  # every element is written by the kernels
         if n:
             rc = _lib.lib().st_distance_matrix(
                 self._handle, None if ids_ptr is None else ids_ptr.ctypes.data, n, 0, n,

@@ -47,13 +47,8 @@ def test_fresh_result_comes_from_the_pinned_pool_and_is_recycled(tree):
     n = 3_000_000
     p = _pairs(ft, n, 1)
     gc.collect()
-    _lib.wait_for_pool()
     _lib.lib().st_host_trim(0)  # blocks cached by earlier tests would be handed out first
-    first = T.distances_bulk(p)  # a size seen for the first time: served at once from pageable memory ...
-    assert type(first) is np.ndarray and first.flags.owndata and not _pinned(first)
-    _lib.wait_for_pool()         # ... while a helper thread page-locks a pool block for the next calls
     r = T.distances_bulk(p)
-    assert np.array_equal(r, first)
     assert type(r) is np.ndarray and r.dtype == np.float64 and r.shape == (n,) and r.flags.c_contiguous
     assert r.flags.writeable and _pinned(r)
     sel = np.random.default_rng(2).integers(0, n, 100000)
@@ -63,12 +58,8 @@ def test_fresh_result_comes_from_the_pinned_pool_and_is_recycled(tree):
     view = r[10:20]  # a view keeps the block alive
     del r
     gc.collect()
-    os.environ["SUCHTREE_B200_PINNED_RESULTS"] = "2"  # wait for a block instead of falling back to pageable
-    try:
-        r2 = T.distances_bulk(p)
-    finally:
-        del os.environ["SUCHTREE_B200_PINNED_RESULTS"]
-    assert _pinned(r2) and r2.ctypes.data != ptr and np.array_equal(view, keep[10:20])
+    r2 = T.distances_bulk(p)
+    assert r2.ctypes.data != ptr and np.array_equal(view, keep[10:20])
     del view
     gc.collect()
     r3 = T.distances_bulk(p)  # the first block is back in the pool: same size class -> recycled
@@ -81,7 +72,6 @@ def test_fresh_result_comes_from_the_pinned_pool_and_is_recycled(tree):
 
 def test_pool_trim_and_foreign_pointer():
     L = _lib.lib()
-    _lib.wait_for_pool()
     a = _lib.pinned_empty((1 << 20,), np.float64)
     assert _pinned(a)
     a[:] = 1.5
@@ -100,9 +90,8 @@ def test_large_repeated_input_is_registered_in_place_then_released(tree):
     assert not _pinned(p)
     r1 = T.distances_bulk(p)
     assert not _pinned(p)  # default policy: a one-off call does not pay for pinning
-    r2 = T.distances_bulk(p)  # second sighting: a helper thread page-locks the array in place ...
-    _lib.wait_for_registrations()
-    assert _pinned(p)  # ... and from then on it is DMA'd directly
+    r2 = T.distances_bulk(p)
+    assert _pinned(p)  # second sighting: page-locked in place, DMA'd directly from now on
     r3 = T.distances_bulk(p)
     r4 = T.distances_bulk(p[: n // 2])  # a view of a registered array
     sel = np.random.default_rng(4).integers(0, n, 100000)
@@ -129,12 +118,11 @@ def test_register_policy_env(tree):
     finally:
         del os.environ["SUCHTREE_B200_REGISTER"]
     os.environ["SUCHTREE_B200_REGISTER"] = "1"
-    os.environ["SUCHTREE_B200_REGISTER_SYNC"] = "1"
     try:
         c = T.distances_bulk(p)
         assert _pinned(p)
     finally:
-        del os.environ["SUCHTREE_B200_REGISTER"], os.environ["SUCHTREE_B200_REGISTER_SYNC"]
+        del os.environ["SUCHTREE_B200_REGISTER"]
     assert np.array_equal(a, b) and np.array_equal(a, c)
 
 
@@ -229,10 +217,8 @@ def test_matrix_writer_covers_every_element(tree):
 def test_pairwise_distances_large_host_result_is_pinned_and_exact(tree):
     T, ot, ft = tree
     nodes = list(range(0, 6000, 2))  # 3000 x 3000 x 8 B = 72 MB: several bands
-    D0 = T.pairwise_distances(nodes)  # first sighting of the size: pageable result, driver-staged D2H
-    _lib.wait_for_pool()
     D = T.pairwise_distances(nodes)
-    assert D.shape == (3000, 3000) and _pinned(D) and np.array_equal(D, D0)
+    assert D.shape == (3000, 3000) and _pinned(D)
     assert np.array_equal(D, D.T) and np.all(np.diagonal(D) == 0.0)
     a, b = np.meshgrid(nodes[:50], nodes, indexing="ij")
     want = ot.distances_f64_climb(np.stack([a.ravel(), b.ravel()], axis=1).astype(np.int64)).reshape(50, 3000)

@@ -380,9 +380,8 @@ def test_input_registration_bookkeeping_without_a_device(monkeypatch):
     assert _lib.maybe_register(big) is False and not calls
     monkeypatch.setenv("SUCHTREE_B200_REGISTER", "2")
     assert _lib.maybe_register(big) is False and not calls  # first sighting
-    assert _lib.maybe_register(big[: 1 << 12]) is False  # second sighting (through a view): a helper thread ...
-    _lib.wait_for_registrations()
-    assert calls == [("reg", big.ctypes.data, big.nbytes)]  # ... registers the OWNER
+    assert _lib.maybe_register(big[: 1 << 12]) is True  # second sighting (through a view): the OWNER is registered
+    assert calls == [("reg", big.ctypes.data, big.nbytes)]
     assert _lib.maybe_register(big) is True and len(calls) == 1
     # memory owned by something that is not an ndarray is left alone
     raw = bytearray(1 << 18)
