@@ -51,7 +51,8 @@ def test_our_arm_line_has_the_contract_keys(name, n):
     assert per_gpu > 5e10
 
 
-@pytest.mark.parametrize("name,n", [("r02_bench_n1.json", 1), ("r02_bench_n2.json", 2), ("r02_bench_n8.json", 8)])
+@pytest.mark.parametrize("name,n", [("r02_bench_n1.json", 1), ("r02_bench_n2.json", 2), ("r02_bench_n4.json", 4),
+                                    ("r02_bench_n8.json", 8)])
 def test_round2_line_reports_the_reference_signature_and_its_roofline(name, n):
     """Round 2: e2e is the reference's own call (pageable numpy in, fresh array out, no out=
     kwarg, no pinned buffers handed in), measured over `steps` calls, with a copy roofline
