@@ -147,34 +147,6 @@ __device__ __forceinline__ RecRaw st_ld_rec(const TreeView &tv, int32_t id) {
     r.rd_hi = __longlong_as_double((long long)a);
     return r;
 }
-// Compact layout, paired form: ONE 256-bit load of the 32-byte sector that holds the node's
-// record AND its slot neighbour's (slot = id + shift, see st_tree_create): the neighbour of
-// most leaves is their parent, so when the MRCA turns out to be that node its root distance
-// is already here -- no third, dependent gather (ladder-like trees, sister queries).
-struct RecPaired {
-    RecRaw r;
-    double nb_rd;   // root distance of the node in the other half of the sector
-    int32_t nb_id;  // its id: id + 1 (lower half) or id - 1 (upper half); may be -1 / n_nodes (padding)
-};
-__device__ __forceinline__ RecPaired st_ld_rec_paired(const TreeView &tv, int32_t id) {
-    RecPaired o;
-    const char *p = reinterpret_cast<const char *>(tv.rec16 + id);
-    const bool upper = (reinterpret_cast<uintptr_t>(p) & 16) != 0;
-    uint64_t w0, w1, w2, w3;
-    asm volatile("ld.global.nc.L2::evict_last.v4.b64 {%0,%1,%2,%3}, [%4];"
-                 : "=l"(w0), "=l"(w1), "=l"(w2), "=l"(w3)
-                 : "l"(p - (upper ? 16 : 0)));
-    const uint64_t keys = upper ? w3 : w1;
-    const uint32_t mask = (1u << tv.block_shift) - 1u, base = uint32_t(id) & ~mask;
-    const uint32_t sf = uint32_t(keys), pr = uint32_t(keys >> 32);
-    o.r.rd_hi = __longlong_as_double((long long)(upper ? w2 : w0));
-    o.r.rd_lo = 0.0;
-    o.r.suf = (uint64_t(sf >> tv.block_shift) << 32) | (base + (sf & mask));
-    o.r.pre = (uint64_t(pr >> tv.block_shift) << 32) | (base + (pr & mask));
-    o.nb_rd = __longlong_as_double((long long)(upper ? w0 : w2));
-    o.nb_id = upper ? id - 1 : id + 1;
-    return o;
-}
 template <int M = 2>
 __device__ __forceinline__ dd st_ld_rd(const TreeView &tv, int32_t id) {
     if (st_compact<M>(tv)) return dd{__ldg(&tv.rec16[id].rd), 0.0};
@@ -296,8 +268,10 @@ struct RecC {
     uint32_t key;
     double nb_rd;  // NB only: root distance of the node in the other half of the 32-byte sector
 };
-// NB = true: ONE 256-bit load of the whole sector (the record and its slot neighbour's, see
-// st_ld_rec_paired); NB = false: the 16-byte record alone
+// NB = true (paired records): ONE 256-bit load of the 32-byte sector that holds the node's record
+// AND its slot neighbour's (slot = id + shift, see st_tree_create): the neighbour of most leaves is
+// their parent, so when the MRCA turns out to be that node its root distance is already here -- no
+// third, dependent gather (ladder-like trees, sister queries).  NB = false: the 16-byte record alone
 template <bool NB>
 __device__ __forceinline__ RecC st_ld_rec_c(const TreeView &tv, int32_t id, bool hi_side) {
     if (NB) {

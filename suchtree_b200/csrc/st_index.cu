@@ -208,7 +208,7 @@ __global__ void k_compact_tables(int nb, int levels, int bs, int ts, const uint6
     }
 }
 
-// Which pair kernel suits this tree?  The paired-record kernel (st_ld_rec_paired) saves the
+// Which pair kernel suits this tree?  The paired-record kernel (st_ld_rec_c<true>) saves the
 // third, dependent gather whenever the MRCA is the sector neighbour of an endpoint, and costs a
 // few per cent when it is not.  Probe: N random leaf pairs; count those whose MRCA is NOT a block
 // minimum (the plain kernel would gather rd[mrca]) and, of those, the ones a sector neighbour
@@ -579,7 +579,7 @@ extern "C" int st_tree_create_ex(int device, int64_t n_nodes, const int32_t *par
             // neighbour (id - 1 or id + 1): slot = id + shift with the shift that puts most leaves
             // into the SAME sector as their parent, so that a query whose MRCA is the parent of
             // one endpoint (ladder-like trees: always) finds rd[mrca] in a sector it loads anyway
-            // (st_ld_rec_paired).  n + 2 slots, zero padded: the paired load never leaves the array.
+            // (st_ld_rec_c<true>).  n + 2 slots, zero padded: the paired load never leaves the array.
             int64_t votes[2] = {0, 0};
             for (int64_t v = 0; v < n_nodes; v += 2)
                 if (left[v] == -1 && parent[v] >= 0) ++votes[parent[v] == v + 1 ? 0 : 1];

@@ -100,38 +100,14 @@ __device__ __forceinline__ void st_pair(const TreeView &tv, const SmemTables &sm
     if (want_m) m = st_mrca_id<M>(tv, sm, k, ft);
 }
 
-// the same with paired records (compact layout): rd[mrca] from the block table, an endpoint,
-// an endpoint's sector neighbour -- or, failing all that, one more gather
-__device__ __forceinline__ void st_pair_paired(const TreeView &tv, const SmemTables &sm, const PairQ &q,
-                                               const RecRaw &l, const RecRaw &h, double nbl, double nbh,
-                                               bool want_d, bool want_m, double &d, int32_t &m) {
-    bool ft = false;
-    const uint64_t k = q.lo == q.hi ? uint64_t(uint32_t(q.lo))
-                                    : st_rmq<1>(tv, sm, q.lo, q.hi, l.suf, h.pre, &ft);
-    if (want_d) {
-        double rm;
-        if (ft) {
-            rm = sm.brd8[st_key_id(k)];
-        } else {
-            const int32_t id = st_key_id(k);
-            // slot parity of an id: which half of its sector, hence which neighbour came along
-            const bool lo_upper = (reinterpret_cast<uintptr_t>(tv.rec16 + q.lo) & 16) != 0;
-            const bool hi_upper = (reinterpret_cast<uintptr_t>(tv.rec16 + q.hi) & 16) != 0;
-            if (id == q.hi + (hi_upper ? -1 : 1)) rm = nbh;
-            else if (id == q.lo + (lo_upper ? -1 : 1)) rm = nbl;
-            else if (id == q.lo) rm = l.rd_hi;
-            else if (id == q.hi) rm = h.rd_hi;
-            else rm = __ldg(&tv.rec16[id].rd);
-        }
-        d = st_patristic(dd{l.rd_hi, 0.0}, dd{h.rd_hi, 0.0}, dd{rm, 0.0});
-    }
-    if (want_m) m = st_mrca_id<1>(tv, sm, k, ft);
-}
-
 // P pairs per thread per iteration: 2P independent record gathers are in flight
 // before anything depends on them (the kernel is latency-bound on those gathers).
-// PR = 1 (compact layout only): endpoint records come with their sector neighbours
-// (st_ld_rec_paired), and rd[mrca] is taken from an endpoint or a neighbour when it is one.
+// PR selects the form of the per-pair work:
+//   0  generic (any layout: wide records, double-double root distances, 64-bit keys)
+//   2  lean compact (st_pair_c: 3 registers per record, 32-bit keys) -- the default for compact trees
+//   3  lean compact with PAIRED records: each endpoint's whole 32-byte sector is fetched with one
+//      256-bit load, and rd[mrca] is taken from an endpoint or its sector neighbour when the MRCA
+//      is one (ladder-like trees; chosen per tree by the build-time probe, st_tree_create)
 template <typename IdxT, int P, int M, int QT, int MINB, int PR>
 __global__ void __launch_bounds__(QT, MINB)
 k_pairs(const TreeView tv, const IdxT *__restrict__ pairs, int64_t n, double *__restrict__ out,
@@ -189,17 +165,10 @@ k_pairs(const TreeView tv, const IdxT *__restrict__ pairs, int64_t n, double *__
             continue;
         }
         RecRaw l[P], h[P];
-        double nbl[P], nbh[P];  // PR: root distances of the endpoints' sector neighbours
 #pragma unroll
         for (int k = 0; k < P; ++k) {
-            if (PR) {
-                const RecPaired pl = st_ld_rec_paired(tv, q[k].lo), ph = st_ld_rec_paired(tv, q[k].hi);
-                l[k] = pl.r; h[k] = ph.r;
-                nbl[k] = pl.nb_rd; nbh[k] = ph.nb_rd;
-            } else {
-                l[k] = st_ld_rec<M>(tv, q[k].lo);
-                h[k] = st_ld_rec<M>(tv, q[k].hi);
-            }
+            l[k] = st_ld_rec<M>(tv, q[k].lo);
+            h[k] = st_ld_rec<M>(tv, q[k].hi);
         }
         double d[P];
         int32_t m[P];
@@ -207,8 +176,7 @@ k_pairs(const TreeView tv, const IdxT *__restrict__ pairs, int64_t n, double *__
         for (int k = 0; k < P; ++k) {
             d[k] = 0.0;
             m[k] = 0;
-            if (PR) st_pair_paired(tv, sm, q[k], l[k], h[k], nbl[k], nbh[k], want_d, want_m, d[k], m[k]);
-            else st_pair<M>(tv, sm, q[k], l[k], h[k], want_d, want_m, d[k], m[k]);
+            st_pair<M>(tv, sm, q[k], l[k], h[k], want_d, want_m, d[k], m[k]);
             if (q[k].bad) {
                 d[k] = nan;
                 m[k] = -1;
@@ -290,11 +258,8 @@ static int st_paired_records(const st_tree *t) {
 template <typename IdxT, int P>
 static int launch_variant(const st_tree *t, const void *d_pairs, int64_t n, double *d_out,
                           int32_t *d_mrca, cudaStream_t stream, RangeStatus *status) {
-    if (t->compact && P == 2 && st_paired_records(t)) {
-        const char *e = getenv("SUCHTREE_B200_LEAN");
-        if (e && e[0] == '0') return launch_variant_m<IdxT, 2, 1, 1>(t, d_pairs, n, d_out, d_mrca, stream, status);
+    if (t->compact && P == 2 && st_paired_records(t))
         return launch_variant_m<IdxT, 2, 1, 3>(t, d_pairs, n, d_out, d_mrca, stream, status);
-    }
     if (t->compact) {
         // lean compact path (3 registers per record, 32-bit keys): +1 % over the generic one on
         // every tree shape, bit-identical; SUCHTREE_B200_LEAN = 0 keeps the generic path (tests).
