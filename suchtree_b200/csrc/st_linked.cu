@@ -38,6 +38,35 @@ __device__ __forceinline__ double linked_query(const TreeView &tv, const SmemTab
     return st_patristic(dd{l.rd_hi, l.rd_lo}, dd{h.rd_hi, h.rd_lo}, st_mrca_rd<M>(tv, sm, key, ft));
 }
 
+// Row-cached queries.  In the (i, j < i) enumeration consecutive pairs share their `i` link: its
+// two records (one per tree) are loaded once per row and kept in registers, so a pair costs ONE
+// new record gather per tree instead of two.  Compact layout only (M = 1); the other layouts
+// take the plain query.
+struct RecFull {
+    double rd;
+    uint32_t suf, pre;
+};
+__device__ __forceinline__ RecFull st_ld_rec_full(const TreeView &tv, int32_t id) {
+    uint64_t a, b;
+    asm volatile("ld.global.nc.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(tv.rec16 + id));
+    return RecFull{__longlong_as_double((long long)a), uint32_t(b), uint32_t(b >> 32)};
+}
+// distance(a, b) with a's record at hand
+template <int M>
+__device__ __forceinline__ double linked_query_row(const TreeView &tv, const SmemTables &sm, int32_t a,
+                                                   const RecFull &ra, int32_t b) {
+    if (M != 1) return linked_query<M>(tv, sm, a, b);
+    if (a == b) return 0.0;
+    const RecFull rb = st_ld_rec_full(tv, b);
+    const bool a_lo = a < b;
+    const RecC l{a_lo ? ra.rd : rb.rd, a_lo ? ra.suf : rb.suf, 0.0};
+    const RecC h{a_lo ? rb.rd : ra.rd, a_lo ? rb.pre : ra.pre, 0.0};
+    double d = 0.0;
+    int32_t m = 0;
+    st_pair_c<false>(tv, sm, PairQ{a_lo ? a : b, a_lo ? b : a, false}, l, h, true, false, d, m);
+    return d;
+}
+
 // layout mode of a tree as a template argument (0 wide, 1 compact, 3 wide records +
 // 32-bit tables): the two-tree kernels are instantiated per pair of modes, so no
 // run-time layout branches or dead table pointers cost registers
@@ -657,10 +686,19 @@ k_linked_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ 
     int64_t q = wbeg + (threadIdx.x & 31);
     int64_t i = 1, j = 0;
     if (q < wend) tri_unrank(first + q, i, j);
+    int64_t row = -1;  // the row (link i) whose records are cached below
+    int2 l2 = make_int2(0, 0);
+    RecFull ra{0.0, 0u, 0u}, rb{0.0, 0u, 0u};
     for (; q < wend; q += 32, tri_advance(i, j, 32)) {
-        const int2 l1 = __ldg(links + j), l2 = __ldg(links + i);
-        const double x = linked_query<MA>(ta, sa, l1.y, l2.y) - x0;
-        const double y = linked_query<MB>(tb, sb, l1.x, l2.x) - y0;
+        if (i != row) {
+            row = i;
+            l2 = __ldg(links + i);
+            if (MA == 1) ra = st_ld_rec_full(ta, l2.y);
+            if (MB == 1) rb = st_ld_rec_full(tb, l2.x);
+        }
+        const int2 l1 = __ldg(links + j);
+        const double x = linked_query_row<MA>(ta, sa, l2.y, ra, l1.y) - x0;
+        const double y = linked_query_row<MB>(tb, sb, l2.x, rb, l1.x) - y0;
         m.sx += x; m.sy += y;
         m.sxx += x * x; m.syy += y * y; m.sxy += x * y;
     }
@@ -914,11 +952,20 @@ k_clade_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ l
             i = int32_t(i64);
             j = int32_t(j64);
         }
+        int32_t row = -1;  // the row (link i of the run) whose records are cached below
+        int2 l2 = make_int2(0, 0);
+        RecFull ra{0.0, 0u, 0u}, rb{0.0, 0u, 0u};
         for (int32_t q = lane; q < len; q += 32) {
-            const int2 l1 = __ldg(run + j), l2 = __ldg(run + i);
+            if (i != row) {
+                row = i;
+                l2 = __ldg(run + i);
+                if (MA == 1) ra = st_ld_rec_full(ta, l2.y);
+                if (MB == 1) rb = st_ld_rec_full(tb, l2.x);
+            }
+            const int2 l1 = __ldg(run + j);
             for (j += 32; j >= i; ++i) j -= i;  // 32 positions on in the (i, j<i) enumeration
-            const double x = linked_query<MA>(ta, sa, l1.y, l2.y) - sh.x;
-            const double y = linked_query<MB>(tb, sb, l1.x, l2.x) - sh.y;
+            const double x = linked_query_row<MA>(ta, sa, l2.y, ra, l1.y) - sh.x;
+            const double y = linked_query_row<MB>(tb, sb, l2.x, rb, l1.x) - sh.y;
             m.sx += x; m.sy += y;
             m.sxx += x * x; m.syy += y * y; m.sxy += x * y;
         }
