@@ -2,6 +2,9 @@
 // call), the pinned result pool behind the Python shim's fresh result arrays, the
 // registration helpers for large caller inputs, and the copy roofline of the host path.
 #include "st_hostctx.cuh"
+#include "st_hostpool.cuh"
+
+#include <sys/mman.h>
 
 #include <algorithm>
 #include <chrono>
@@ -100,8 +103,8 @@ int st_lane_ensure_stage(HostLane *l, int64_t n, bool need_h_in, bool need_h_out
             cudaFree(l->d_in[i]);
             cudaFree(l->d_out[i]);
             cudaFree(l->d_out2[i]);
-            if (l->h_in[i]) cudaFreeHost(l->h_in[i]);
-            if (l->h_out[i]) cudaFreeHost(l->h_out[i]);
+            if (l->h_in[i]) st_host_free(l->h_in[i]);
+            if (l->h_out[i]) st_host_free(l->h_out[i]);
             l->d_in[i] = l->d_out[i] = l->d_out2[i] = l->h_in[i] = l->h_out[i] = nullptr;
         }
         l->stage_pairs = 0;
@@ -113,10 +116,9 @@ int st_lane_ensure_stage(HostLane *l, int64_t n, bool need_h_in, bool need_h_out
         l->stage_pairs = want;
     }
     for (int i = 0; i < ST_LANE_SLOTS; ++i) {
-        if (need_h_in && !l->h_in[i])
-            ST_CUDA(cudaHostAlloc(&l->h_in[i], size_t(l->stage_pairs) * 16, cudaHostAllocPortable));
-        if (need_h_out && !l->h_out[i])
-            ST_CUDA(cudaHostAlloc(&l->h_out[i], size_t(l->stage_pairs) * 8, cudaHostAllocPortable));
+        int rc = ST_OK;
+        if (need_h_in && !l->h_in[i] && (rc = st_pinned_alloc(size_t(l->stage_pairs) * 16, &l->h_in[i])) != ST_OK) return rc;
+        if (need_h_out && !l->h_out[i] && (rc = st_pinned_alloc(size_t(l->stage_pairs) * 8, &l->h_out[i])) != ST_OK) return rc;
     }
     return ST_OK;
 }
@@ -186,10 +188,20 @@ int st_raise_smem_impl(const void *kern, int device, int bytes) {
 // pool is page-locked already, so the D2H copies land in it directly.  Freed blocks are
 // cached (same-shape calls in a loop recycle two blocks) up to a byte cap.
 namespace {
+// One page-locked block.  Large blocks are anonymous mappings on transparent huge pages,
+// first-touched by the host pool and then page-locked in place (cudaHostRegister): 0.04-0.09 s
+// for 800 MB against 0.31-0.41 s for cudaHostAlloc on the same box (scripts/pin_exp.cu,
+// profiles/r02_summary.md) -- the cost a first large call pays.  Small blocks, and boxes where
+// the mapping or the registration fails, use cudaHostAlloc.
+struct PinnedBlk {
+    size_t cls = 0;        // size class (bytes handed out)
+    void *map = nullptr;   // mmap base (NULL: the block came from cudaHostAlloc)
+    size_t map_bytes = 0;
+};
 struct PinnedPool {
     std::mutex mu;
-    std::unordered_map<void *, size_t> live;            // handed out: ptr -> class bytes
-    std::multimap<size_t, void *> free_blocks;          // cached: class bytes -> ptr
+    std::unordered_map<void *, PinnedBlk> live;           // handed out
+    std::multimap<size_t, std::pair<void *, PinnedBlk>> free_blocks;  // cached: class bytes -> block
     size_t cached_bytes = 0;
     size_t cap_bytes = size_t(4) << 30;
     bool cap_read = false;
@@ -202,52 +214,104 @@ size_t size_class(size_t bytes) {
     const size_t step = std::max(min_step, p >> 3);
     return (bytes + step - 1) / step * step;
 }
+
+const size_t ST_HUGE = size_t(2) << 20;
+const size_t ST_MAP_MIN = size_t(16) << 20;  // below this cudaHostAlloc is as quick
+
+bool map_mode_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("SUCHTREE_B200_PINNED_MMAP");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
+// page-locked block of `cls` bytes (a multiple of 2 MiB); false: the caller falls back
+bool map_pinned(size_t cls, void **out, PinnedBlk *blk) {
+    const size_t map_bytes = cls + ST_HUGE;
+    void *base = mmap(nullptr, map_bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (base == MAP_FAILED) return false;
+    char *q = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(base) + ST_HUGE - 1) & ~uintptr_t(ST_HUGE - 1));
+    madvise(q, cls, MADV_HUGEPAGE);  // advisory: 4 KiB pages still work, only slower to lock
+    const int parts = int(std::min<size_t>(size_t(st_host_threads()), cls / (size_t(8) << 20) + 1));
+    st_parallel_for(parts, [&](int p, int np) {  // first touch in parallel (zero pages are faulted in here)
+        const size_t b = (cls / 4096) * size_t(p) / size_t(np) * 4096, e = (cls / 4096) * size_t(p + 1) / size_t(np) * 4096;
+        for (size_t o = b; o < e; o += 4096) q[o] = 0;
+    });
+    if (cudaHostRegister(q, cls, cudaHostRegisterPortable) != cudaSuccess) {
+        cudaGetLastError();
+        munmap(base, map_bytes);
+        return false;
+    }
+    blk->cls = cls;
+    blk->map = base;
+    blk->map_bytes = map_bytes;
+    *out = q;
+    return true;
+}
+
+void release_pinned(void *p, const PinnedBlk &b) {
+    if (b.map) {
+        if (cudaHostUnregister(p) != cudaSuccess) cudaGetLastError();  // (at interpreter exit the runtime may be gone)
+        munmap(b.map, b.map_bytes);
+    } else if (cudaFreeHost(p) != cudaSuccess) {
+        cudaGetLastError();
+    }
+}
 }  // namespace
 
-extern "C" int st_host_alloc(int64_t bytes, void **out) {
-    if (!out || bytes < 0) return ST_ERR_INVALID_ARG;
+int st_pinned_alloc(size_t bytes, void **out) {
     *out = nullptr;
-    const size_t cls = size_class(size_t(std::max<int64_t>(bytes, 1)));
+    const size_t cls = size_class(std::max<size_t>(bytes, 1));
     {
         std::lock_guard<std::mutex> l(g_pool.mu);
         auto it = g_pool.free_blocks.find(cls);
         if (it != g_pool.free_blocks.end()) {
-            *out = it->second;
+            *out = it->second.first;
+            g_pool.live[*out] = it->second.second;
             g_pool.free_blocks.erase(it);
             g_pool.cached_bytes -= cls;
-            g_pool.live[*out] = cls;
             return ST_OK;
         }
     }
     void *p = nullptr;
-    cudaError_t e = cudaHostAlloc(&p, cls, cudaHostAllocPortable);
-    if (e != cudaSuccess) {
-        // make room: drop the cache and retry once
-        std::vector<void *> drop;
-        {
-            std::lock_guard<std::mutex> l(g_pool.mu);
-            for (auto &kv : g_pool.free_blocks) drop.push_back(kv.second);
-            g_pool.free_blocks.clear();
-            g_pool.cached_bytes = 0;
+    PinnedBlk blk;
+    blk.cls = cls;
+    if (!(cls >= ST_MAP_MIN && map_mode_enabled() && map_pinned(cls, &p, &blk))) {
+        cudaError_t e = cudaHostAlloc(&p, cls, cudaHostAllocPortable);
+        if (e != cudaSuccess) {
+            // make room: drop the cache and retry once
+            std::vector<std::pair<void *, PinnedBlk>> drop;
+            {
+                std::lock_guard<std::mutex> l(g_pool.mu);
+                for (auto &kv : g_pool.free_blocks) drop.push_back(kv.second);
+                g_pool.free_blocks.clear();
+                g_pool.cached_bytes = 0;
+            }
+            for (auto &q : drop) release_pinned(q.first, q.second);
+            cudaGetLastError();
+            e = cudaHostAlloc(&p, cls, cudaHostAllocPortable);
         }
-        for (void *q : drop) cudaFreeHost(q);
-        cudaGetLastError();
-        e = cudaHostAlloc(&p, cls, cudaHostAllocPortable);
-    }
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        st_set_error("st_host_alloc: cudaHostAlloc(%zu) failed: %s", cls, cudaGetErrorString(e));
-        return e == cudaErrorMemoryAllocation ? ST_ERR_NOMEM : ST_ERR_CUDA;
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            st_set_error("st_host_alloc: cudaHostAlloc(%zu) failed: %s", cls, cudaGetErrorString(e));
+            return e == cudaErrorMemoryAllocation ? ST_ERR_NOMEM : ST_ERR_CUDA;
+        }
     }
     std::lock_guard<std::mutex> l(g_pool.mu);
-    g_pool.live[p] = cls;
+    g_pool.live[p] = blk;
     *out = p;
     return ST_OK;
 }
 
+extern "C" int st_host_alloc(int64_t bytes, void **out) {
+    if (!out || bytes < 0) return ST_ERR_INVALID_ARG;
+    return st_pinned_alloc(size_t(bytes), out);
+}
+
 extern "C" int st_host_free(void *p) {
     if (!p) return ST_OK;
-    size_t cls = 0;
+    PinnedBlk blk;
     bool keep = false;
     {
         std::lock_guard<std::mutex> l(g_pool.mu);
@@ -256,24 +320,24 @@ extern "C" int st_host_free(void *p) {
             st_set_error("st_host_free: pointer was not allocated by st_host_alloc");
             return ST_ERR_INVALID_ARG;
         }
-        cls = it->second;
+        blk = it->second;
         g_pool.live.erase(it);
         if (!g_pool.cap_read) {
             g_pool.cap_read = true;
             if (const char *e = getenv("SUCHTREE_B200_PINNED_CACHE_MB")) g_pool.cap_bytes = size_t(atoll(e)) << 20;
         }
-        if (g_pool.cached_bytes + cls <= g_pool.cap_bytes) {
-            g_pool.free_blocks.emplace(cls, p);
-            g_pool.cached_bytes += cls;
+        if (g_pool.cached_bytes + blk.cls <= g_pool.cap_bytes) {
+            g_pool.free_blocks.emplace(blk.cls, std::make_pair(p, blk));
+            g_pool.cached_bytes += blk.cls;
             keep = true;
         }
     }
-    if (!keep && cudaFreeHost(p) != cudaSuccess) cudaGetLastError();  // (at interpreter exit the runtime may be gone)
+    if (!keep) release_pinned(p, blk);
     return ST_OK;
 }
 
 extern "C" int st_host_trim(int64_t keep_bytes) {
-    std::vector<void *> drop;
+    std::vector<std::pair<void *, PinnedBlk>> drop;
     {
         std::lock_guard<std::mutex> l(g_pool.mu);
         while (!g_pool.free_blocks.empty() && int64_t(g_pool.cached_bytes) > std::max<int64_t>(keep_bytes, 0)) {
@@ -283,8 +347,7 @@ extern "C" int st_host_trim(int64_t keep_bytes) {
             g_pool.free_blocks.erase(it);
         }
     }
-    for (void *q : drop)
-        if (cudaFreeHost(q) != cudaSuccess) cudaGetLastError();
+    for (auto &q : drop) release_pinned(q.first, q.second);
     return ST_OK;
 }
 

@@ -51,6 +51,9 @@ struct LaneGuard {
 // grow the lane's staging to hold chunks of min(n, ST_STAGE_PAIRS_MAX) pairs
 int st_lane_ensure_stage(HostLane *lane, int64_t n, bool need_h_in, bool need_h_out);
 
+// page-locked memory from the pool behind st_host_alloc (release with st_host_free)
+int st_pinned_alloc(size_t bytes, void **out);
+
 // Read the lane's status word after its kernels (synchronises `stream`, which must be
 // ordered after every kernel that could have written it); clears it when set.
 // *max_bad / *min_bad = 0 when nothing was flagged.
