@@ -216,7 +216,7 @@ size_t size_class(size_t bytes) {
 }
 
 const size_t ST_HUGE = size_t(2) << 20;
-const size_t ST_MAP_MIN = size_t(16) << 20;  // below this cudaHostAlloc is as quick
+const size_t ST_MAP_MIN = size_t(4) << 20;  // two huge pages; below this cudaHostAlloc is as quick
 
 bool map_mode_enabled() {
     static const bool on = [] {

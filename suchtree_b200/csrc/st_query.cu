@@ -458,6 +458,22 @@ static int host_pairs_small(const st_tree *t, HostLane *lane, const int64_t *pai
     return ST_OK;
 }
 
+// Pairs per chunk of the pipeline: the staging slot for long calls; a mid-size call is cut
+// into several chunks so that packing, the two copy directions and the kernel overlap within it
+// (SUCHTREE_B200_CHUNK_PAIRS overrides: experiments).
+static int64_t st_chunk_pairs(int64_t n, int64_t stage_pairs) {
+    // about four chunks per call, 2^18 .. stage_pairs pairs each (scripts/midsize_exp.py: 4e6 pairs
+    // 1.72 -> 1.14 ms, 2e6 0.82 -> 0.66 ms, 1e6 0.45 -> 0.39 ms; 3e7 and beyond: whole slots)
+    int64_t c = int64_t(1) << 18;
+    while (c * 8 <= n) c <<= 1;
+    c = std::min(c, stage_pairs);
+    if (const char *e = getenv("SUCHTREE_B200_CHUNK_PAIRS")) {
+        const int64_t v = atoll(e);
+        if (v >= 4096) c = std::min(stage_pairs, v & ~int64_t(3));
+    }
+    return c;
+}
+
 static int host_pairs_run(const st_tree *t, const int64_t *pairs, int64_t s0, int64_t s1, int64_t n,
                           double *out_d, int32_t *out_m) {
     if (!t || n < 0 || (n > 0 && (!pairs || (!out_d == !out_m)))) {  // exactly one output
@@ -491,7 +507,7 @@ static int host_pairs_run(const st_tree *t, const int64_t *pairs, int64_t s0, in
     const bool hybrid = pack && pack_fraction < 1.0 && in_pinned;
     int rc = st_lane_ensure_stage(lane, n, pack, !out_pinned);
     if (rc != ST_OK) return rc;
-    const int64_t C = lane->stage_pairs;
+    const int64_t C = st_chunk_pairs(n, lane->stage_pairs);
     const size_t out_elem = out_d ? 8 : 4;
     char *user_out = out_d ? reinterpret_cast<char *>(out_d) : reinterpret_cast<char *>(out_m);
     int64_t chunk_begin[ST_LANE_SLOTS] = {0, 0, 0}, chunk_len[ST_LANE_SLOTS] = {0, 0, 0};

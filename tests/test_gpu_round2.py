@@ -83,21 +83,21 @@ def test_pool_trim_and_foreign_pointer():
 
 
 def test_large_pool_blocks_are_huge_page_mappings_locked_in_place():
-    """Blocks of >= 16 MiB are anonymous mappings (2 MiB aligned, transparent huge pages where the
+    """Blocks of >= 4 MiB are anonymous mappings (2 MiB aligned, transparent huge pages where the
     kernel grants them) page-locked with cudaHostRegister; smaller ones come from cudaHostAlloc.
     Both kinds are page-locked, writable everywhere, recycled by size class and released by trim."""
     L = _lib.lib()
     gc.collect()
     L.st_host_trim(0)
     big = _lib.pinned_empty((5 << 20,), np.float64)  # 40 MiB
-    small = _lib.pinned_empty((1 << 18,), np.float64)  # 2 MiB
+    small = _lib.pinned_empty((1 << 17,), np.float64)  # 1 MiB
     assert _pinned(big) and _pinned(small) and _pinned(big[-1:])
     if os.environ.get("SUCHTREE_B200_PINNED_MMAP", "1") != "0":
         assert big.ctypes.data % (2 << 20) == 0
     big[:] = 2.5
     big[-1] = 7.0
     small[:] = 1.0
-    assert big[0] == 2.5 and big[-1] == 7.0 and float(small.sum()) == float(1 << 18)
+    assert big[0] == 2.5 and big[-1] == 7.0 and float(small.sum()) == float(1 << 17)
     ptr = big.ctypes.data
     del big
     gc.collect()
