@@ -16,6 +16,7 @@ import os
 import numpy as np
 
 from . import _lib, shard
+from .extras import LinkedExtras
 from .tree import SuchTree
 
 _UINT64_MAX = np.iinfo(np.uint64).max
@@ -47,7 +48,7 @@ def _as_f64_vector(v):
     return np.ascontiguousarray(a)
 
 
-class SuchLinkedTrees:
+class SuchLinkedTrees(LinkedExtras):
     def __init__(self, tree_a, tree_b, link_matrix):
         # the reference seeds its xorshift64* state in __cinit__ (MuchTree.pyx:2572-2573),
         # i.e. before anything else happens -- same draw, same place

@@ -15,6 +15,7 @@ import numpy as np
 
 from . import _lib, newick
 from .exceptions import InvalidNodeError, NodeNotFoundError, TreeStructureError
+from .extras import TreeExtras
 
 
 def _deprecation_warning(old_name, new_name, version="2.0"):
@@ -50,7 +51,7 @@ def _read_tree_input(tree_input):
         return f.read()
 
 
-class SuchTree:
+class SuchTree(TreeExtras):
     """Immutable, strictly bifurcating phylogenetic tree resident on one B200.
 
     SuchTree(tree_input) accepts what the reference accepts (MuchTree.pyx:126-155).
