@@ -23,11 +23,15 @@ with open(os.path.join(HERE, "golden", "trees.json")) as f:
     TREES = json.load(f)
 
 
-def _source(name):
+def _source(name, text=True):
+    """NEWICK text of a golden tree (text=False: what SuchTree() takes -- the string or the path)."""
     nw = TREES[name].get("newick")
     if nw:
         return nw
-    with open(os.path.join(DATA, name)) as f:
+    path = os.path.join(DATA, name)
+    if not text:
+        return path
+    with open(path) as f:
         return f.read()
 
 
@@ -193,7 +197,7 @@ def test_extras_on_host_double(name):
 def test_extras_on_device_tree(name):
     from suchtree_b200 import SuchTree
 
-    check_tree(SuchTree(_source(name)), API["trees"][name])
+    check_tree(SuchTree(_source(name, text=False)), API["trees"][name])
 
 
 @pytest.mark.gpu
