@@ -29,7 +29,8 @@ setup(
     version="0.1.0",
     description="B200-native batched patristic distances: a drop-in for the hot path of SuchTree",
     packages=["suchtree_b200"],
-    package_data={"suchtree_b200": ["libsuchtree_b200.so", "csrc/*.cu", "csrc/*.cuh", "include/*.h"]},
+    package_data={"suchtree_b200": ["libsuchtree_b200.so", "libsuchtree_b200_py.so", "csrc/*.cu", "csrc/*.cuh", "include/*.h",
+                                   "pyglue/*.c"]},
     python_requires=">=3.9",
     install_requires=["numpy"],
     cmdclass={"build_py": BuildWithNvcc},

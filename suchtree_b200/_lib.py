@@ -181,6 +181,32 @@ def bench_lib():
     return _bench_lib
 
 
+_py_glue = False  # False: not tried yet; None: unavailable
+
+
+def py_glue():
+    """The CPython glue library (name -> id walks in C), or None when it cannot be built here
+    (no compiler / no Python.h): callers keep their Python walk then.  Loaded with PyDLL: the
+    GIL stays held, arguments are Python objects."""
+    global _py_glue
+    if _py_glue is False:
+        with _lock:
+            if _py_glue is False:
+                g = None
+                try:
+                    with _build_lock():
+                        if _build.py_glue_needs_build():
+                            _build.build_py_glue()
+                    if os.path.exists(_build.PY_LIB):
+                        g = C.PyDLL(_build.PY_LIB)
+                        g.st_py_names_to_ids.restype = C.c_ssize_t
+                        g.st_py_names_to_ids.argtypes = [C.py_object, C.py_object, C.c_void_p, C.c_ssize_t]
+                except Exception:
+                    g = None
+                _py_glue = g
+    return _py_glue
+
+
 def last_error():
     return lib().st_last_error().decode(errors="replace")
 

@@ -2,6 +2,7 @@
 
     libsuchtree_b200.so        the product: csrc/*.cu behind include/suchtree_b200.h
     libsuchtree_b200_bench.so  bench-only tooling: bench/*.cu behind include/suchtree_b200_bench.h
+    libsuchtree_b200_py.so     CPython glue of the by-name entry points: pyglue/st_pynames.c (gcc)
 
     python -m suchtree_b200.build [--force] [--verbose]
 
@@ -22,6 +23,10 @@ CSRC = os.path.join(HERE, "csrc")
 BENCH_SRC = os.path.join(HERE, "bench")
 LIB = os.path.join(HERE, "libsuchtree_b200.so")
 BENCH_LIB = os.path.join(HERE, "libsuchtree_b200_bench.so")
+# CPython glue (name -> id walks of the by-name entry points): plain C against Python.h, loaded
+# with ctypes.PyDLL; optional -- without it the shim runs the same walk in Python
+PY_SRC = os.path.join(HERE, "pyglue", "st_pynames.c")
+PY_LIB = os.path.join(HERE, "libsuchtree_b200_py.so")
 # the C headers: <repo>/include in a checkout, <package>/include when pip-installed
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 if not os.path.exists(os.path.join(INCLUDE, "suchtree_b200.h")):
@@ -147,11 +152,46 @@ def _build_one(which, force, verbose, extra):
     return lib
 
 
-def build(force=False, verbose=False, extra=(), which=("product", "bench")):
+def py_glue_id():
+    h = hashlib.sha1()
+    with open(PY_SRC, "rb") as f:
+        h.update(f.read())
+    h.update(sys.version.encode())
+    return h.hexdigest()[:16]
+
+
+def py_glue_needs_build():
+    if not os.path.exists(PY_SRC):
+        return False
+    return not os.path.exists(PY_LIB) or built_id(PY_LIB) != py_glue_id()
+
+
+def build_py_glue(verbose=False):
+    """gcc -shared against this interpreter's Python.h; returns the path, or None when there is
+    no compiler / no header (the shim then keeps its Python walk)."""
+    import sysconfig
+
+    inc = sysconfig.get_paths().get("include") or ""
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if not cc or not os.path.exists(os.path.join(inc, "Python.h")):
+        return None
+    cmd = [cc, "-O2", "-shared", "-fPIC", "-fvisibility=hidden", "-I", inc, PY_SRC, "-o", PY_LIB]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    with open(_id_file(PY_LIB), "w") as f:
+        f.write(py_glue_id() + "\n")
+    return PY_LIB
+
+
+def build(force=False, verbose=False, extra=(), which=("product", "bench", "py")):
     """One object per translation unit (compiled in parallel, only the stale ones),
     then one device-link-free shared library per target."""
     for w in which:
-        if force or extra or needs_build(w):
+        if w == "py":
+            if force or py_glue_needs_build():
+                build_py_glue(verbose)
+        elif force or extra or needs_build(w):
             _build_one(w, force, verbose, extra)
     return LIB
 

@@ -578,3 +578,34 @@ def test_more_callers_than_lanes_wait_their_turn(tree):
         t.join(timeout=300)
     assert not errs, errs
     assert len(out) == 12
+
+
+# ------------------------------------------------------- by-name entry points, C glue -------
+def test_by_name_entry_points_same_through_c_glue_and_python_walk():
+    """distances_by_name / quartet_topologies_by_name (MuchTree.pyx:945-979, :1378-1422): the C
+    name -> id walk and the Python one give the same lists, and the same errors."""
+    from suchtree_b200.exceptions import NodeNotFoundError
+
+    T = SuchTree(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "data", "fishworm_guest.tree"))
+    names = T.leaf_names
+    rng = np.random.default_rng(8)
+    pairs = [(names[a], names[b]) for a, b in rng.integers(0, len(names), size=(20000, 2))]
+    quartets = [tuple(names[i] for i in rng.choice(len(names), 4, replace=False)) for _ in range(2000)]
+    if _lib.py_glue() is None:
+        pytest.skip("C glue not built here")
+    d_c, q_c = T.distances_by_name(pairs), T.quartet_topologies_by_name(quartets)
+    assert isinstance(d_c, list) and isinstance(d_c[0], float) and isinstance(q_c[0], frozenset)
+    saved = _lib._py_glue
+    _lib._py_glue = None
+    try:
+        d_p, q_p = T.distances_by_name(pairs), T.quartet_topologies_by_name(quartets)
+    finally:
+        _lib._py_glue = saved
+    assert d_c == d_p and q_c == q_p
+    ids = np.array([[T.leaves[a], T.leaves[b]] for a, b in pairs], dtype=np.int64)
+    assert d_c == T.distances_bulk(ids).tolist()
+    with pytest.raises(NodeNotFoundError):
+        T.distances_by_name(pairs[:10] + [(names[0], "nope")])
+    with pytest.raises(TypeError):
+        T.distances_by_name(pairs[:10] + [(names[0], 3)])
+    assert T.distances_by_name([[names[0], names[1]]]) == T.distances_by_name([(names[0], names[1])])

@@ -392,3 +392,39 @@ def test_input_registration_bookkeeping_without_a_device(monkeypatch):
     del big
     gc.collect()
     assert key not in _lib._registered and calls[-1] == ("unreg", ptr)
+
+
+# ------------------------------------------------------------- name -> id glue (C) ----------
+def test_py_glue_converts_name_rows_and_reports_the_first_bad_row():
+    """pyglue/st_pynames.c: the by-name entry points' name -> id walk as one C loop
+    (MuchTree.pyx:964-975, :1397-1408).  -1 = all rows converted; otherwise the index of the
+    first row the reference's own loop has to look at (it raises the reference's error)."""
+    import ctypes as C
+
+    from suchtree_b200 import _lib
+
+    g = _lib.py_glue()
+    if g is None:
+        pytest.skip("no C compiler / Python.h here: the shim keeps its Python walk")
+    leaves = {"n%d" % i: 2 * i for i in range(1000)}
+    rng = np.random.default_rng(0)
+    idx = rng.integers(0, 1000, size=(5000, 2))
+    rows = [("n%d" % a, "n%d" % b) for a, b in idx]
+    out = np.full((5000, 2), -7, dtype=np.int64)
+    assert g.st_py_names_to_ids(rows, leaves, out.ctypes.data, 2) == -1
+    assert np.array_equal(out, 2 * idx)
+    rows4 = [["n1", "n2", "n3", "n4"], ("n5", "n6", "n7", "n8")]  # lists and tuples both count as rows
+    out4 = np.empty((2, 4), dtype=np.int64)
+    assert g.st_py_names_to_ids(rows4, leaves, out4.ctypes.data, 4) == -1
+    assert out4.tolist() == [[2, 4, 6, 8], [10, 12, 14, 16]]
+    for bad_row, at in ((("n1", "nope"), 17), (("n1", 3), 4), (("n1",), 0), ("n1n2", 9), (("n1", "n2", "n3"), 4999)):
+        r = list(rows)
+        r[at] = bad_row
+        assert g.st_py_names_to_ids(r, leaves, out.ctypes.data, 2) == at
+    assert g.st_py_names_to_ids([], leaves, out.ctypes.data, 2) == -1
+    assert g.st_py_names_to_ids(tuple(rows), leaves, out.ctypes.data, 2) == 0  # not a list: caller's slow path
+
+    class Name(str):
+        pass
+
+    assert g.st_py_names_to_ids([(Name("n1"), "n2")], leaves, out.ctypes.data, 2) == 0  # exact str only
