@@ -132,7 +132,7 @@ k_pairs(const TreeView tv, const IdxT *__restrict__ pairs, int64_t n, double *__
             st_decode_pair<IdxT, P>(cur, k, a, b);
             q[k] = st_make_query(tv, a, b);
         }
-        if (PR >= 2) {  // lean compact path (PR = 3: with the sector neighbours)
+        if constexpr (PR >= 2) {  // lean compact path (PR = 3: with the sector neighbours)
             constexpr bool NB = PR == 3;
             RecC lc[P], hc[P];
 #pragma unroll
@@ -162,35 +162,35 @@ k_pairs(const TreeView tv, const IdxT *__restrict__ pairs, int64_t n, double *__
                 else if (P == 2) st_st_stream_i32x2(mrca_out + P * i, mc[0], mc[1]);
                 else st_st_stream_i32(mrca_out + i, mc[0]);
             }
-            continue;
-        }
-        RecRaw l[P], h[P];
+        } else {
+            RecRaw l[P], h[P];
 #pragma unroll
-        for (int k = 0; k < P; ++k) {
-            l[k] = st_ld_rec<M>(tv, q[k].lo);
-            h[k] = st_ld_rec<M>(tv, q[k].hi);
-        }
-        double d[P];
-        int32_t m[P];
-#pragma unroll
-        for (int k = 0; k < P; ++k) {
-            d[k] = 0.0;
-            m[k] = 0;
-            st_pair<M>(tv, sm, q[k], l[k], h[k], want_d, want_m, d[k], m[k]);
-            if (q[k].bad) {
-                d[k] = nan;
-                m[k] = -1;
+            for (int k = 0; k < P; ++k) {
+                l[k] = st_ld_rec<M>(tv, q[k].lo);
+                h[k] = st_ld_rec<M>(tv, q[k].hi);
             }
-        }
-        if (want_d) {
-            if (P == 4) st_st_stream_f64x4(out + P * i, d[0], d[1], d[2], d[3]);
-            else if (P == 2) st_st_stream_f64x2(out + P * i, d[0], d[1]);
-            else st_st_stream_f64(out + i, d[0]);
-        }
-        if (want_m) {
-            if (P == 4) st_st_stream_i32x4(mrca_out + P * i, m[0], m[1], m[2], m[3]);
-            else if (P == 2) st_st_stream_i32x2(mrca_out + P * i, m[0], m[1]);
-            else st_st_stream_i32(mrca_out + i, m[0]);
+            double d[P];
+            int32_t m[P];
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                d[k] = 0.0;
+                m[k] = 0;
+                st_pair<M>(tv, sm, q[k], l[k], h[k], want_d, want_m, d[k], m[k]);
+                if (q[k].bad) {
+                    d[k] = nan;
+                    m[k] = -1;
+                }
+            }
+            if (want_d) {
+                if (P == 4) st_st_stream_f64x4(out + P * i, d[0], d[1], d[2], d[3]);
+                else if (P == 2) st_st_stream_f64x2(out + P * i, d[0], d[1]);
+                else st_st_stream_f64(out + i, d[0]);
+            }
+            if (want_m) {
+                if (P == 4) st_st_stream_i32x4(mrca_out + P * i, m[0], m[1], m[2], m[3]);
+                else if (P == 2) st_st_stream_i32x2(mrca_out + P * i, m[0], m[1]);
+                else st_st_stream_i32(mrca_out + i, m[0]);
+            }
         }
     }
     // the n % P pairs left over: one thread each
@@ -227,7 +227,10 @@ static int launch_variant_m(const st_tree *t, const void *d_pairs, int64_t n, do
     static thread_local int cached_smem[64] = {0}, cached_per_sm[64] = {0};
     const int smem = t->query_smem_bytes, dv = t->device & 63;
     if (smem > 48 * 1024 && configured_smem[dv] < smem) {
-        ST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        // raise-only and process-wide (st_hostctx.cuh): a thread with smaller tables can never
+        // lower the limit under another thread's launch; the thread-local mark only skips the lock
+        const int rc = st_raise_smem(kern, t->device, smem);
+        if (rc != ST_OK) return rc;
         configured_smem[dv] = smem;
     }
     if (cached_per_sm[dv] == 0 || cached_smem[dv] != smem) {
