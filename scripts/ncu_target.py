@@ -1,6 +1,7 @@
 """A short, single-kernel workload for `ncu --set full` captures (run under gpurun):
     python scripts/ncu_target.py pairs  <yule|balanced|caterpillar> <n_pairs> [paired]
     python scripts/ncu_target.py quartets <n_quartets> <qpt> <idx_bits>
+    python scripts/ncu_target.py linked      (cfg 4: 3 sampler launches, then 3 exhaustive-moment launches)
 3 warm-up launches + 2 launches of the kernel under study on device-resident input."""
 import os, sys
 sys.path.insert(0, '.')
@@ -22,6 +23,20 @@ if what == 'pairs':
     T.random_leaf_pairs_device(3, 0, n, pairs.data_ptr(), idx_bits=32, stream=s)
     for _ in range(5):
         T.distances_device(pairs.data_ptr(), n, out.data_ptr(), idx_bits=32, stream=s)
+elif what == 'linked':
+    import numpy as np
+    from suchtree_b200 import SuchLinkedTrees
+    n = 100_000
+    A, B = SuchTree.from_flat(synth.yule_tree(n, seed=4)), SuchTree.from_flat(synth.yule_tree(n, seed=5))
+    rng = np.random.default_rng(6)
+    ll = np.stack([2 * rng.integers(0, n, n), 2 * rng.integers(0, n, n)], axis=1).astype(np.int64)
+    S = SuchLinkedTrees.from_linklist(A, B, ll)
+    for _ in range(3):
+        S.sample_moments(125_000_000, seed=7, x0=20.0, y0=20.0)
+    S2 = SuchLinkedTrees.from_linklist(A, B, ll[:44904])
+    for _ in range(3):
+        S2.linked_moments(0, 126_020_270, x0=20.0, y0=20.0)
+    T = A
 else:
     n, qpt, bits = int(sys.argv[2]), sys.argv[3], int(sys.argv[4])
     os.environ['SUCHTREE_B200_QPT'] = qpt

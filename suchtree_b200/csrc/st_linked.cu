@@ -67,6 +67,60 @@ __device__ __forceinline__ double linked_query_row(const TreeView &tv, const Sme
     return d;
 }
 
+// Joined link records.  A sample or a link pair needs, per link and per tree, the endpoint's root
+// distance and its two block keys -- found so far by following the link row to one record per
+// tree (three dependent random sectors per link).  When both trees have the compact layout
+// and the fields fit, the handle keeps them JOINED per link: one 32-byte record = one sector
+//     rd_a, rd_b                    root distances of the link's TreeA / TreeB leaf
+//     pk_a, pk_b                    id | suffix key << ib | prefix key << (ib + kb), per tree
+// so a sampled pair costs 2 random sectors instead of 6, and the exhaustive (i, j < i)
+// enumeration -- lanes adjacent in j -- reads them CONTIGUOUSLY: no random gathers at all beyond
+// the ~3 % of pairs whose MRCA is not a block minimum.  Same arithmetic (st_pair_c), same bits.
+struct __align__(32) LinkRec {
+    double rd_a, rd_b;
+    uint64_t pk_a, pk_b;
+};
+static_assert(sizeof(LinkRec) == 32, "LinkRec must be one sector");
+struct JoinBits {
+    int ib_a, kb_a, ib_b, kb_b;  // id bits / key bits of TreeA's and TreeB's packed word
+};
+__device__ __forceinline__ LinkRec st_ld_linkrec(const LinkRec *p) {
+    uint64_t w0, w1, w2, w3;
+    asm volatile("ld.global.nc.L2::evict_last.v4.b64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(w0), "=l"(w1), "=l"(w2), "=l"(w3)
+                 : "l"(p));
+    return LinkRec{__longlong_as_double((long long)w0), __longlong_as_double((long long)w1), w2, w3};
+}
+// distance between the leaves of two links in one tree, from the joined halves alone
+__device__ __forceinline__ double joined_query(const TreeView &tv, const SmemTables &sm, double rd1, uint64_t pk1,
+                                               double rd2, uint64_t pk2, int ib, int kb) {
+    const uint32_t idm = (1u << ib) - 1u, km = (1u << kb) - 1u;
+    const int32_t a = int32_t(uint32_t(pk1) & idm), b = int32_t(uint32_t(pk2) & idm);
+    if (a == b) return 0.0;
+    const bool a_lo = a < b;
+    const uint64_t pl = a_lo ? pk1 : pk2, ph = a_lo ? pk2 : pk1;
+    const RecC l{a_lo ? rd1 : rd2, uint32_t(pl >> ib) & km, 0.0};
+    const RecC h{a_lo ? rd2 : rd1, uint32_t(ph >> (ib + kb)) & km, 0.0};
+    double d = 0.0;
+    int32_t m = 0;
+    st_pair_c<false>(tv, sm, PairQ{a_lo ? a : b, a_lo ? b : a, false}, l, h, true, false, d, m);
+    return d;
+}
+// builds the joined records of `L` link rows (b, a)
+__global__ void k_join_links(const TreeView ta, const TreeView tb, const int2 *__restrict__ rows, int64_t L,
+                             JoinBits jb, LinkRec *__restrict__ out) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= L) return;
+    const int2 r = rows[i];
+    const NodeRec16 a = ta.rec16[r.y], b = tb.rec16[r.x];
+    LinkRec o;
+    o.rd_a = a.rd;
+    o.rd_b = b.rd;
+    o.pk_a = uint64_t(uint32_t(r.y)) | (uint64_t(a.suf) << jb.ib_a) | (uint64_t(a.pre) << (jb.ib_a + jb.kb_a));
+    o.pk_b = uint64_t(uint32_t(r.x)) | (uint64_t(b.suf) << jb.ib_b) | (uint64_t(b.pre) << (jb.ib_b + jb.kb_b));
+    out[i] = o;
+}
+
 // layout mode of a tree as a template argument (0 wide, 1 compact, 3 wide records +
 // 32-bit tables): the two-tree kernels are instantiated per pair of modes, so no
 // run-time layout branches or dead table pointers cost registers
@@ -141,12 +195,15 @@ struct st_links {
     int64_t L = 0;
     int32_t *col_a = nullptr, *col_b = nullptr;  // linklist[:,1] (TreeA ids), linklist[:,0] (TreeB ids)
     int2 *rows = nullptr;                        // (b, a) per link, for the samplers
+    LinkRec *joined = nullptr;                   // joined records of `rows` (NULL: layouts / field widths do not allow it)
+    JoinBits jb{0, 0, 0, 0};
     // per-clade scans (st_links_clade_moments), built on first use per side (0: TreeB, 1: TreeA):
     // the links sorted (stably) by their id on that side, and first[v] = number of links with
     // side id < v -- a clade (an id interval) is then the run [first[lo], first[hi + 1])
     std::vector<int2> h_rows;
     mutable std::mutex scan_mu;
     mutable int2 *rows_sorted[2] = {nullptr, nullptr};
+    mutable LinkRec *joined_sorted[2] = {nullptr, nullptr};  // joined records of rows_sorted[side]
     mutable int32_t *first[2] = {nullptr, nullptr};
 };
 
@@ -168,11 +225,47 @@ extern "C" void st_links_destroy(st_links *k) {
     cudaFree(k->col_a);
     cudaFree(k->col_b);
     cudaFree(k->rows);
+    cudaFree(k->joined);
     for (int i = 0; i < 2; ++i) {
+        cudaFree(k->joined_sorted[i]);
         cudaFree(k->rows_sorted[i]);
         cudaFree(k->first[i]);
     }
     delete k;
+}
+
+// field widths of one tree's packed word, or false when a joined record cannot hold the tree
+static bool join_bits(const st_tree *t, int *ib, int *kb) {
+    if (!t->compact) return false;
+    *ib = std::max(1, st_ceil_log2_i64(t->n_nodes));
+    *kb = std::min(31, (64 - *ib) / 2);
+    if (*ib > 31) return false;
+    // compact keys are depth << block_shift | offset in block, depth <= the tree's depth
+    const uint64_t max_key = (uint64_t(uint32_t(t->depth)) << t->block_shift) | ((uint64_t(1) << t->block_shift) - 1);
+    return max_key < (uint64_t(1) << *kb);
+}
+// SUCHTREE_B200_JOINED = 0 keeps the separate link rows + node records (tests, experiments); read per call
+static bool joined_enabled() {
+    const char *e = getenv("SUCHTREE_B200_JOINED");
+    return !(e && e[0] == '0');
+}
+// joined records of L device rows into a fresh allocation (stream-ordered on the default stream, synchronised)
+static int build_joined(const st_links *k, const int2 *d_rows, int64_t L, LinkRec **out) {
+    *out = nullptr;
+    if (L < 1) return ST_OK;
+    LinkRec *d = nullptr;
+    if (cudaMalloc(reinterpret_cast<void **>(&d), size_t(L) * sizeof(LinkRec)) != cudaSuccess) {
+        cudaGetLastError();
+        return ST_OK;  // not an error: the callers fall back to the separate rows
+    }
+    k_join_links<<<int((L + 255) / 256), 256>>>(k->ta->view, k->tb->view, d_rows, L, k->jb, d);
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+        st_set_error("st_links: building the joined link records failed");
+        cudaFree(d);
+        return ST_ERR_CUDA;
+    }
+    *out = d;
+    return ST_OK;
 }
 
 extern "C" int st_links_create(const st_tree *ta, const st_tree *tb, const int64_t *linklist, int64_t L,
@@ -221,6 +314,13 @@ extern "C" int st_links_create(const st_tree *ta, const st_tree *tb, const int64
         st_set_error("st_links_create: %s", cudaGetErrorString(cudaGetLastError()));
         st_links_destroy(k);
         return ST_ERR_CUDA;
+    }
+    if (join_bits(ta, &k->jb.ib_a, &k->jb.kb_a) && join_bits(tb, &k->jb.ib_b, &k->jb.kb_b)) {
+        rc = build_joined(k, k->rows, L, &k->joined);
+        if (rc != ST_OK) {
+            st_links_destroy(k);
+            return rc;
+        }
     }
     *out = k;
     return ST_OK;
@@ -543,11 +643,14 @@ __device__ __forceinline__ double warp_sum(double v) {
 // both trees' block tables live in shared memory (up to ~2 x 96 KB): one big CTA per SM
 static const int MLT = 1024;
 
-template <int MA, int MB>
+// J: joined link records (LinkRec, both trees compact) instead of link rows + node records
+template <int MA, int MB, bool J = false>
 __global__ void __launch_bounds__(MLT)
-k_sample_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ links,
+k_sample_moments(const TreeView ta, const TreeView tb, const void *__restrict__ links_v, JoinBits jb,
                  uint32_t n_links, uint64_t seed, int64_t first, int64_t n, double x0, double y0,
                  double *__restrict__ partials /* [grid][5] */) {
+    const int2 *__restrict__ links = static_cast<const int2 *>(links_v);
+    const LinkRec *__restrict__ joined = static_cast<const LinkRec *>(links_v);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // two table sets back to back (second one 16-byte aligned)
     __shared__ __align__(8) uint64_t tables_bar[2];
@@ -570,10 +673,18 @@ k_sample_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ 
         for (int h = 0; h < 2; ++h) {
             const int64_t s = 2 * c + h;
             if (s < first || s >= first + n) continue;
-            int2 l1 = __ldg(links + st_bounded(w[2 * h], n_links));
-            int2 l2 = __ldg(links + st_bounded(w[2 * h + 1], n_links));
-            double x = linked_query<MA>(ta, sa, l1.y, l2.y) - x0;
-            double y = linked_query<MB>(tb, sb, l1.x, l2.x) - y0;
+            double x, y;
+            if constexpr (J) {
+                const LinkRec r1 = st_ld_linkrec(joined + st_bounded(w[2 * h], n_links));
+                const LinkRec r2 = st_ld_linkrec(joined + st_bounded(w[2 * h + 1], n_links));
+                x = joined_query(ta, sa, r1.rd_a, r1.pk_a, r2.rd_a, r2.pk_a, jb.ib_a, jb.kb_a) - x0;
+                y = joined_query(tb, sb, r1.rd_b, r1.pk_b, r2.rd_b, r2.pk_b, jb.ib_b, jb.kb_b) - y0;
+            } else {
+                int2 l1 = __ldg(links + st_bounded(w[2 * h], n_links));
+                int2 l2 = __ldg(links + st_bounded(w[2 * h + 1], n_links));
+                x = linked_query<MA>(ta, sa, l1.y, l2.y) - x0;
+                y = linked_query<MB>(tb, sb, l1.x, l2.x) - y0;
+            }
             m.sx += x; m.sy += y;
             m.sxx += x * x; m.syy += y * y; m.sxy += x * y;
         }
@@ -634,9 +745,16 @@ extern "C" int st_links_sample_moments(const st_links *k, uint64_t seed, int64_t
 #define ST_LAUNCH_SAMPLE(MA, MB)                                                                        \
     rc_launch = st_raise_smem(k_sample_moments<MA, MB>, ta->device, smem);                              \
     if (rc_launch == ST_OK)                                                                             \
-        k_sample_moments<MA, MB><<<grid, MLT, smem, s>>>(ta->view, tb->view, k->rows, uint32_t(k->L), seed, \
+        k_sample_moments<MA, MB><<<grid, MLT, smem, s>>>(ta->view, tb->view, k->rows, k->jb, uint32_t(k->L), seed, \
                                                          first_sample, n_samples, x0, y0, d_part)
-    ST_DISPATCH_MODES(tree_mode(ta), tree_mode(tb), ST_LAUNCH_SAMPLE);
+    if (k->joined && joined_enabled()) {
+        rc_launch = st_raise_smem(k_sample_moments<1, 1, true>, ta->device, smem);
+        if (rc_launch == ST_OK)
+            k_sample_moments<1, 1, true><<<grid, MLT, smem, s>>>(ta->view, tb->view, k->joined, k->jb, uint32_t(k->L),
+                                                                 seed, first_sample, n_samples, x0, y0, d_part);
+    } else {
+        ST_DISPATCH_MODES(tree_mode(ta), tree_mode(tb), ST_LAUNCH_SAMPLE);
+    }
 #undef ST_LAUNCH_SAMPLE
     if (rc_launch != ST_OK) {  // the kernel was not launched: no result to report
         cudaFreeAsync(d_part, s);
@@ -662,10 +780,12 @@ extern "C" int st_sample_moments(const st_tree *ta, const st_tree *tb, const int
 // enumeration (MuchTree.pyx:2919-2925), reduced in registers / shuffles / one partial
 // per CTA.  This is the inner loop of the reference's per-clade correlation scan
 // (docs/examples/SuchLinkedTree_examples.md:299-310).  Shardable by k-range.
-template <int MA, int MB>
+template <int MA, int MB, bool J = false>
 __global__ void __launch_bounds__(MLT)
-k_linked_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ links, int64_t first,
+k_linked_moments(const TreeView ta, const TreeView tb, const void *__restrict__ links_v, JoinBits jb, int64_t first,
                  int64_t n, double x0, double y0, double *__restrict__ partials /* [grid][5] */) {
+    const int2 *__restrict__ links = static_cast<const int2 *>(links_v);
+    const LinkRec *__restrict__ joined = static_cast<const LinkRec *>(links_v);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t tables_bar[2];
     const int offs = (st_table_bytes(ta.n_blocks, ta.st_levels, st_table_mode(ta)) + 15) & ~15;
@@ -689,16 +809,28 @@ k_linked_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ 
     int64_t row = -1;  // the row (link i) whose records are cached below
     int2 l2 = make_int2(0, 0);
     RecFull ra{0.0, 0u, 0u}, rb{0.0, 0u, 0u};
+    LinkRec ri{0.0, 0.0, 0ull, 0ull};
     for (; q < wend; q += 32, tri_advance(i, j, 32)) {
-        if (i != row) {
-            row = i;
-            l2 = __ldg(links + i);
-            if (MA == 1) ra = st_ld_rec_full(ta, l2.y);
-            if (MB == 1) rb = st_ld_rec_full(tb, l2.x);
+        double x, y;
+        if constexpr (J) {
+            if (i != row) {
+                row = i;
+                ri = st_ld_linkrec(joined + i);
+            }
+            const LinkRec rj = st_ld_linkrec(joined + j);  // lanes adjacent in j: contiguous records
+            x = joined_query(ta, sa, ri.rd_a, ri.pk_a, rj.rd_a, rj.pk_a, jb.ib_a, jb.kb_a) - x0;
+            y = joined_query(tb, sb, ri.rd_b, ri.pk_b, rj.rd_b, rj.pk_b, jb.ib_b, jb.kb_b) - y0;
+        } else {
+            if (i != row) {
+                row = i;
+                l2 = __ldg(links + i);
+                if (MA == 1) ra = st_ld_rec_full(ta, l2.y);
+                if (MB == 1) rb = st_ld_rec_full(tb, l2.x);
+            }
+            const int2 l1 = __ldg(links + j);
+            x = linked_query_row<MA>(ta, sa, l2.y, ra, l1.y) - x0;
+            y = linked_query_row<MB>(tb, sb, l2.x, rb, l1.x) - y0;
         }
-        const int2 l1 = __ldg(links + j);
-        const double x = linked_query_row<MA>(ta, sa, l2.y, ra, l1.y) - x0;
-        const double y = linked_query_row<MB>(tb, sb, l2.x, rb, l1.x) - y0;
         m.sx += x; m.sy += y;
         m.sxx += x * x; m.syy += y * y; m.sxy += x * y;
     }
@@ -748,9 +880,16 @@ extern "C" int st_links_linked_moments(const st_links *k, int64_t first_pair, in
 #define ST_LAUNCH_LINKED(MA, MB)                                                                 \
     rc_launch = st_raise_smem(k_linked_moments<MA, MB>, ta->device, smem);                       \
     if (rc_launch == ST_OK)                                                                      \
-        k_linked_moments<MA, MB><<<grid, MLT, smem, s>>>(ta->view, tb->view, k->rows, first_pair, \
+        k_linked_moments<MA, MB><<<grid, MLT, smem, s>>>(ta->view, tb->view, k->rows, k->jb, first_pair, \
                                                          n_pairs, x0, y0, d_part)
-    ST_DISPATCH_MODES(tree_mode(ta), tree_mode(tb), ST_LAUNCH_LINKED);
+    if (k->joined && joined_enabled()) {
+        rc_launch = st_raise_smem(k_linked_moments<1, 1, true>, ta->device, smem);
+        if (rc_launch == ST_OK)
+            k_linked_moments<1, 1, true><<<grid, MLT, smem, s>>>(ta->view, tb->view, k->joined, k->jb, first_pair,
+                                                                 n_pairs, x0, y0, d_part);
+    } else {
+        ST_DISPATCH_MODES(tree_mode(ta), tree_mode(tb), ST_LAUNCH_LINKED);
+    }
 #undef ST_LAUNCH_LINKED
     if (rc_launch != ST_OK) {  // the kernel was not launched: no result to report
         cudaFreeAsync(d_part, s);
@@ -919,9 +1058,9 @@ __global__ void k_clade_shift(const TreeView ta, const TreeView tb, const int2 *
                             linked_query<2>(tb, st_global_tables(tb), l1.x, l2.x));
 }
 
-template <int MA, int MB>
+template <int MA, int MB, bool J = false>
 __global__ void __launch_bounds__(MLT)
-k_clade_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ links,
+k_clade_moments(const TreeView ta, const TreeView tb, const void *__restrict__ links_v, JoinBits jb,
                 const int32_t *__restrict__ run_begin, const double2 *__restrict__ shift,
                 const CladeItem *__restrict__ items, int32_t n_items, int32_t *__restrict__ next_item,
                 double *__restrict__ partials /* [n_items][5] */) {
@@ -942,7 +1081,9 @@ k_clade_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ l
         const int4 raw = __ldg(reinterpret_cast<const int4 *>(items + it));
         const int64_t first = (int64_t)((uint64_t(uint32_t(raw.y)) << 32) | uint32_t(raw.x));
         const int32_t clade = raw.z, len = raw.w;
-        const int2 *__restrict__ run = links + __ldg(run_begin + clade);
+        const int32_t rb0 = __ldg(run_begin + clade);
+        const int2 *__restrict__ run = static_cast<const int2 *>(links_v) + rb0;
+        const LinkRec *__restrict__ jrun = static_cast<const LinkRec *>(links_v) + rb0;
         const double2 sh = __ldg(shift + clade);
         Mom5 m{0, 0, 0, 0, 0};
         int32_t i = 1, j = 0;  // link indices inside the run (n_links < 2^31)
@@ -955,17 +1096,30 @@ k_clade_moments(const TreeView ta, const TreeView tb, const int2 *__restrict__ l
         int32_t row = -1;  // the row (link i of the run) whose records are cached below
         int2 l2 = make_int2(0, 0);
         RecFull ra{0.0, 0u, 0u}, rb{0.0, 0u, 0u};
+        LinkRec ri{0.0, 0.0, 0ull, 0ull};
         for (int32_t q = lane; q < len; q += 32) {
-            if (i != row) {
-                row = i;
-                l2 = __ldg(run + i);
-                if (MA == 1) ra = st_ld_rec_full(ta, l2.y);
-                if (MB == 1) rb = st_ld_rec_full(tb, l2.x);
+            double x, y;
+            if constexpr (J) {
+                if (i != row) {
+                    row = i;
+                    ri = st_ld_linkrec(jrun + i);
+                }
+                const LinkRec rj = st_ld_linkrec(jrun + j);  // lanes adjacent in j: contiguous records
+                for (j += 32; j >= i; ++i) j -= i;  // 32 positions on in the (i, j<i) enumeration
+                x = joined_query(ta, sa, ri.rd_a, ri.pk_a, rj.rd_a, rj.pk_a, jb.ib_a, jb.kb_a) - sh.x;
+                y = joined_query(tb, sb, ri.rd_b, ri.pk_b, rj.rd_b, rj.pk_b, jb.ib_b, jb.kb_b) - sh.y;
+            } else {
+                if (i != row) {
+                    row = i;
+                    l2 = __ldg(run + i);
+                    if (MA == 1) ra = st_ld_rec_full(ta, l2.y);
+                    if (MB == 1) rb = st_ld_rec_full(tb, l2.x);
+                }
+                const int2 l1 = __ldg(run + j);
+                for (j += 32; j >= i; ++i) j -= i;  // 32 positions on in the (i, j<i) enumeration
+                x = linked_query_row<MA>(ta, sa, l2.y, ra, l1.y) - sh.x;
+                y = linked_query_row<MB>(tb, sb, l2.x, rb, l1.x) - sh.y;
             }
-            const int2 l1 = __ldg(run + j);
-            for (j += 32; j >= i; ++i) j -= i;  // 32 positions on in the (i, j<i) enumeration
-            const double x = linked_query_row<MA>(ta, sa, l2.y, ra, l1.y) - sh.x;
-            const double y = linked_query_row<MB>(tb, sb, l2.x, rb, l1.x) - sh.y;
             m.sx += x; m.sy += y;
             m.sxx += x * x; m.syy += y * y; m.sxy += x * y;
         }
@@ -1036,6 +1190,14 @@ static int ensure_scan_index(const st_links *k, int side) {
         cudaFree(d_rows);
         cudaFree(d_first);
         return ST_ERR_CUDA;
+    }
+    if (k->joined) {  // the same records in the sorted order (a clade's links are then contiguous records)
+        const int rc = build_joined(k, d_rows, L, &k->joined_sorted[side]);
+        if (rc != ST_OK) {
+            cudaFree(d_rows);
+            cudaFree(d_first);
+            return rc;
+        }
     }
     k->first[side] = d_first;
     k->rows_sorted[side] = d_rows;
@@ -1145,9 +1307,16 @@ extern "C" int st_links_clade_moments(const st_links *k, int side, const int64_t
 #define ST_LAUNCH_CLADE(MA, MB)                                                                          \
     rc2 = st_raise_smem(k_clade_moments<MA, MB>, ta->device, smem);                                      \
     if (rc2 == ST_OK)                                                                                    \
-        k_clade_moments<MA, MB><<<grid, MLT, smem, s>>>(ta->view, tb->view, rows, d_run, d_shift, d_items, \
+        k_clade_moments<MA, MB><<<grid, MLT, smem, s>>>(ta->view, tb->view, rows, k->jb, d_run, d_shift, d_items, \
                                                         n_items, d_next, d_part)
-        ST_DISPATCH_MODES(tree_mode(ta), tree_mode(tb), ST_LAUNCH_CLADE);
+        if (k->joined_sorted[side] && joined_enabled()) {
+            rc2 = st_raise_smem(k_clade_moments<1, 1, true>, ta->device, smem);
+            if (rc2 == ST_OK)
+                k_clade_moments<1, 1, true><<<grid, MLT, smem, s>>>(ta->view, tb->view, k->joined_sorted[side], k->jb,
+                                                                    d_run, d_shift, d_items, n_items, d_next, d_part);
+        } else {
+            ST_DISPATCH_MODES(tree_mode(ta), tree_mode(tb), ST_LAUNCH_CLADE);
+        }
 #undef ST_LAUNCH_CLADE
         if (rc2 != ST_OK) return fail(rc2);
     }

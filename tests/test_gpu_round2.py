@@ -609,3 +609,64 @@ def test_by_name_entry_points_same_through_c_glue_and_python_walk():
     with pytest.raises(TypeError):
         T.distances_by_name(pairs[:10] + [(names[0], 3)])
     assert T.distances_by_name([[names[0], names[1]]]) == T.distances_by_name([(names[0], names[1])])
+
+
+# ------------------------------------------------------------ joined link records -----------
+def _moments(m):
+    return (m.n, m.sx, m.sy, m.sxx, m.syy, m.sxy)
+
+
+def test_joined_link_records_give_the_same_bits_as_separate_rows():
+    """The handle's one-sector-per-link records (both trees' root distances and block keys, compact
+    layouts only) feed the Philox sampler, the exhaustive moments and the clade scan; every sum must
+    equal the separate-rows path bit for bit, and both must agree with the oracle's distances
+    (MuchTree.pyx:2900-2934 pair order; :62-79 moments)."""
+    n = 3000
+    fa, fb = synth.yule_tree(n, seed=31), synth.yule_tree(n, seed=32)
+    A, B = SuchTree.from_flat(fa), SuchTree.from_flat(fb)
+    rng = np.random.default_rng(33)
+    L = 700
+    ll = np.stack([2 * rng.integers(0, n, L), 2 * rng.integers(0, n, L)], axis=1).astype(np.int64)
+    got = {}
+    for mode in ("0", "1"):
+        os.environ["SUCHTREE_B200_JOINED"] = mode
+        try:
+            S = SuchLinkedTrees.from_linklist(A, B, ll)
+            got[mode] = (_moments(S.sample_moments(200001, seed=5, first_sample=3, x0=1.0, y0=2.0)),
+                         _moments(S.linked_moments(17, 200000, x0=1.0, y0=2.0)),
+                         S.clade_pearson(min_links=3, max_links=400))
+        finally:
+            del os.environ["SUCHTREE_B200_JOINED"]
+    assert got["0"][0] == got["1"][0] and got["0"][1] == got["1"][1]
+    for key in ("r", "n_pairs", "n_links"):
+        assert np.array_equal(got["0"][2][key], got["1"][2][key], equal_nan=True), key
+    # against the oracle: exhaustive moments over the first pairs of the enumeration
+    S = SuchLinkedTrees.from_linklist(A, B, ll)
+    oa, ob = O.OracleTree(fa.parent, fa.distance), O.OracleTree(fb.parent, fb.distance)
+    lk = S.linklist
+    i, j = np.array([(i, j) for i in range(1, 60) for j in range(i)]).T
+    da = oa.distances_f64(np.stack([lk[j, 1], lk[i, 1]], axis=1))
+    db = ob.distances_f64(np.stack([lk[j, 0], lk[i, 0]], axis=1))
+    m = S.linked_moments(0, len(i))
+    assert m.n == len(i)
+    assert abs(m.sx - da.sum()) <= 1e-9 * da.sum() and abs(m.sxy - (da * db).sum()) <= 1e-9 * (da * db).sum()
+
+
+def test_joined_link_records_fall_back_when_a_tree_does_not_fit():
+    """A caterpillar's block keys (depth up to 10^5) do not fit the packed word: the handle keeps
+    separate rows, and the results are those of the generic path."""
+    fa, fb = synth.caterpillar_tree(40000, seed=1), synth.yule_tree(40000, seed=2)
+    A, B = SuchTree.from_flat(fa), SuchTree.from_flat(fb)
+    rng = np.random.default_rng(3)
+    ll = np.stack([2 * rng.integers(0, 40000, 500), 2 * rng.integers(0, 40000, 500)], axis=1).astype(np.int64)
+    S = SuchLinkedTrees.from_linklist(A, B, ll)
+    m1 = _moments(S.sample_moments(50000, seed=1))
+    os.environ["SUCHTREE_B200_JOINED"] = "0"
+    try:
+        m0 = _moments(SuchLinkedTrees.from_linklist(A, B, ll).sample_moments(50000, seed=1))
+    finally:
+        del os.environ["SUCHTREE_B200_JOINED"]
+    assert m0 == m1
+    d = S.linked_distances()
+    oa = O.OracleTree(fa.parent, fa.distance)
+    assert np.array_equal(d["TreeA"][:2000], oa.distances_f64(d["ids_A"][:2000]))
