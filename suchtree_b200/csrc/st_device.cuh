@@ -48,6 +48,18 @@ __device__ __forceinline__ double st_patristic(dd ra, dd rb, dd rm) {
     dd r = dd_add(s, m2);
     return r.hi;  // normalised: hi = fl(hi + lo)
 }
+// The same value for operands whose low words are zero (compact layout: every root distance is
+// exact in fp64): st_patristic() with the additions of +0.0 and the renormalisations of already
+// normalised pairs taken out -- 18 fp64 operations instead of 42, the same bits (x + 0.0 = x for
+// every x but -0.0, which can only arise where the result is 0).  The linked-tree moment kernels
+// are issue-bound on exactly these operations (profiles/r02_summary.md).
+__device__ __forceinline__ double st_patristic_c(double ra, double rb, double rm) {
+    const dd s = dd_two_sum(ra, rb);           // dd_add(ra, rb): exact, already normalised
+    const dd t = dd_two_sum(s.hi, -2.0 * rm);  // dd_add(s, -2 rm): high words ...
+    const double lo = __dadd_rn(t.lo, s.lo);   // ... low words (the second operand's is zero)
+    const dd u = dd_fast_two_sum(t.hi, lo);
+    return __dadd_rn(u.hi, u.lo);              // the last renormalisation's high word
+}
 // one-add variant for pre-combined operands (matrix writer): fl(x + y)
 __device__ __forceinline__ double dd_add_to_double(dd x, dd y) {
     dd s = dd_two_sum(x.hi, y.hi);
@@ -336,7 +348,7 @@ __device__ __forceinline__ void st_pair_c(const TreeView &tv, const SmemTables &
             rm = id == q.lo ? l.rd : (id == q.hi ? h.rd : __ldg(&tv.rec16[id].rd));
         }
     }
-    if (want_d) d = st_patristic(dd{l.rd, 0.0}, dd{h.rd, 0.0}, dd{rm, 0.0});
+    if (want_d) d = st_patristic_c(l.rd, h.rd, rm);
     if (want_m) m = id;
 }
 

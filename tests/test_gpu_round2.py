@@ -670,3 +670,51 @@ def test_joined_link_records_fall_back_when_a_tree_does_not_fit():
     d = S.linked_distances()
     oa = O.OracleTree(fa.parent, fa.distance)
     assert np.array_equal(d["TreeA"][:2000], oa.distances_f64(d["ids_A"][:2000]))
+
+
+# ----------------------------------------- compact arithmetic where rounding happens --------
+def test_compact_distance_arithmetic_rounds_once_on_inexact_sums():
+    """Edges 16 or 2^k, k in [-46, -40], depth 8: every root distance is exact in fp64 (compact
+    layout), but rd[a] + rd[b] - 2 rd[mrca] needs up to 55 bits (about one pair in six).  The lean kernels (st_patristic_c: the
+    double-double sum with its no-op steps removed), the generic kernel (full double-double) and
+    the joined-record linked path must all return the correctly rounded value of the exact sum."""
+    ft = synth.balanced_tree(256, seed=5)
+    rng = np.random.default_rng(6)
+    k = np.where(rng.random(ft.size) < 0.5, 4, rng.integers(-46, -39, size=ft.size))
+    ft.distance = np.ldexp(1.0, k).astype(np.float32)
+    ft.distance[ft.root] = -1.0
+    T = SuchTree.from_flat(ft)
+    assert T.index_info["layout"] == 1
+    unit = 46
+    units = [0] * ft.size  # exact root distances in units of 2^-46
+    depth_first = list(T.traverse_preorder())
+    for v in depth_first:
+        p = int(ft.parent[v])
+        units[v] = 0 if p == -1 else units[p] + (1 << (int(k[v]) + unit))
+    p = rng.integers(0, ft.size, size=(200_000, 2)).astype(np.int64)
+    m = T.common_ancestors_bulk(p)
+    exact = [units[a] + units[b] - 2 * units[c] for (a, b), c in zip(p.tolist(), m.tolist())]
+    inexact = sum(1 for d in exact if d and d.bit_length() - ((d & -d).bit_length() - 1) > 53)
+    assert inexact > 10000  # the case under test does occur
+    want = np.array([d / float(1 << unit) for d in exact])  # int / float: correctly rounded
+    for paired, lean in (("1", "1"), ("0", "1"), ("0", "0")):
+        d = _with_env("SUCHTREE_B200_PAIRED", paired, lambda: _with_env("SUCHTREE_B200_LEAN", lean, lambda: T.distances_bulk(p)))
+        assert np.array_equal(d, want), (paired, lean)
+    W = SuchTree.from_flat(ft, _wide=True)  # 32-byte records, double-double root distances
+    assert np.array_equal(W.distances_bulk(p), want)
+    D = T.pairwise_distances(list(range(0, ft.size, 3)))
+    ids = np.arange(0, ft.size, 3)
+    a, b = np.meshgrid(ids, ids, indexing="ij")
+    assert np.array_equal(D.ravel(), T.distances_bulk(np.stack([a.ravel(), b.ravel()], axis=1)))
+    # linked paths: joined records and separate rows
+    leaves = T.leaf_node_ids
+    ll = np.stack([rng.choice(leaves, 300), rng.choice(leaves, 300)], axis=1).astype(np.int64)
+    for mode in ("0", "1"):
+        S = _with_env("SUCHTREE_B200_JOINED", mode, lambda: SuchLinkedTrees.from_linklist(T, T, ll))
+        res = _with_env("SUCHTREE_B200_JOINED", mode, lambda: S.linked_distances())
+        ia = res["ids_A"]
+        ma = T.common_ancestors_bulk(ia)
+        wa = np.array([(units[x] + units[y] - 2 * units[c]) / float(1 << unit) for (x, y), c in zip(ia.tolist(), ma.tolist())])
+        assert np.array_equal(res["TreeA"], wa)
+        mo = _with_env("SUCHTREE_B200_JOINED", mode, lambda: S.linked_moments())
+        assert abs(mo.sx - wa.sum()) <= 1e-12 * wa.sum()
