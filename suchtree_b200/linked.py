@@ -314,21 +314,29 @@ class SuchLinkedTrees(LinkedExtras):
         sumsq_a = np.zeros(buckets)
         sumsq_b = np.zeros(buckets)
         samples = 0
-        all_a, all_b = [], []
+        # every cycle's distances land directly in the result arrays (page-locked when large: the
+        # D2H copies need no staging); the arrays grow geometrically, the result is a view
+        bn = buckets * n
+        cap = max(1, min(maxcycles, 4))
+        out_a = _lib.result_empty((cap * bn,), np.float64)
+        out_b = _lib.result_empty((cap * bn,), np.float64)
         seed = C.c_uint64(self._seed)
         cycles = 0
         lib = _lib.lib()
         while True:
-            da = np.empty(buckets * n)
-            db = np.empty(buckets * n)
+            if cycles == cap:
+                cap = min(max(maxcycles, cap + 1), 2 * cap)
+                grown_a = _lib.result_empty((cap * bn,), np.float64)
+                grown_b = _lib.result_empty((cap * bn,), np.float64)
+                grown_a[: cycles * bn] = out_a[: cycles * bn]
+                grown_b[: cycles * bn] = out_b[: cycles * bn]
+                out_a, out_b = grown_a, grown_b
             rc = lib.st_links_sample_cycle(
                 links, C.byref(seed), buckets, n,
-                da.ctypes.data, db.ctypes.data, sums_a.ctypes.data, sumsq_a.ctypes.data,
-                sums_b.ctypes.data, sumsq_b.ctypes.data)
+                out_a.ctypes.data + cycles * bn * 8, out_b.ctypes.data + cycles * bn * 8,
+                sums_a.ctypes.data, sumsq_a.ctypes.data, sums_b.ctypes.data, sumsq_b.ctypes.data)
             self._seed = int(seed.value)
             _lib.check(rc)
-            all_a.append(da)
-            all_b.append(db)
             samples += n
             with np.errstate(invalid="ignore"):
                 dev_a = (sumsq_a / samples - (sums_a / samples) ** 2) ** 0.5
@@ -353,8 +361,8 @@ class SuchLinkedTrees(LinkedExtras):
             if cycles >= maxcycles:
                 return None
         return {
-            "TreeA": np.concatenate(all_a),
-            "TreeB": np.concatenate(all_b),
+            "TreeA": out_a[: cycles * bn],
+            "TreeB": out_b[: cycles * bn],
             "n_pairs": (L * (L - 1)) / 2,
             "n_samples": n * buckets * cycles,
             "deviation_a": float(deviation_a),
