@@ -16,6 +16,7 @@
 
 #include "st_device.cuh"
 #include "st_hostctx.cuh"
+#include "st_hostpool.cuh"
 
 static const int LT = 256;
 
@@ -598,8 +599,19 @@ extern "C" int st_links_sample_cycle(const st_links *k, uint64_t *seed, int32_t 
     }
     k_bucket_sums<<<dim3(unsigned(buckets), 2), 256, 0, s>>>(d_out, n, buckets, d_stats);
     std::vector<double> stats(size_t(buckets) * 4);
-    cudaMemcpyAsync(out_a, d_out, size_t(total) * 8, cudaMemcpyDeviceToHost, s);
-    cudaMemcpyAsync(out_b, d_out + total, size_t(total) * 8, cudaMemcpyDeviceToHost, s);
+    // pageable result arrays (the Python shim's): one D2H of both vectors into the lane's page-locked
+    // staging, then a parallel copy out -- a pageable cudaMemcpy of 2 x 2 MB per cycle is what the
+    // cycle used to spend most of its time in
+    const bool direct = st_is_pinned(out_a) && st_is_pinned(out_b);
+    double *h_stage = nullptr;
+    if (!direct && 2 * total <= ST_STAGE_PAIRS_MAX && st_lane_ensure_stage(lane, 2 * total, false, true) == ST_OK)
+        h_stage = static_cast<double *>(lane->h_out[0]);
+    if (h_stage) {
+        cudaMemcpyAsync(h_stage, d_out, size_t(total) * 16, cudaMemcpyDeviceToHost, s);
+    } else {
+        cudaMemcpyAsync(out_a, d_out, size_t(total) * 8, cudaMemcpyDeviceToHost, s);
+        cudaMemcpyAsync(out_b, d_out + total, size_t(total) * 8, cudaMemcpyDeviceToHost, s);
+    }
     cudaMemcpyAsync(stats.data(), d_stats, stats.size() * 8, cudaMemcpyDeviceToHost, s);
     cleanup();
     cudaError_t e = cudaStreamSynchronize(s);
@@ -607,6 +619,10 @@ extern "C" int st_links_sample_cycle(const st_links *k, uint64_t *seed, int32_t 
     if (e != cudaSuccess) {
         st_set_error("st_sample_linked_cycle: %s", cudaGetErrorString(e));
         return ST_ERR_CUDA;
+    }
+    if (h_stage) {
+        st_parallel_copy(out_a, h_stage, size_t(total) * 8);
+        st_parallel_copy(out_b, h_stage + total, size_t(total) * 8);
     }
     for (int i = 0; i < buckets; ++i) {  // stats: [TreeA sum | TreeA sumsq | TreeB sum | TreeB sumsq][buckets]
         sums_a[i] += stats[i];

@@ -314,20 +314,23 @@ class SuchLinkedTrees(LinkedExtras):
         sumsq_a = np.zeros(buckets)
         sumsq_b = np.zeros(buckets)
         samples = 0
-        # every cycle's distances land directly in the result arrays (page-locked when large: the
-        # D2H copies need no staging); the arrays grow geometrically, the result is a view
+        # every cycle's distances land directly in the result arrays (the library stages the D2H
+        # copies through its lane's page-locked buffer).  As the reference does (:2990-2995), room
+        # for maxcycles cycles is reserved up front -- np.empty touches no pages, so only the cycles
+        # that run cost memory -- up to 1 GiB per array; beyond that the arrays grow geometrically.
+        # The result is a view of the first `cycles` cycles.
         bn = buckets * n
-        cap = max(1, min(maxcycles, 4))
-        out_a = _lib.result_empty((cap * bn,), np.float64)
-        out_b = _lib.result_empty((cap * bn,), np.float64)
+        cap = max(1, min(maxcycles, (1 << 27) // max(bn, 1)))
+        out_a = np.empty(cap * bn)
+        out_b = np.empty(cap * bn)
         seed = C.c_uint64(self._seed)
         cycles = 0
         lib = _lib.lib()
         while True:
             if cycles == cap:
                 cap = min(max(maxcycles, cap + 1), 2 * cap)
-                grown_a = _lib.result_empty((cap * bn,), np.float64)
-                grown_b = _lib.result_empty((cap * bn,), np.float64)
+                grown_a = np.empty(cap * bn)
+                grown_b = np.empty(cap * bn)
                 grown_a[: cycles * bn] = out_a[: cycles * bn]
                 grown_b[: cycles * bn] = out_b[: cycles * bn]
                 out_a, out_b = grown_a, grown_b
