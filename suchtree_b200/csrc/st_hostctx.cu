@@ -39,27 +39,7 @@ struct Joiner {
     }
 } g_joiner;
 
-// The entry points take their per-call device scratch from the device's stream-ordered pool
-// (cudaMallocAsync).  By default that pool hands everything unused back to the driver at every
-// synchronisation, so a loop of calls re-maps its scratch each time (measured: 2.7 ms per cycle of
-// sample_linked_distances, of which the kernels are 0.1 ms).  Keep up to 1 GiB cached
-// (SUCHTREE_B200_POOL_KEEP_MB overrides; 0 restores the default).
-void keep_pool_memory(int device) {
-    static std::mutex mu;
-    static bool done[ST_MAX_DEVICES] = {false};
-    std::lock_guard<std::mutex> l(mu);
-    if (done[device]) return;
-    done[device] = true;
-    uint64_t keep = uint64_t(1) << 30;
-    if (const char *e = getenv("SUCHTREE_B200_POOL_KEEP_MB")) keep = uint64_t(atoll(e)) << 20;
-    cudaMemPool_t pool = nullptr;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) != cudaSuccess ||
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess)
-        cudaGetLastError();  // an optimisation only
-}
-
 int lane_create(int device, HostLane **out) {
-    keep_pool_memory(device);
     HostLane *l = new HostLane();
     l->device = device;
     for (int i = 0; i < ST_LANE_SLOTS; ++i) {
