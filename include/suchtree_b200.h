@@ -261,6 +261,14 @@ ST_API int st_pearson(int device, const double *x, const double *y, int64_t n, d
  * id pairs into int32 pinned staging -- the host stage of st_distances(). */
 ST_API int st_bench_pack(int64_t n_pairs, int iters, double *pairs_per_s);
 
+/* ---- the host stage of st_distances() / st_mrca() on its own (tests, measurements; no device):
+ * packs n (a, b) int64 pairs (element strides as in st_distances) into the bit stream the pair
+ * kernel reads -- pair i in bits [i * 2w, (i + 1) * 2w), a in the low w = id_bits bits, b above --
+ * with the host thread pool.  out: ceil(n * 2w / 64) + 1 words.  *or_of_ids = OR of every id seen
+ * (a bit at or above w set <=> some id is negative or >= 2^w). */
+ST_API int st_host_pack_pairs(const int64_t *pairs, int64_t stride0, int64_t stride1, int64_t n, int id_bits,
+                       uint64_t *out, uint64_t *or_of_ids);
+
 /* ---- measurement helper: what the host interface can carry -- `iters` rounds of an H2D copy
  * of h2d_bytes and a concurrent D2H copy of d2h_bytes between pinned host memory and the
  * device, in chunks of chunk_bytes (<= 0: 64 MiB) on two streams; *seconds = wall time per

@@ -17,6 +17,9 @@ int st_host_threads();  // parts worth using for bandwidth-bound loops
 // (2: pairs, 4: quartets), rows strided by s0, columns by s1 (elements).  Returns the OR of
 // everything seen: any bit >= 31 set <=> some id is negative or >= 2^31.
 uint64_t st_pack_ids(const int64_t *src, int64_t s0, int64_t s1, int64_t rows, int32_t *dst, int width);
+// int64 pairs -> the bit-packed pair stream of the pair kernel (2w bits per pair, a low, b high);
+// returns the OR of all ids seen; dst: ceil(rows * 2w / 64) + 1 words
+uint64_t st_pack_pairs_bits(const int64_t *src, int64_t s0, int64_t s1, int64_t rows, uint64_t *dst, int w);
 void st_parallel_copy(void *dst, const void *src, size_t bytes);
 // the reference's report for an out-of-range array (MuchTree.pyx:897-903): max id if it is
 // >= n_nodes, else min id -> st_bad_node() / st_last_error()

@@ -652,6 +652,7 @@ extern "C" int st_tree_create_ex(int device, int64_t n_nodes, const int32_t *par
     t->view.mst = t->d_mst;
     t->view.status = t->d_status;
     t->view.n_nodes = n;
+    t->view.id_bits = std::max(1, st_ceil_log2_i64(n));
     t->view.n_blocks = t->n_blocks;
     t->view.n_micro = t->n_micro;
     t->view.block_shift = bs;

@@ -92,6 +92,7 @@ struct TreeView {
     int32_t compact;         // 1: rec16 (16-byte records) is the live node array
     int32_t compact_tables;  // 1: stk32 / bid (+ brd8, or brd with wide records) are the live block tables
     int32_t table_shift;     // compact block-table keys: depth << table_shift | block
+    int32_t id_bits;         // ceil(log2(n_nodes)), >= 1: width of one id in the bit-packed pair stream (st_query.cu)
 };
 
 struct st_tree {
@@ -129,6 +130,7 @@ struct st_tree {
 // query kernels (st_query.cu)
 // status = NULL: the tree's own word (device API, read by st_check_range); host calls pass
 // their lane's word
+static const int ST_IDX_PACKED = -2;  // idx_bits value: the bit-packed pair stream (internal: host pipeline only)
 int st_launch_pairs(const st_tree *t, const void *d_pairs, int idx_bits, int64_t n, double *d_out,
                     int32_t *d_mrca, cudaStream_t stream, RangeStatus *status = nullptr);
 int st_read_range_status(const st_tree *t, cudaStream_t stream, bool *bad);

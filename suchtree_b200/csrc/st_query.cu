@@ -17,6 +17,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 #include "st_device.cuh"
 #ifndef ST_LEAN_DEFAULT
@@ -67,6 +68,24 @@ __device__ __forceinline__ void st_decode_pair(const RawPairs<IdxT, P> &r, int k
         a = (long long)r.w[2 * k];
         b = (long long)r.w[2 * k + 1];
     }
+}
+
+// Bit-packed pair stream of the host pipeline (st_pack_pairs_bits): pair i = bits [i * 2w, (i+1) * 2w)
+// of a little-endian bit stream, w = tv.id_bits; a in the low w bits, b above it.  Three aligned
+// 32-bit words cover any pair (2w <= 62, bit offset in the first word <= 31); neighbouring lanes
+// read overlapping words, which L1 serves.  The buffer has one spare 64-bit word at its end.
+struct StPackedPairs {};
+__device__ __forceinline__ void st_load_pair_packed(const uint32_t *__restrict__ base, int64_t i, int w,
+                                                    long long &a, long long &b) {
+    const uint64_t off = uint64_t(i) * uint64_t(2 * w);
+    const uint32_t *p = base + (off >> 5);
+    const int sh = int(off & 31);
+    const uint32_t x0 = __ldg(p), x1 = __ldg(p + 1), x2 = __ldg(p + 2);
+    const uint64_t lo = uint64_t(x0) | (uint64_t(x1) << 32);
+    const uint64_t v = (lo >> sh) | (sh ? (uint64_t(x2) << (64 - sh)) : 0ull);
+    const uint64_t m = (uint64_t(1) << w) - 1;
+    a = (long long)(v & m);
+    b = (long long)((v >> w) & m);
 }
 
 // range check as SuchTree.distances_bulk does before the kernel (MuchTree.pyx:897-903),
@@ -124,13 +143,22 @@ k_pairs(const TreeView tv, const IdxT *__restrict__ pairs, int64_t n, double *__
     // (prefetching the next iteration's ids, and 4 pairs per thread, were both measured
     //  and are no faster: profiles/r01_summary.md)
     for (; i < groups; i += stride) {
-        const RawPairs<IdxT, P> cur = st_load_pairs<IdxT, P>(pairs, P * i);
         PairQ q[P];
+        if constexpr (std::is_same<IdxT, StPackedPairs>::value) {
 #pragma unroll
-        for (int k = 0; k < P; ++k) {
-            long long a, b;
-            st_decode_pair<IdxT, P>(cur, k, a, b);
-            q[k] = st_make_query(tv, a, b);
+            for (int k = 0; k < P; ++k) {
+                long long a, b;
+                st_load_pair_packed(reinterpret_cast<const uint32_t *>(pairs), P * i + k, tv.id_bits, a, b);
+                q[k] = st_make_query(tv, a, b);
+            }
+        } else {
+            const RawPairs<IdxT, P> cur = st_load_pairs<IdxT, P>(pairs, P * i);
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                long long a, b;
+                st_decode_pair<IdxT, P>(cur, k, a, b);
+                q[k] = st_make_query(tv, a, b);
+            }
         }
         if constexpr (PR >= 2) {  // lean compact path (PR = 3: with the sector neighbours)
             constexpr bool NB = PR == 3;
@@ -198,7 +226,10 @@ k_pairs(const TreeView tv, const IdxT *__restrict__ pairs, int64_t n, double *__
     if (P > 1 && t < n - groups * P) {
         const int64_t i = groups * P + t;
         long long a, b;
-        st_decode_pair<IdxT, 1>(st_load_pairs<IdxT, 1>(pairs, i), 0, a, b);
+        if constexpr (std::is_same<IdxT, StPackedPairs>::value)
+            st_load_pair_packed(reinterpret_cast<const uint32_t *>(pairs), i, tv.id_bits, a, b);
+        else
+            st_decode_pair<IdxT, 1>(st_load_pairs<IdxT, 1>(pairs, i), 0, a, b);
         const PairQ q = st_make_query(tv, a, b);
         const RecRaw l = st_ld_rec<M>(tv, q.lo), h = st_ld_rec<M>(tv, q.hi);
         double d = 0.0;
@@ -287,6 +318,12 @@ static int st_pairs_per_thread() {  // SUCHTREE_B200_PPT = 1 | 2 | 4 (read per l
 int st_launch_pairs(const st_tree *t, const void *d_pairs, int idx_bits, int64_t n, double *d_out,
                     int32_t *d_mrca, cudaStream_t stream, RangeStatus *status) {
     if (n == 0) return ST_OK;
+    if (idx_bits == ST_IDX_PACKED) {  // the host pipeline's bit-packed stream (2 x tv.id_bits per pair, 4-byte aligned)
+        const bool ok16 = (!d_out || reinterpret_cast<uintptr_t>(d_out) % 16 == 0) &&
+                          (!d_mrca || reinterpret_cast<uintptr_t>(d_mrca) % 8 == 0);
+        if (ok16) return launch_variant<StPackedPairs, 2>(t, d_pairs, n, d_out, d_mrca, stream, status);
+        return launch_variant<StPackedPairs, 1>(t, d_pairs, n, d_out, d_mrca, stream, status);
+    }
     if (idx_bits != 32 && idx_bits != 64) {
         st_set_error("idx_bits must be 32 or 64 (got %d)", idx_bits);
         return ST_ERR_INVALID_ARG;
@@ -334,6 +371,10 @@ extern "C" int st_distances_device(const st_tree *t, const void *d_pairs, int id
                                    double *d_out, int32_t *d_mrca, void *stream) {
     if (!t || n < 0 || (n > 0 && !d_pairs) || (!d_out && !d_mrca && n > 0)) {
         st_set_error("st_distances_device: bad arguments");
+        return ST_ERR_INVALID_ARG;
+    }
+    if (idx_bits != 32 && idx_bits != 64) {
+        st_set_error("idx_bits must be 32 or 64 (got %d)", idx_bits);
         return ST_ERR_INVALID_ARG;
     }
     DeviceGuard g(t->device);
@@ -400,8 +441,10 @@ extern "C" int st_random_leaf_pairs_device(const st_tree *t, uint64_t seed, int6
 // Chunked 3-slot pipeline on a LANE of the device's host context (st_hostctx.cuh):
 // pack(chunk c+1) on the host pool | H2D + kernel + D2H of chunk c on one of the lane's
 // three streams | copy-out(chunk c-2).  The caller's int64 ids (the drop-in dtype, any
-// strides, pageable or pinned) are packed to int32 into pinned staging by the host
-// thread pool: half the PCIe bytes (8 instead of 16 per pair).  Results go straight to
+// strides, pageable or pinned) are BIT-PACKED into pinned staging by the host thread pool:
+// 2 x ceil(log2(n_nodes)) bits per pair (4.5 bytes for a 100k-leaf tree instead of 16), which
+// the pair kernel decodes itself (StPackedPairs).  What bounds the call on one GPU is the host's
+// memory system, and the staging write + DMA read is the part of that traffic the width decides.  Results go straight to
 // the caller's buffer when it is page-locked (the Python shim's result arrays come from
 // the pinned pool, st_host_alloc), else through pinned staging + a parallel copy.
 // A pinned (or registered) contiguous input is partly DMA'd as it is and read by the
@@ -498,12 +541,15 @@ static int host_pairs_run(const st_tree *t, const int64_t *pairs, int64_t s0, in
         if (e[0] == 'd' && in_pinned) pack = false;  // "direct"
         if (e[0] == 'p') pack = true;                // "pack"
     }
-    // hybrid: PCIe wants the ids packed (8 instead of 16 B/pair), host memory bandwidth
-    // wants them left alone (packing costs 24 B/pair of host traffic on top of the DMA's):
-    // pack a fraction of every chunk and ship the rest as int64.  With several ranks on one host (one process per GPU) the
-    // host memory system is the shared bottleneck and plain DMA wins: measured on an
-    // 8-GPU box, N = 8: 6.3e9 (0 %) vs 5.4e9 (45 %) pairs/s; one GPU: 3.2e9 vs 3.8e9.
-    double pack_fraction = 0.45;
+    // hybrid: PCIe wants the ids packed (4.5 instead of 16 B/pair for a 100k-leaf tree), host memory
+    // bandwidth wants them left alone (packing costs a CPU read of the ids plus the staging write and
+    // its DMA read on top of what the DMA of the results moves): pack a fraction of every chunk and
+    // ship the rest as int64.  One GPU, 1e8 pairs, fraction 0 / 0.3 / 0.45 / 0.6 / 0.8 / 1:
+    // 3.14 / 3.91 / 4.36 / 4.76 / 4.48 / 3.96e9 pairs/s (profiles/r02_packfrac_bits.json; with the
+    // int32 packing of earlier rounds the curve was flat at 3.7-3.8e9).  With several ranks on one
+    // host (one process per GPU) the host memory system is the shared bottleneck and plain DMA wins
+    // (8-GPU box, int32 packing: 6.3e9 at 0 % vs 5.4e9 at 45 %).
+    double pack_fraction = 0.6;
     if (const char *e = getenv("LOCAL_WORLD_SIZE"))
         if (atoi(e) > 1) pack_fraction = 0.0;
     if (const char *e = getenv("SUCHTREE_B200_PACK_FRACTION")) pack_fraction = std::min(1.0, std::max(0.0, atof(e)));
@@ -543,26 +589,30 @@ static int host_pairs_run(const st_tree *t, const int64_t *pairs, int64_t s0, in
         // contiguous input): DMA'd as int64 while the pool packs
         const int64_t mp = pack ? (hybrid ? (int64_t(double(m) * pack_fraction) & ~int64_t(3)) : m) : 0;
         char *d_in = static_cast<char *>(lane->d_in[s]);
+        // packed part: the bit-packed pair stream (2 x id_bits per pair + one spare word); the
+        // unpacked part follows it, 32-byte aligned
+        const int w = t->view.id_bits;
+        const size_t packed_bytes = mp > 0 ? ((size_t(mp) * size_t(2 * w) + 63) / 64 + 1) * 8 : 0;
+        char *d_direct = d_in + ((packed_bytes + 31) & ~size_t(31));
         if (mp < m)
-            ST_CUDA(cudaMemcpyAsync(d_in + size_t(mp) * 8, src + 2 * mp, size_t(m - mp) * 16,
-                                    cudaMemcpyHostToDevice, st));
+            ST_CUDA(cudaMemcpyAsync(d_direct, src + 2 * mp, size_t(m - mp) * 16, cudaMemcpyHostToDevice, st));
         if (mp > 0) {
-            int32_t *hp = static_cast<int32_t *>(lane->h_in[s]);
-            const uint64_t acc = st_pack_ids(src, s0, s1, mp, hp, 2);
-            if (acc >> 31) {  // a negative id, or one beyond int32: cannot be a node of any tree
+            uint64_t *hp = static_cast<uint64_t *>(lane->h_in[s]);
+            const uint64_t acc = st_pack_pairs_bits(src, s0, s1, mp, hp, w);
+            if (acc >> w) {  // a negative id, or one of more than id_bits bits: not a node of this tree
                 quiesce();
                 st_report_range(pairs, s0, s1, n, 2, t->n_nodes);
                 return ST_ERR_NODE_RANGE;
             }
-            ST_CUDA(cudaMemcpyAsync(d_in, hp, size_t(mp) * 8, cudaMemcpyHostToDevice, st));
-            rc = st_launch_pairs(t, d_in, 32, mp, dd_out, dm_out, st, lane->d_status);
+            ST_CUDA(cudaMemcpyAsync(d_in, hp, packed_bytes, cudaMemcpyHostToDevice, st));
+            rc = st_launch_pairs(t, d_in, ST_IDX_PACKED, mp, dd_out, dm_out, st, lane->d_status);
             if (rc != ST_OK) {
                 quiesce();
                 return rc;
             }
         }
         if (mp < m) {
-            rc = st_launch_pairs(t, d_in + size_t(mp) * 8, 64, m - mp, dd_out ? dd_out + mp : nullptr,
+            rc = st_launch_pairs(t, d_direct, 64, m - mp, dd_out ? dd_out + mp : nullptr,
                                  dm_out ? dm_out + mp : nullptr, st, lane->d_status);
             if (rc != ST_OK) {
                 quiesce();
@@ -621,6 +671,17 @@ extern "C" int st_bench_pack(int64_t n_pairs, int iters, double *pairs_per_s) {
     cudaFreeHost(src);
     cudaFreeHost(dst);
     *pairs_per_s = (acc >> 31) ? 0.0 : double(n_pairs) * iters / dt;
+    return ST_OK;
+}
+
+extern "C" int st_host_pack_pairs(const int64_t *pairs, int64_t stride0, int64_t stride1, int64_t n, int id_bits,
+                                  uint64_t *out, uint64_t *or_of_ids) {
+    if (!pairs || !out || n < 0 || id_bits < 1 || id_bits > 31) {
+        st_set_error("st_host_pack_pairs: bad arguments");
+        return ST_ERR_INVALID_ARG;
+    }
+    const uint64_t acc = st_pack_pairs_bits(pairs, stride0, stride1, n, out, id_bits);
+    if (or_of_ids) *or_of_ids = acc;
     return ST_OK;
 }
 

@@ -428,3 +428,35 @@ def test_py_glue_converts_name_rows_and_reports_the_first_bad_row():
         pass
 
     assert g.st_py_names_to_ids([(Name("n1"), "n2")], leaves, out.ctypes.data, 2) == 0  # exact str only
+
+
+# ------------------------------------------------------------- bit-packed pair stream -------
+@pytest.mark.parametrize("w", [1, 2, 7, 17, 18, 21, 31])
+def test_host_packer_writes_the_bit_stream_the_pair_kernel_reads(w):
+    """st_host_pack_pairs (the host stage of st_distances, MuchTree.pyx:872-909 takes int64 pairs):
+    pair i occupies bits [i*2w, (i+1)*2w), a low, b high; any n (word boundaries, parts of the
+    thread pool), any strides; the OR of the ids flags what cannot be a node id."""
+    import ctypes as C
+
+    from suchtree_b200 import _lib
+
+    L = _lib.lib()
+    rng = np.random.default_rng(w)
+    for n in (1, 2, 63, 64, 65, 1000, 32768 * 3 + 17, 400_001):
+        ids = rng.integers(0, 1 << w, size=(n, 2), dtype=np.int64)
+        words = (n * 2 * w + 63) // 64 + 1
+        for arr in (ids, np.asfortranarray(ids), np.ascontiguousarray(ids[:, ::-1])[:, ::-1]):
+            out = np.full(words, 0xDEADBEEFDEADBEEF, dtype=np.uint64)
+            acc = C.c_uint64()
+            rc = L.st_host_pack_pairs(arr.ctypes.data, arr.strides[0] // 8, arr.strides[1] // 8, n, w,
+                                      out.ctypes.data, C.byref(acc))
+            assert rc == 0 and acc.value >> w == 0
+            bits = np.unpackbits(out[:-1].view(np.uint8), bitorder="little")[: n * 2 * w].reshape(n, 2, w)
+            got = (bits.astype(np.int64) << np.arange(w, dtype=np.int64)).sum(axis=2)
+            assert np.array_equal(got, ids), (w, n)
+    bad = np.array([[0, 1], [1 << w, 0]], dtype=np.int64)
+    out = np.zeros(4, dtype=np.uint64)
+    acc = C.c_uint64()
+    assert L.st_host_pack_pairs(bad.ctypes.data, 2, 1, 2, w, out.ctypes.data, C.byref(acc)) == 0 and acc.value >> w
+    bad[1, 0] = -1
+    assert L.st_host_pack_pairs(bad.ctypes.data, 2, 1, 2, w, out.ctypes.data, C.byref(acc)) == 0 and acc.value >> w
