@@ -493,8 +493,21 @@ def run_ours(args):
         "achieved": 24.0 * e2e_value / 1e9, "peak": 24.0 * copy_pairs_per_s / 1e9, "unit": "GB/s",
         "frac": e2e_value / copy_pairs_per_s,
         "peak_pairs_per_s": copy_pairs_per_s, "algorithmic_bytes_per_pair": 24,
-        "note": "frac can exceed 1: the pipeline packs 45 % of the ids to int32 on the host, so fewer bytes "
-                "cross PCIe than the plain copy moves",
+        "note": "frac can exceed 1: the pipeline bit-packs part of every chunk's ids on the host (2 x ceil(log2 "
+                "n_nodes) bits per pair; 70 % of a chunk on one GPU, 20 % with two local ranks, 0 % beyond), so "
+                "fewer bytes cross PCIe than the plain copy moves; `packed_bound` is the same measurement with "
+                "every id packed -- what PCIe alone would allow if packing cost the host nothing",
+    }
+    # the other end of the bracket: H2D of fully bit-packed ids || D2H of the results
+    id_bits = max(1, int(T.size - 1).bit_length())
+    sec2 = C.c_double(0)
+    barrier()
+    rc_copy2 = _lib.lib().st_bench_copy(local, (2 * id_bits * n_e2e + 7) // 8, 8 * n_e2e, 64 << 20, 5, C.byref(sec2))
+    copy2_s = all_max(sec2.value if rc_copy2 == 0 else float("nan"))
+    e2e_roofline["packed_bound"] = {
+        "what": "cudaMemcpyAsync pinned H2D of %.2f B/pair (2 x %d bits) || pinned D2H of 8 B/pair, same chunking and "
+                "ranks" % (2 * id_bits / 8.0, id_bits),
+        "peak_pairs_per_s": world * n_e2e / copy2_s, "frac": e2e_value / (world * n_e2e / copy2_s),
     }
 
     # ---- rooflines (rank 0's kernel; all ranks run the same launch)

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <mutex>
 #include <thread>
+#include <utility>
 #include <vector>
 
 namespace {
@@ -173,18 +174,68 @@ uint64_t st_pack_ids(const int64_t *src, int64_t s0, int64_t s1, int64_t m, int3
 // boundary for every w) and streams whole 64-bit words (movnti).  Returns the OR of all ids: a
 // bit at or above w set <=> some id is negative or >= 2^w (ids in [n_nodes, 2^w) are caught by
 // the kernel).  dst needs room for ceil(m * 2w / 64) + 1 words.
+static inline void st_stream_u64(uint64_t *p, uint64_t v) {
+#if defined(__SSE2__) && defined(__x86_64__)
+    _mm_stream_si64(reinterpret_cast<long long *>(p), (long long)v);
+#else
+    *p = v;
+#endif
+}
+// One group of 64 contiguous pairs = exactly 2W words, every shift a compile-time constant
+// (template recursion instead of a carried fill counter: straight-line code, no branches).
+template <int W, int I>
+struct PackStep {
+    static __attribute__((always_inline)) inline void run(const int64_t *__restrict__ q, uint64_t &acc, uint64_t &seen,
+                                                          uint64_t *__restrict__ &out) {
+        constexpr int B = 2 * W, fill = (I * B) & 63;
+        const uint64_t x = uint64_t(q[2 * I]), y = uint64_t(q[2 * I + 1]);
+        seen |= x | y;
+        const uint64_t v = (x | (y << W)) & ((uint64_t(1) << B) - 1);
+        if constexpr (fill == 0) acc = v;
+        else acc |= v << fill;
+        if constexpr (fill + B >= 64) {
+            st_stream_u64(out++, acc);
+            constexpr int rest = fill + B - 64;  // bits of v that belong to the next word
+            if constexpr (rest > 0) acc = v >> (B - rest);
+            else acc = 0;
+        }
+        if constexpr (I + 1 < 64) PackStep<W, I + 1>::run(q, acc, seen, out);
+    }
+};
+template <int W>
+static uint64_t pack_groups(const int64_t *__restrict__ src, int64_t n_groups, uint64_t *__restrict__ out) {
+    uint64_t seen = 0, acc = 0;
+    for (int64_t g = 0; g < n_groups; ++g, src += 128) PackStep<W, 0>::run(src, acc, seen, out);
+    return seen;
+}
+typedef uint64_t (*PackGroupsFn)(const int64_t *, int64_t, uint64_t *);
+template <int... Ws>
+static const PackGroupsFn *pack_group_table(std::integer_sequence<int, Ws...>) {
+    static const PackGroupsFn table[] = {pack_groups<Ws + 1>...};  // W = 1 .. 31
+    return table;
+}
+
 uint64_t st_pack_pairs_bits(const int64_t *src, int64_t s0, int64_t s1, int64_t m, uint64_t *dst, int w) {
     const int bits = 2 * w;
     const int64_t groups = (m + 63) / 64;
     const int parts = int(std::min<int64_t>(st_host_threads(), m / 32768 + 1));
+    const bool contiguous = (s0 == 2 && s1 == 1);
+    const PackGroupsFn fast = pack_group_table(std::make_integer_sequence<int, 31>())[w - 1];
     std::vector<uint64_t> accs(size_t(parts), 0);
     st_parallel_for(parts, [&](int p, int np) {
-        const int64_t b = (groups * p / np) * 64, e = std::min<int64_t>(m, (groups * (p + 1) / np) * 64);
+        int64_t b = (groups * p / np) * 64;
+        const int64_t e = std::min<int64_t>(m, (groups * (p + 1) / np) * 64);
         uint64_t *out = dst + (b / 64) * bits;  // 64 pairs = `bits` words
         uint64_t seen = 0, acc = 0;
+        if (contiguous && e - b >= 64) {  // whole groups: the unrolled form
+            const int64_t ng = (e - b) / 64;
+            seen = fast(src + 2 * b, ng, out);
+            out += ng * bits;
+            b += ng * 64;
+        }
         int fill = 0;
         const int64_t *q = src + b * s0;
-        for (int64_t i = b; i < e; ++i, q += s0) {
+        for (int64_t i = b; i < e; ++i, q += s0) {  // strided input, and the last partial group
             const uint64_t x = uint64_t(q[0]), y = uint64_t(q[s1]);
             seen |= x | y;
             const uint64_t v = (x | (y << w)) & ((uint64_t(1) << bits) - 1);
@@ -192,11 +243,7 @@ uint64_t st_pack_pairs_bits(const int64_t *src, int64_t s0, int64_t s1, int64_t 
             fill += bits;
             if (fill >= 64) {
                 fill -= 64;
-#if defined(__SSE2__) && defined(__x86_64__)
-                _mm_stream_si64(reinterpret_cast<long long *>(out++), (long long)acc);
-#else
-                *out++ = acc;
-#endif
+                st_stream_u64(out++, acc);
                 acc = fill ? v >> (bits - fill) : 0;
             }
         }

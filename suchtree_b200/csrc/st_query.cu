@@ -545,13 +545,17 @@ static int host_pairs_run(const st_tree *t, const int64_t *pairs, int64_t s0, in
     // bandwidth wants them left alone (packing costs a CPU read of the ids plus the staging write and
     // its DMA read on top of what the DMA of the results moves): pack a fraction of every chunk and
     // ship the rest as int64.  One GPU, 1e8 pairs, fraction 0 / 0.3 / 0.45 / 0.6 / 0.8 / 1:
-    // 3.14 / 3.91 / 4.36 / 4.76 / 4.48 / 3.96e9 pairs/s (profiles/r02_packfrac_bits.json; with the
-    // int32 packing of earlier rounds the curve was flat at 3.7-3.8e9).  With several ranks on one
+    // 3.14 / 3.91 / 4.30 / 4.64 / 4.67 / 4.18e9 pairs/s, 0.7: 4.90e9 (profiles/r02_packfrac_bits*.json;
+    // with the int32 packing of earlier rounds the curve was flat at 3.7-3.8e9).  With several ranks on one
     // host (one process per GPU) the host memory system is the shared bottleneck and plain DMA wins
     // (8-GPU box, int32 packing: 6.3e9 at 0 % vs 5.4e9 at 45 %).
-    double pack_fraction = 0.6;
-    if (const char *e = getenv("LOCAL_WORLD_SIZE"))
-        if (atoi(e) > 1) pack_fraction = 0.0;
+    double pack_fraction = 0.7;
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) {
+        // two ranks, fraction 0 / 0.2 / 0.4 / 0.6: 6.10 / 6.35 / 6.12 / 5.75e9 pairs/s in total
+        const int lw = atoi(e);
+        if (lw == 2) pack_fraction = 0.2;
+        else if (lw > 2) pack_fraction = 0.0;
+    }
     if (const char *e = getenv("SUCHTREE_B200_PACK_FRACTION")) pack_fraction = std::min(1.0, std::max(0.0, atof(e)));
     const bool hybrid = pack && pack_fraction < 1.0 && in_pinned;
     int rc = st_lane_ensure_stage(lane, n, pack, !out_pinned);
