@@ -149,3 +149,31 @@ def test_concurrent_host_calls_from_threads(tree):
     for (tr, orc, p), (d, m) in zip(jobs, results):
         want_d, want_m = orc.distances_f64_climb(p, with_mrca=True)
         assert np.array_equal(d, want_d) and np.array_equal(m, want_m)
+
+
+@pytest.mark.parametrize("kind", ["wide", "tables", "compact_small_blocks", "caterpillar", "three_nodes"])
+def test_bit_packed_stream_on_every_layout_and_id_width(kind):
+    """The chunked host pipeline ships ids as a 2 x ceil(log2 n_nodes)-bit stream that the pair
+    kernel decodes; every index layout has its own instantiation of that kernel, and the width
+    runs from 2 bits (a 3-node tree) up.  Distances and MRCA ids against the oracle, ragged
+    counts (whole groups of 64 pairs, a partial last word, the odd last pair)."""
+    if kind == "three_nodes":
+        ft = synth.yule_tree(2, seed=1)
+    elif kind == "caterpillar":
+        ft = synth.caterpillar_tree(70000, seed=2)
+    else:
+        ft = synth.yule_tree(20000, seed=13)
+    ot = O.OracleTree(ft.parent, ft.distance)
+    env = {"tables": {"SUCHTREE_B200_LAYOUT": "tables"}}.get(kind, {})
+    os.environ.update(env)
+    try:
+        T = SuchTree.from_flat(ft, _wide=True) if kind == "wide" else (
+            SuchTree.from_flat(ft, _block_shift=3) if kind == "compact_small_blocks" else SuchTree.from_flat(ft))
+    finally:
+        for k in env:
+            del os.environ[k]
+    for n in (300_001, 262_145 + 63, 1 << 19):
+        p = _pairs(ft, n, n % 1000)
+        want, wm = ot.distances_f64_climb(p, with_mrca=True)
+        assert np.array_equal(T.distances_bulk(p), want), (kind, n)
+        assert np.array_equal(T.common_ancestors_bulk(p), wm), (kind, n)
