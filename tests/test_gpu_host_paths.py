@@ -160,7 +160,7 @@ def test_bit_packed_stream_on_every_layout_and_id_width(kind):
     if kind == "three_nodes":
         ft = synth.yule_tree(2, seed=1)
     elif kind == "caterpillar":
-        ft = synth.caterpillar_tree(70000, seed=2)
+        ft = synth.caterpillar_tree(6000, seed=2)
     else:
         ft = synth.yule_tree(20000, seed=13)
     ot = O.OracleTree(ft.parent, ft.distance)
