@@ -499,7 +499,10 @@ def run_ours(args):
                 "every id packed -- what PCIe alone would allow if packing cost the host nothing",
     }
     # the other end of the bracket: H2D of fully bit-packed ids || D2H of the results
-    id_bits = max(1, int(T.size - 1).bit_length())
+    _pf, _ib = C.c_double(0), C.c_int(0)
+    _lib.check(_lib.lib().st_host_route_info(T._handle, C.byref(_pf), C.byref(_ib)))
+    route_frac, route_bits = (float(_pf.value) if in_registered else 1.0), int(_ib.value)
+    id_bits = route_bits
     sec2 = C.c_double(0)
     barrier()
     rc_copy2 = _lib.lib().st_bench_copy(local, (2 * id_bits * n_e2e + 7) // 8, 8 * n_e2e, 64 << 20, 5, C.byref(sec2))
@@ -562,6 +565,8 @@ def run_ours(args):
         "cpu_baseline": cpu_baseline,
         "e2e": {
             "value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n_e2e, "d2h_bytes_per_step": 8 * n_e2e,
+            "h2d_bytes_over_pcie_per_step": int(n_e2e * (route_frac * 2 * route_bits / 8.0 + (1.0 - route_frac) * 16)),
+            "pack_fraction": route_frac, "id_bits": route_bits,
             "pairs_per_step_per_gpu": n_e2e, "steps": args.steps, "matches_device_path": e2e_ok,
             "call": "r = SuchTree.distances_bulk(pairs): pairs = ordinary numpy int64 (n,2) array (the same "
                     "array every step), r = fresh numpy float64 (n,) -- the reference's signature, "

@@ -266,6 +266,9 @@ ST_API int st_bench_pack(int64_t n_pairs, int iters, double *pairs_per_s);
  * kernel reads -- pair i in bits [i * 2w, (i + 1) * 2w), a in the low w = id_bits bits, b above --
  * with the host thread pool.  out: ceil(n * 2w / 64) + 1 words.  *or_of_ids = OR of every id seen
  * (a bit at or above w set <=> some id is negative or >= 2^w). */
+/* what the chunked host pipeline does with a page-locked input of this tree in this process: the
+ * fraction of every chunk it bit-packs (the rest is DMA'd as int64) and the id width of the stream. */
+ST_API int st_host_route_info(const st_tree *t, double *pack_fraction, int *id_bits);
 ST_API int st_host_pack_pairs(const int64_t *pairs, int64_t stride0, int64_t stride1, int64_t n, int id_bits,
                        uint64_t *out, uint64_t *or_of_ids);
 

@@ -87,6 +87,7 @@ SIGNATURES = {
     "st_moments_pearson": (C.c_double, [C.POINTER(Moments)]),
     "st_pearson": (_int, [_int, _vp, _vp, _i64, C.POINTER(C.c_double)]),
     "st_bench_pack": (_int, [_i64, _int, C.POINTER(C.c_double)]),
+    "st_host_route_info": (_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "st_host_pack_pairs": (_int, [_vp, _i64, _i64, _i64, _int, _vp, C.POINTER(C.c_uint64)]),
     "st_bench_copy": (_int, [_int, _i64, _i64, _i64, _int, C.POINTER(C.c_double)]),
     "st_host_alloc": (_int, [_i64, C.POINTER(_vp)]),

@@ -504,6 +504,20 @@ static int host_pairs_small(const st_tree *t, HostLane *lane, const int64_t *pai
     return ST_OK;
 }
 
+// fraction of every chunk of a page-locked input whose ids are bit-packed by the host (the rest is
+// DMA'd as int64); see host_pairs_run
+static double st_default_pack_fraction() {
+    double pack_fraction = 0.7;
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) {
+        // two ranks, fraction 0 / 0.2 / 0.4 / 0.6: 6.10 / 6.35 / 6.12 / 5.75e9 pairs/s in total
+        const int lw = atoi(e);
+        if (lw == 2) pack_fraction = 0.2;
+        else if (lw > 2) pack_fraction = 0.0;
+    }
+    if (const char *e = getenv("SUCHTREE_B200_PACK_FRACTION")) pack_fraction = std::min(1.0, std::max(0.0, atof(e)));
+    return pack_fraction;
+}
+
 // Pairs per chunk of the pipeline: the staging slot for long calls; a mid-size call is cut
 // into several chunks so that packing, the two copy directions and the kernel overlap within it
 // (SUCHTREE_B200_CHUNK_PAIRS overrides: experiments).
@@ -549,14 +563,7 @@ static int host_pairs_run(const st_tree *t, const int64_t *pairs, int64_t s0, in
     // with the int32 packing of earlier rounds the curve was flat at 3.7-3.8e9).  With several ranks on one
     // host (one process per GPU) the host memory system is the shared bottleneck and plain DMA wins
     // (8-GPU box, int32 packing: 6.3e9 at 0 % vs 5.4e9 at 45 %).
-    double pack_fraction = 0.7;
-    if (const char *e = getenv("LOCAL_WORLD_SIZE")) {
-        // two ranks, fraction 0 / 0.2 / 0.4 / 0.6: 6.10 / 6.35 / 6.12 / 5.75e9 pairs/s in total
-        const int lw = atoi(e);
-        if (lw == 2) pack_fraction = 0.2;
-        else if (lw > 2) pack_fraction = 0.0;
-    }
-    if (const char *e = getenv("SUCHTREE_B200_PACK_FRACTION")) pack_fraction = std::min(1.0, std::max(0.0, atof(e)));
+    const double pack_fraction = st_default_pack_fraction();
     const bool hybrid = pack && pack_fraction < 1.0 && in_pinned;
     int rc = st_lane_ensure_stage(lane, n, pack, !out_pinned);
     if (rc != ST_OK) return rc;
@@ -675,6 +682,13 @@ extern "C" int st_bench_pack(int64_t n_pairs, int iters, double *pairs_per_s) {
     cudaFreeHost(src);
     cudaFreeHost(dst);
     *pairs_per_s = (acc >> 31) ? 0.0 : double(n_pairs) * iters / dt;
+    return ST_OK;
+}
+
+extern "C" int st_host_route_info(const st_tree *t, double *pack_fraction, int *id_bits) {
+    if (!t) return ST_ERR_INVALID_ARG;
+    if (pack_fraction) *pack_fraction = st_default_pack_fraction();
+    if (id_bits) *id_bits = t->view.id_bits;
     return ST_OK;
 }
 
