@@ -258,7 +258,8 @@ ST_API double st_moments_pearson(const st_moments *m);
 ST_API int st_pearson(int device, const double *x, const double *y, int64_t n, double *r);
 
 /* ---- measurement helper: rate (pairs/s) at which the host thread pool packs int64
- * id pairs into int32 pinned staging -- the host stage of st_distances(). */
+ * id pairs into int32 pinned staging -- the host stage of medium-size calls and of
+ * st_quartet_topologies() (long st_distances() / st_mrca() calls use the bit stream below). */
 ST_API int st_bench_pack(int64_t n_pairs, int iters, double *pairs_per_s);
 
 /* ---- the host stage of st_distances() / st_mrca() on its own (tests, measurements; no device):

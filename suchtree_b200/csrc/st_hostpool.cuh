@@ -1,5 +1,6 @@
 // Small persistent host thread pool for the drop-in (host-buffer) entry points:
-// packs the caller's int64 id arrays into int32 pinned staging (half the PCIe
+// packs the caller's int64 id arrays into pinned staging (a bit stream of 2 x id_bits per pair
+// for the chunked pair pipeline, int32 for medium-size calls and quartets: a fraction of the PCIe
 // bytes) and copies results out of pinned staging, in parallel, while the GPU
 // works on the previous chunk.
 #pragma once

@@ -596,7 +596,7 @@ static int host_pairs_run(const st_tree *t, const int64_t *pairs, int64_t s0, in
         const int64_t *src = pairs + done * s0;
         double *dd_out = out_d ? static_cast<double *>(lane->d_out[s]) : nullptr;
         int32_t *dm_out = out_m ? static_cast<int32_t *>(lane->d_out2[s]) : nullptr;
-        // first mp pairs: packed to int32 by the host pool; the rest (hybrid mode, pinned
+        // first mp pairs: bit-packed by the host pool; the rest (hybrid mode, pinned
         // contiguous input): DMA'd as int64 while the pool packs
         const int64_t mp = pack ? (hybrid ? (int64_t(double(m) * pack_fraction) & ~int64_t(3)) : m) : 0;
         char *d_in = static_cast<char *>(lane->d_in[s]);

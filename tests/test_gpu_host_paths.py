@@ -1,5 +1,5 @@
 """The host-buffer entry points (what the drop-in Python call uses) across their
-internal routes: the small-call zero-copy path, the packed (int32 staging) path, the
+internal routes: the small-call zero-copy path, the packed (bit-stream staging) path, the
 hybrid packed/direct split for pinned input, pageable vs pinned results, strided input,
 chunk boundaries, and the range errors each route must report like the reference
 (MuchTree.pyx:897-903)."""
@@ -36,7 +36,7 @@ def test_small_and_medium_calls_match_oracle(tree, n):
 
 def test_multi_chunk_pageable_pinned_and_hybrid_agree(tree):
     """2 chunks + a ragged tail through every combination of pageable / pinned input and
-    output; pinned contiguous input takes the hybrid split (part int32-packed, part int64)."""
+    output; pinned contiguous input takes the hybrid split (part bit-packed, part int64)."""
     import torch
 
     T, ot, ft = tree
