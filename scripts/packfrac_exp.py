@@ -11,7 +11,7 @@ for leaves, name in ((100_000, "yule100k"),):
     n = 100_000_000
     P = 2 * np.random.default_rng(0).integers(0, leaves, size=(n, 2))
     ref = T.distances_bulk(P); T.distances_bulk(P)
-    for frac in ("0.45", "0.55", "0.6", "0.65", "0.7", "0.8", "1.0"):
+    for frac in ("0.0", "0.3", "0.45", "0.6", "0.7", "0.8", "1.0"):
         os.environ["SUCHTREE_B200_PACK_FRACTION"] = frac
         r = T.distances_bulk(P)
         ts = []
