@@ -254,7 +254,8 @@ ST_API int st_clade_moments(const st_tree *tree_a, const st_tree *tree_b, const 
  * the reference's formula (MuchTree.pyx:79) on centred sums. */
 ST_API double st_moments_pearson(const st_moments *m);
 
-/* ---- pearson(): replaces _pearson (MuchTree.pyx:62-79); x, y HOST double[n]. */
+/* ---- pearson(): replaces _pearson (MuchTree.pyx:62-79); x, y HOST double[n], pageable or
+ * page-locked; streamed to the device in chunks, fp64 shifted moments, fixed-order fold. */
 ST_API int st_pearson(int device, const double *x, const double *y, int64_t n, double *r);
 
 /* ---- measurement helper: rate (pairs/s) at which the host thread pool packs int64

@@ -23,9 +23,10 @@ _UINT64_MAX = np.iinfo(np.uint64).max
 
 
 def pearson(x, y, device=None):
-    """Pearson correlation of two float64 vectors; MuchTree.pyx:81-87 (two-pass
-    formula of :62-79 with fp64 accumulators on the GPU).  device: default LOCAL_RANK
-    (one process per GPU), like SuchTree."""
+    """Pearson correlation of two float64 vectors; MuchTree.pyx:81-87 (the formula of :62-79
+    with fp64 accumulators on the GPU: the vectors are streamed to the device in chunks and
+    folded into shifted moments in one pass).  device: default LOCAL_RANK (one process per
+    GPU), like SuchTree."""
     if device is None:
         device = int(os.environ.get("LOCAL_RANK", "0"))
     x = _as_f64_vector(x)
