@@ -534,11 +534,16 @@ extern "C" int st_distance_matrix(const st_tree *t, const int64_t *ids, int64_t 
     if (ids) {
         int64_t *d_ids64 = nullptr;
         int *d_flag = nullptr;
-        ST_CUDA(cudaMalloc(&d_ids, size_t(n) * 4));
-        if (cudaMalloc(&d_ids64, size_t(n) * 8) != cudaSuccess || cudaMalloc(&d_flag, 4) != cudaSuccess) {
-            cudaFree(d_ids);
-            cudaFree(d_ids64);
-            st_set_error("st_distance_matrix: cudaMalloc failed");
+        // stream-ordered scratch (recycled by the pool: a cudaMalloc / cudaFree pair costs more than a
+        // small matrix does, and cudaFree synchronises the whole device)
+        if (cudaMallocAsync(reinterpret_cast<void **>(&d_ids), size_t(n) * 4, s) != cudaSuccess ||
+            cudaMallocAsync(reinterpret_cast<void **>(&d_ids64), size_t(n) * 8, s) != cudaSuccess ||
+            cudaMallocAsync(reinterpret_cast<void **>(&d_flag), 4, s) != cudaSuccess) {
+            cudaGetLastError();
+            if (d_ids) cudaFreeAsync(d_ids, s);
+            if (d_ids64) cudaFreeAsync(d_ids64, s);
+            cudaStreamSynchronize(s);
+            st_set_error("st_distance_matrix: device allocation failed");
             return ST_ERR_NOMEM;
         }
         cudaMemcpyAsync(d_ids64, ids, size_t(n) * 8, cudaMemcpyHostToDevice, s);
@@ -550,15 +555,15 @@ extern "C" int st_distance_matrix(const st_tree *t, const int64_t *ids, int64_t 
         unsigned long long mxb = 0;
         long long mnb = 0;
         rc = st_lane_read_status(lane, s, &mxb, &mnb);  // synchronises s
-        cudaFree(d_ids64);
-        cudaFree(d_flag);
+        cudaFreeAsync(d_ids64, s);
+        cudaFreeAsync(d_flag, s);
         if (rc == ST_OK && (mxb != 0 || mnb != 0)) {
             st_set_bad_node(mxb != 0 ? (int64_t)mxb : (int64_t)mnb);
             st_set_error("node id %lld out of bounds (tree size %lld)", (long long)st_bad_node(), (long long)t->n_nodes);
             rc = ST_ERR_NODE_RANGE;
         }
         if (rc != ST_OK) {
-            cudaFree(d_ids);
+            cudaFreeAsync(d_ids, s);
             return rc;
         }
         sorted = !unsorted;
@@ -566,8 +571,8 @@ extern "C" int st_distance_matrix(const st_tree *t, const int64_t *ids, int64_t 
 
     if (out_on_device) {
         rc = launch_matrix(t, d_ids, sorted, n, row_begin, row_end, out, s);
-        cudaStreamSynchronize(s);  // d_ids is freed below
-        cudaFree(d_ids);
+        if (d_ids) cudaFreeAsync(d_ids, s);  // ordered after the kernels on s
+        cudaStreamSynchronize(s);
         return rc;
     }
 
@@ -585,7 +590,7 @@ extern "C" int st_distance_matrix(const st_tree *t, const int64_t *ids, int64_t 
             cudaGetLastError();
             if (d_band[0]) cudaFreeAsync(d_band[0], lane->streams[0]);
             cudaStreamSynchronize(lane->streams[0]);
-            cudaFree(d_ids);
+            if (d_ids) cudaFreeAsync(d_ids, s);
             st_set_error("st_distance_matrix: device allocation of a %lld-row band failed", (long long)band_rows);
             return ST_ERR_NOMEM;
         }
@@ -613,6 +618,6 @@ extern "C" int st_distance_matrix(const st_tree *t, const int64_t *ids, int64_t 
             rc = ST_ERR_CUDA;
         }
     }
-    cudaFree(d_ids);
+    if (d_ids) cudaFreeAsync(d_ids, s);  // both streams have been synchronised: nothing reads it any more
     return rc;
 }
